@@ -1,0 +1,131 @@
+/* nnmpc.h — C ABI of libnnmpc.so: the B200 (sm_100a) linear-MPC / structured-NN hot path.
+ *
+ * The reference (pratyushkumar211/industrial_nnmpc_2021) is pure Python and has no FFI; its
+ * boundary for this path is the Python object API of lib/linearMPC.py and lib/LinearMPCLayers.py.
+ * Each entry point below names the reference method it replaces (file:line in /root/reference).
+ * The Python drop-ins in industrial_nnmpc_2021_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *  - all matrices are float64, row-major, contiguous unless a stride is named;
+ *  - "host" pointers are ordinary CPU memory, "dev" pointers are CUDA device memory on the
+ *    handle's device (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t (NULL = default);
+ *  - every function returns 0 on success, a negative nnmpc_status on error (message through
+ *    nnmpc_last_error(), thread-local) and NNMPC_WARN_MAXITER (>0) when some sample hit max_iter;
+ *  - the caller owns every buffer it passes; handles own only the replicated operators and
+ *    scratch, released by *_destroy.  Handles are immutable after create; one device per handle.
+ */
+#ifndef NNMPC_H
+#define NNMPC_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NNMPC_OK = 0,
+  NNMPC_WARN_MAXITER = 1,
+  NNMPC_ERR_BADARG = -1,
+  NNMPC_ERR_CUDA = -2,
+  NNMPC_ERR_NOMEM = -3,
+  NNMPC_ERR_UNSUPPORTED = -4
+} nnmpc_status;
+
+typedef struct nnmpc_qp nnmpc_qp_t;    /* condensed regulator QP operators + solver scratch */
+typedef struct nnmpc_ts nnmpc_ts_t;    /* target-selector operators */
+typedef struct nnmpc_sim nnmpc_sim_t;  /* closed-loop offline data generator */
+typedef struct nnmpc_mlp nnmpc_mlp_t;  /* structured-network weights */
+
+int nnmpc_version(void);
+const char* nnmpc_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long nnmpc_launch_count(void);
+/* sum over all solved samples of the Douglas-Rachford iterations they used (for flop accounting) */
+long long nnmpc_iteration_count(void);
+
+/* ---- regulator QP:  DenseQPRegulator (lib/linearMPC.py:321-517) -------------------------------
+ *   min_u 1/2 u'Pu + (tq x0)'u   s.t.  lb <= u_k <= ub  for every stage k     (box path, :481)
+ * Operators (host, uploaded once; built by industrial_nnmpc_2021_b200.condense):
+ *   P     n x n      Hessian (:472)                       tq    n x nxa   linear-term map (:473)
+ *   Top   n x n      (P + diag(rho))^-1 diag(rho)          Mtq   n x nxa   (P + diag(rho))^-1 tq
+ *   Kunc  n x nxa    -P^-1 tq  (unconstrained law; equals the LQR sequence, :356)
+ *   n = N*nu must be even, nxa even (pad with a zero column otherwise). */
+int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N,
+                    const double* P_host, const double* tq_host, const double* Top_host,
+                    const double* Mtq_host, const double* Kunc_host, double alpha, int device);
+int nnmpc_qp_destroy(nnmpc_qp_t* h);
+
+/* Batched solve; replaces one DenseQPRegulator.solve(x0) per sample (:495-512) with the bounds
+ * mutation of LinearMPCController.get_control_sequence (:685-686) passed per sample instead.
+ *   x0     dev B x nxa   deviation state [x-xs; uprev-us] (:688)
+ *   lb,ub  dev B x nu    per-sample stage bounds ulb-us, uub-us
+ *   u      dev B x n     out: minimiser (deviation variables; caller adds us, :689)
+ *   v_state dev B x n    in/out Douglas-Rachford state for warm starts, or NULL;  warm != 0 uses it
+ *   cost,kkt dev B       out (nullable): optimal value 1/2u'Pu+q'u and ||u-clip(u-(Pu+q))||_inf
+ *   iters  dev B int     out (nullable): iterations used per sample
+ * Stops each sample when its true KKT residual (evaluated with P in FP64) <= tol. */
+int nnmpc_qp_solve(nnmpc_qp_t* h, int B, const double* x0, const double* lb, const double* ub,
+                   double* u, double* v_state, int warm, double* cost, double* kkt, int* iters,
+                   double tol, int max_iter, void* stream);
+/* Same with HOST buffers (copies in/out inside the call); the end-to-end entry point. */
+int nnmpc_qp_solve_host(nnmpc_qp_t* h, int B, const double* x0, const double* lb, const double* ub,
+                        double* u, double* cost, double* kkt, int* iters, double tol, int max_iter);
+
+/* ---- target selector:  TargetSelector.solve (lib/linearMPC.py:298-311), H empty, A stable ------
+ * Reduced exactly to the nu-dim box QP  min 1/2 us'Ht us + (Fy ysp + Fd d + f0)'us,
+ * xs = Gx us + Gd d  (Gx = (I-A)^-1 B, Gd = (I-A)^-1 Bd).  nu <= 32. */
+int nnmpc_ts_create(nnmpc_ts_t** out, int nx, int nu, int ny, int nd, const double* Ht_host,
+                    const double* Fy_host, const double* Fd_host, const double* f0_host,
+                    const double* Gx_host, const double* Gd_host, const double* ulb_host,
+                    const double* uub_host, int device);
+int nnmpc_ts_destroy(nnmpc_ts_t* h);
+/* ysp: dev B rows of ny doubles, row stride ysp_stride (doubles); d likewise. */
+int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride, const double* d,
+                   long long d_stride, double* xs, double* us, int* iters, void* stream);
+int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d, double* xs,
+                        double* us, int* iters);
+
+/* ---- closed-loop offline data generation: simulate_offline (lib/linearMPC.py:827-880) ---------
+ * B independent trajectories (the reference's processes, :786-825) advanced T steps together:
+ * target selector -> regulator QP (warm started) -> u = useq[0:nu] -> x+ = Ax + Bu + Bd d.
+ *   ABd    host nx x (nx+nu+nd): [A | B | Bd]
+ * Inputs  setpoints dev [B][T][ny], disturbances dev [B][T][nd]  (chunk-major, as _split_scenarios)
+ * Outputs x,xs dev [B][T][nx]; uprev,us,u dev [B][T][nu]  (row t = state BEFORE step t, :868-872)
+ *         iters dev [B][T] int, kkt dev [B][T] (nullable)
+ *   x_io, uprev_io dev B x nx / B x nu: in = initial state (:837-838), out = state after T steps */
+int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, int nu, int nd,
+                     int ny, const double* ABd_host, int device);
+int nnmpc_sim_destroy(nnmpc_sim_t* h);
+int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
+                  const double* setpoints, const double* disturbances, double* x, double* uprev,
+                  double* xs, double* us, double* u, int* iters, double* kkt, double tol,
+                  int max_iter, void* stream);
+int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
+                       const double* setpoints, const double* disturbances, double* x, double* uprev,
+                       double* xs, double* us, double* u, int* iters, double* kkt, double tol,
+                       int max_iter);
+
+/* ---- structured network: RegulatorLayerWithUprev / WithoutUprev (lib/LinearMPCLayers.py:15-115)
+ * and its NumPy deployment form NeuralNetworkController (lib/controller_evaluation.py:863-892).
+ *   u = us + f(x,[uprev],xs,us) - f(xs,[us],xs,us),  f = (Dense+ReLU) x (L-1), Dense(no bias)
+ * weights: Keras get_weights() order [W1,b1,...,W_{L-1},b_{L-1},Wout], W_i (in_i x out_i) row-major;
+ * dims[0..L] = layer widths with dims[0] = input width (2nx+2nu or 2nx+nu), dims[L] = nu. */
+int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_layers,
+                     const int* dims, const double* const* weights_host,
+                     const double* const* biases_host, int device);
+int nnmpc_mlp_destroy(nnmpc_mlp_t* h);
+/* x,xs dev B x nx; uprev,us dev B x nu (uprev ignored when !with_uprev); out dev B x nu.
+ * xscale dev nx or NULL (x/xscale, xs/xscale, :863-866); ulb/uub dev nu or NULL (clip, :888-892). */
+int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev,
+                      const double* xs, const double* us, const double* xscale, const double* ulb,
+                      const double* uub, double* out, void* stream);
+int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev,
+                           const double* xs, const double* us, const double* xscale,
+                           const double* ulb, const double* uub, double* out);
+
+/* ---- self test: C = A * Bt^T through the same GEMM kernel (used by tests) ---------------------- */
+int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,
+                  long long ldb, double* C, long long ldc, const int* rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNMPC_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of csrc/libnnmpc.so (the C ABI declared in include/nnmpc.h).
+
+The library is built in-tree by ``industrial_nnmpc_2021_b200.build``.  There is no CPU
+fallback: ``lib()`` raises when the shared object is missing and every ``*_create`` call fails
+when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libnnmpc.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+vp = C.c_void_p
+
+# symbol -> (restype, argtypes); must list every function declared in include/nnmpc.h
+SIGNATURES = {
+    "nnmpc_version": (C.c_int, []),
+    "nnmpc_last_error": (C.c_char_p, []),
+    "nnmpc_launch_count": (C.c_longlong, []),
+    "nnmpc_iteration_count": (C.c_longlong, []),
+    "nnmpc_qp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
+                                  C.c_double, C.c_int]),
+    "nnmpc_qp_destroy": (C.c_int, [vp]),
+    "nnmpc_qp_solve": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_int, vp]),
+    "nnmpc_qp_solve_host": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int]),
+    "nnmpc_ts_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                  vp, C.c_int]),
+    "nnmpc_ts_destroy": (C.c_int, [vp]),
+    "nnmpc_ts_solve": (C.c_int, [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp, vp, vp, vp]),
+    "nnmpc_ts_solve_host": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "nnmpc_sim_create": (C.c_int, [C.POINTER(vp), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
+    "nnmpc_sim_destroy": (C.c_int, [vp]),
+    "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
+                                C.c_int, vp]),
+    "nnmpc_sim_run_host": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
+                                     C.c_int]),
+    "nnmpc_mlp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(vp),
+                                   C.POINTER(vp), C.c_int]),
+    "nnmpc_mlp_destroy": (C.c_int, [vp]),
+    "nnmpc_mlp_forward": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nnmpc_mlp_forward_host": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nnmpc_gemm_tn": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong,
+                                vp, vp]),
+}
+
+NNMPC_WARN_MAXITER = 1
+_lib = None
+
+
+class NnmpcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libnnmpc.so (once).  Raises if it has not been built - there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NnmpcError(
+            f"{LIB_PATH} is missing: build it with `python -m industrial_nnmpc_2021_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU fallback.")
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    """Raise on a negative status; return True when the call only warned (max_iter reached)."""
+    if rc < 0:
+        msg = lib().nnmpc_last_error().decode(errors="replace")
+        raise NnmpcError(f"{what} failed (status {rc}): {msg}")
+    return rc == NNMPC_WARN_MAXITER
+
+
+def host(a):
+    """C-contiguous float64 view/copy of a host array."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def hptr(a):
+    """void* of a contiguous NumPy array (or None)."""
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def dptr(t):
+    """void* of a contiguous CUDA torch tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise NnmpcError("expected a contiguous CUDA tensor")
+    return vp(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return vp(torch.cuda.current_stream().cuda_stream)

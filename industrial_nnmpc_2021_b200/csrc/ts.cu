@@ -1,0 +1,298 @@
+// Batched steady-state target selector, one warp per sample.
+//
+// Replaces TargetSelector.solve (/root/reference/lib/linearMPC.py:298-311), which calls cvxopt on
+//     min_(xs,us) 1/2|us-usp|^2_Rs + 1/2|C xs + Cd d - ysp|^2_Qs
+//     s.t. (I-A) xs - B us = Bd d ,  ulb <= us <= uub                 (:182-187, H empty)
+// With A open-loop stable the equality eliminates xs = Gx us + Gd d and leaves an nu-dimensional
+// strictly convex box QP,  min 1/2 us'Ht us + f'us,  f = Fy ysp + Fd d + f0  (operators built on
+// the host, see linearMPC.TargetSelector).  nu <= 32, so lane i of a warp owns variable i and the
+// QP is solved EXACTLY by a primal active-set method: equality-constrained solves through a
+// Cholesky factorisation of the masked Hessian held in shared memory, ratio test with warp
+// reductions, multiplier sign check.  (The CDU tuning makes Ht ill-conditioned - Rs = 1e-6 I,
+// cdu_parameters.py:94 - so a first-order method is not an option here.)
+#include "ts.cuh"
+
+namespace nnmpc {
+
+constexpr int TS_WARPS = 4;
+constexpr int TS_LD = 33;
+#define FULLMASK 0xffffffffu
+
+struct TsParams {
+  int B, nx, nu, ny, nd;
+  const double *Ht, *Fy, *Fd, *f0, *Gx, *Gd, *ulb, *uub;
+  const double* ysp; long long ysp_stride;
+  const double* d;   long long d_stride;
+  double* xs; long long xs_stride;
+  double* us; long long us_stride;
+  int* iters; long long iters_stride;
+  int fused;
+  TsFused f;
+};
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
+  __shared__ double Hs[32 * TS_LD];
+  __shared__ double Sw[TS_WARPS][32 * TS_LD];
+  __shared__ double uw[TS_WARPS][32];
+  const int nu = p.nu, nx = p.nx, ny = p.ny, nd = p.nd;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) Hs[(i / nu) * TS_LD + (i % nu)] = p.Ht[i];
+  __syncthreads();
+  double* S = Sw[warp];
+  double* uvec = uw[warp];
+  const bool act = lane < nu;
+  const double lo = act ? p.ulb[lane] : 0.0;
+  const double hi = act ? p.uub[lane] : 0.0;
+  const int maxit = 10 * nu + 20;
+
+  for (int b = blockIdx.x * TS_WARPS + warp; b < p.B; b += gridDim.x * TS_WARPS) {
+    const double* ysp = p.ysp + (long long)b * p.ysp_stride;
+    const double* dd = p.d + (long long)b * p.d_stride;
+    double f = 0.0;
+    if (act) {
+      f = p.f0[lane];
+      const double* fy = p.Fy + (long long)lane * ny;
+      for (int y = 0; y < ny; ++y) f += fy[y] * ysp[y];
+      const double* fd = p.Fd + (long long)lane * nd;
+      for (int k = 0; k < nd; ++k) f += fd[k] * dd[k];
+    }
+    double u = act ? fmin(fmax(0.0, lo), hi) : 0.0;
+    int st = 2;  // 0 free, -1 at lower, +1 at upper, 2 padding lane / degenerate (never released)
+    if (act) st = (hi <= lo) ? 2 : (u <= lo ? -1 : (u >= hi ? 1 : 0));
+    int it = 0;
+    bool done = false;
+    for (; it < maxit && !done; ++it) {
+      uvec[lane] = u;
+      __syncwarp();
+      const unsigned fixedmask = __ballot_sync(FULLMASK, st != 0);
+      double rhs;
+      if (act) {
+        if (st != 0) {
+          rhs = u;
+          for (int j = 0; j <= lane; ++j) S[lane * TS_LD + j] = (j == lane) ? 1.0 : 0.0;
+        } else {
+          rhs = -f;
+          for (int j = 0; j < nu; ++j) {
+            const double hij = Hs[lane * TS_LD + j];
+            const bool jfixed = (fixedmask >> j) & 1u;
+            if (jfixed) rhs -= hij * uvec[j];
+            if (j <= lane) S[lane * TS_LD + j] = jfixed ? 0.0 : hij;
+          }
+        }
+      } else {
+        rhs = 0.0;
+      }
+      __syncwarp();
+      // in-place lower Cholesky of the masked (block-diagonal SPD) matrix
+      for (int k = 0; k < nu; ++k) {
+        const double sd = sqrt(S[k * TS_LD + k]);
+        const double inv = 1.0 / sd;
+        double lik = 0.0;
+        if (lane > k && act) {
+          lik = S[lane * TS_LD + k] * inv;
+          S[lane * TS_LD + k] = lik;
+        }
+        __syncwarp();
+        if (lane == k) S[k * TS_LD + k] = sd;
+        for (int j = k + 1; j < nu; ++j) {
+          const double ljk = S[j * TS_LD + k];
+          if (lane >= j && act) S[lane * TS_LD + j] -= lik * ljk;
+        }
+        __syncwarp();
+      }
+      double bb = rhs;
+      for (int k = 0; k < nu; ++k) {  // L y = rhs
+        const double yk = __shfl_sync(FULLMASK, bb, k) / S[k * TS_LD + k];
+        if (lane == k) bb = yk;
+        else if (lane > k && act) bb -= S[lane * TS_LD + k] * yk;
+      }
+      for (int k = nu - 1; k >= 0; --k) {  // L' x = y
+        const double xk = __shfl_sync(FULLMASK, bb, k) / S[k * TS_LD + k];
+        if (lane == k) bb = xk;
+        else if (lane < k) bb -= S[k * TS_LD + lane] * xk;
+      }
+      const double uh = (st == 0) ? bb : u;
+      double a = 2.0;
+      if (st == 0) {
+        if (uh > hi) a = (hi - u) / (uh - u);
+        else if (uh < lo) a = (lo - u) / (uh - u);
+      }
+      double amin = warp_min_d(a);
+      if (amin >= 1.0) {
+        // full step: u is the minimiser on the current face; check multiplier signs
+        u = uh;
+        __syncwarp();
+        uvec[lane] = u;
+        __syncwarp();
+        double g = f, scale = fabs(f);
+        if (act) {
+          for (int j = 0; j < nu; ++j) {
+            const double t = Hs[lane * TS_LD + j] * uvec[j];
+            g += t;
+            scale += fabs(t);
+          }
+        }
+        double viol = 0.0;
+        if (st == 1) viol = g;         // upper bound active needs g <= 0
+        else if (st == -1) viol = -g;  // lower bound active needs g >= 0
+        if (!(viol > 1.5e-14 * scale)) viol = 0.0;
+        const double vmax = warp_max_d(viol);
+        if (vmax <= 0.0) {
+          done = true;
+        } else {
+          const unsigned who = __ballot_sync(FULLMASK, viol == vmax);
+          if (lane == __ffs(who) - 1) st = 0;
+        }
+      } else {
+        if (amin < 0.0) amin = 0.0;
+        const unsigned who = __ballot_sync(FULLMASK, a <= amin);
+        const int blk = __ffs(who) - 1;
+        if (st == 0) u += amin * (uh - u);
+        if (lane == blk) {
+          if (uh > hi) { u = hi; st = 1; }
+          else { u = lo; st = -1; }
+        }
+      }
+      __syncwarp();
+    }
+    uvec[lane] = u;
+    __syncwarp();
+    if (act) p.us[(long long)b * p.us_stride + lane] = u;
+    if (p.iters && lane == 0) p.iters[(long long)b * p.iters_stride] = it;
+    const TsFused& F = p.f;
+    for (int r = lane; r < nx; r += 32) {
+      double acc = 0.0;
+      const double* gx = p.Gx + (long long)r * nu;
+      for (int j = 0; j < nu; ++j) acc += gx[j] * uvec[j];
+      const double* gd = p.Gd + (long long)r * nd;
+      for (int k = 0; k < nd; ++k) acc += gd[k] * dd[k];
+      p.xs[(long long)b * p.xs_stride + r] = acc;
+      if (p.fused) {
+        const double xv = F.x[(long long)b * nx + r];
+        F.x0[(long long)b * F.nxa_ld + r] = xv - acc;
+        F.row_x[(long long)b * F.row_stride_x + r] = xv;
+      }
+    }
+    if (p.fused) {
+      if (act) {
+        const double up = F.uprev[(long long)b * nu + lane];
+        F.x0[(long long)b * F.nxa_ld + nx + lane] = up - u;
+        F.row_uprev[(long long)b * F.row_stride_u + lane] = up;
+        F.lb[(long long)b * nu + lane] = lo - u;
+        F.ub[(long long)b * nu + lane] = hi - u;
+        F.dus[(long long)b * nu + lane] = F.us_prev[(long long)b * nu + lane] - u;
+        F.us_prev[(long long)b * nu + lane] = u;
+      }
+      for (int c = nx + nu + lane; c < F.nxa_ld; c += 32) F.x0[(long long)b * F.nxa_ld + c] = 0.0;
+    }
+    __syncwarp();
+  }
+}
+
+int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
+                    long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
+                    int* iters, long long iters_stride, const TsFused* fused, cudaStream_t st) {
+  if (B <= 0) return 0;
+  TsParams p{};
+  p.B = B; p.nx = h->nx; p.nu = h->nu; p.ny = h->ny; p.nd = h->nd;
+  p.Ht = h->Ht; p.Fy = h->Fy; p.Fd = h->Fd; p.f0 = h->f0; p.Gx = h->Gx; p.Gd = h->Gd; p.ulb = h->ulb; p.uub = h->uub;
+  p.ysp = ysp; p.ysp_stride = ysp_stride; p.d = d; p.d_stride = d_stride;
+  p.xs = xs; p.xs_stride = xs_stride; p.us = us; p.us_stride = us_stride;
+  p.iters = iters; p.iters_stride = iters_stride;
+  p.fused = fused ? 1 : 0;
+  if (fused) p.f = *fused;
+  int blocks = (B + TS_WARPS - 1) / TS_WARPS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_target_selector<<<blocks, TS_WARPS * 32, 0, st>>>(p);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace nnmpc
+
+using namespace nnmpc;
+
+extern "C" {
+
+int nnmpc_ts_create(nnmpc_ts_t** out, int nx, int nu, int ny, int nd, const double* Ht, const double* Fy,
+                    const double* Fd, const double* f0, const double* Gx, const double* Gd, const double* ulb,
+                    const double* uub, int device) {
+  if (!out || !Ht || !Fy || !Fd || !f0 || !Gx || !Gd || !ulb || !uub)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_create: null argument");
+  if (nu < 1 || nu > 32) return set_error(NNMPC_ERR_UNSUPPORTED, "nnmpc_ts_create: nu=%d not in [1,32]", nu);
+  if (nx < 1 || ny < 1 || nd < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_create: bad sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(NNMPC_ERR_CUDA, "nnmpc_ts_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_create: bad device %d", device);
+  DeviceGuard dg(device);
+  nnmpc_ts* h = new (std::nothrow) nnmpc_ts();
+  if (!h) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+  h->nx = nx; h->nu = nu; h->ny = ny; h->nd = nd; h->device = device;
+  NNMPC_TRY(upload(&h->Ht, Ht, (size_t)nu * nu));
+  NNMPC_TRY(upload(&h->Fy, Fy, (size_t)nu * ny));
+  NNMPC_TRY(upload(&h->Fd, Fd, (size_t)nu * (nd > 0 ? nd : 1)));
+  NNMPC_TRY(upload(&h->f0, f0, (size_t)nu));
+  NNMPC_TRY(upload(&h->Gx, Gx, (size_t)nx * nu));
+  NNMPC_TRY(upload(&h->Gd, Gd, (size_t)nx * (nd > 0 ? nd : 1)));
+  NNMPC_TRY(upload(&h->ulb, ulb, (size_t)nu));
+  NNMPC_TRY(upload(&h->uub, uub, (size_t)nu));
+  *out = h;
+  return 0;
+}
+
+int nnmpc_ts_destroy(nnmpc_ts_t* h) {
+  if (!h) return 0;
+  DeviceGuard dg(h->device);
+  cudaFree(h->Ht); cudaFree(h->Fy); cudaFree(h->Fd); cudaFree(h->f0); cudaFree(h->Gx); cudaFree(h->Gd);
+  cudaFree(h->ulb); cudaFree(h->uub);
+  h->hysp.release(); h->hd.release(); h->hxs.release(); h->hus.release(); h->hiters.release();
+  delete h;
+  return 0;
+}
+
+int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride, const double* d,
+                   long long d_stride, double* xs, double* us, int* iters, void* stream) {
+  if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: null argument");
+  if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: negative batch");
+  DeviceGuard dg(h->device);
+  return ts_solve_device(h, B, ysp, ysp_stride, d, d_stride, xs, h->nx, us, h->nu, iters, 1, nullptr,
+                         (cudaStream_t)stream);
+}
+
+int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d, double* xs, double* us,
+                        int* iters) {
+  if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve_host: null argument");
+  if (B <= 0) return B == 0 ? 0 : set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve_host: negative batch");
+  DeviceGuard dg(h->device);
+  const size_t b = (size_t)B;
+  NNMPC_TRY(h->hysp.ensure(b * h->ny));
+  NNMPC_TRY(h->hd.ensure(b * (h->nd > 0 ? h->nd : 1)));
+  NNMPC_TRY(h->hxs.ensure(b * h->nx));
+  NNMPC_TRY(h->hus.ensure(b * h->nu));
+  NNMPC_TRY(h->hiters.ensure(b));
+  cudaStream_t st = 0;
+  NNMPC_CUDA(cudaMemcpyAsync(h->hysp.p, ysp, b * h->ny * 8, cudaMemcpyHostToDevice, st));
+  if (h->nd > 0) NNMPC_CUDA(cudaMemcpyAsync(h->hd.p, d, b * h->nd * 8, cudaMemcpyHostToDevice, st));
+  NNMPC_TRY(ts_solve_device(h, B, h->hysp.p, h->ny, h->hd.p, h->nd, h->hxs.p, h->nx, h->hus.p, h->nu, h->hiters.p, 1,
+                            nullptr, st));
+  NNMPC_CUDA(cudaMemcpyAsync(xs, h->hxs.p, b * h->nx * 8, cudaMemcpyDeviceToHost, st));
+  NNMPC_CUDA(cudaMemcpyAsync(us, h->hus.p, b * h->nu * 8, cudaMemcpyDeviceToHost, st));
+  if (iters) NNMPC_CUDA(cudaMemcpyAsync(iters, h->hiters.p, b * 4, cudaMemcpyDeviceToHost, st));
+  NNMPC_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Internal interface of the batched target selector (shared by ts.cu and sim.cu).
+#pragma once
+#include "nnmpc_common.cuh"
+
+struct nnmpc_ts {
+  int nx, nu, ny, nd, device;
+  double *Ht, *Fy, *Fd, *f0, *Gx, *Gd, *ulb, *uub;  // device operators
+  nnmpc::DevBuf<double> hysp, hd, hxs, hus;          // staging for the host entry point
+  nnmpc::DevBuf<int> hiters;
+};
+
+namespace nnmpc {
+
+// Optional fused outputs for the closed-loop generator: when `x` is non-null the kernel also
+// forms the regulator inputs x0 = [x-xs; uprev-us], lb = ulb-us, ub = uub-us
+// (LinearMPCController.get_control_sequence, linearMPC.py:685-688), the warm-start shift
+// dus = us_prev - us, and copies (x, uprev) into the dataset row.
+struct TsFused {
+  const double* x;        // B x nx   current state
+  const double* uprev;    // B x nu
+  double* x0;             // B x nxa_ld
+  int nxa_ld;
+  double* lb;             // B x nu
+  double* ub;             // B x nu
+  double* us_prev;        // B x nu  (in: previous target, out: this target)
+  double* dus;            // B x nu
+  double* row_x;          // dataset rows, stride row_stride_x / row_stride_u doubles between samples
+  double* row_uprev;
+  long long row_stride_x, row_stride_u;
+};
+
+int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
+                    long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
+                    int* iters, long long iters_stride, const TsFused* fused, cudaStream_t st);
+
+}  // namespace nnmpc

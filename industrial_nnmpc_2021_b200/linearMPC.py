@@ -1,0 +1,690 @@
+"""Drop-in host-side mirror of the hot path of /root/reference/lib/linearMPC.py.
+
+Same class names, constructor keywords, method signatures and return shapes as the reference;
+every QP solve and the closed-loop plant recursion run in the sm_100a kernels of
+``csrc/libnnmpc.so`` (C ABI in ``include/nnmpc.h``) instead of ``cvxopt``.  Additive batched
+entry points (``solve_batch``, ``OfflineSimulator.generate_batch``) expose the data-parallel
+form the GPU is built for.  PyTorch is used only to own device memory and streams.
+
+There is no CPU fallback: constructing a solver without the built library / a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import time
+
+import numpy as np
+import scipy.linalg
+
+from . import _lib
+from . import condense
+from .condense import dlqr, dlqe, c2d          # noqa: F401  (re-exported like the reference module)
+
+DEFAULT_TOL = 1e-9        # stop on true KKT residual ||u - clip(u - (Pu+q))||_inf <= tol
+DEFAULT_MAX_ITER = 20000
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _device_index(device):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.NnmpcError("no CUDA device visible: this package has no CPU fallback")
+    if device is None:
+        return torch.cuda.current_device()
+    return torch.device(device).index or 0
+
+
+# ------------------------------------------------------------------------------ stability helpers
+def _eigval_eigvec_test(X, Y):
+    """linearMPC.py:66-77."""
+    vals, vecs = np.linalg.eig(X)
+    for vec in vecs[:, np.abs(vals) >= 1.0].T:
+        if np.linalg.norm(Y @ vec) <= 1e-8:
+            return False
+    return True
+
+
+def assert_detectable(A, Cm):
+    assert _eigval_eigvec_test(A, Cm)
+
+
+def assert_stabilizable(A, B):
+    assert _eigval_eigvec_test(A.T, B.T)
+
+
+class LinearPlantSimulator:
+    """x+ = Ax + Bu + Bp p with measurement noise (linearMPC.py:87-131).  Host NumPy, as upstream."""
+
+    def __init__(self, *, A, B, C, Bp, Rv, sample_time, x0):
+        self.A, self.B, self.C, self.Bp = A, B, C, Bp
+        self.Nx, self.Nu, self.Ny = A.shape[0], B.shape[1], C.shape[0]
+        self.measurement_noise_std = np.sqrt(np.diag(Rv)[:, np.newaxis])
+        self.sample_time = sample_time
+        self.x, self.u, self.p = [x0], [], []
+        self.v = [self.measurement_noise_std * np.random.randn(self.Ny, 1)]
+        self.y = [self.C @ x0 + self.v[-1]]
+        self.t = [0.0]
+
+    def step(self, u, p):
+        x = self.A @ self.x[-1] + self.B @ u + self.Bp @ p
+        v = self.measurement_noise_std * np.random.randn(self.Ny, 1)
+        y = self.C @ x + v
+        for lst, val in ((self.x, x), (self.u, u), (self.p, p), (self.v, v), (self.y, y)):
+            lst.append(val)
+        self.t.append(self.t[-1] + self.sample_time)
+        return y
+
+
+class KalmanFilter:
+    """Steady-state Kalman filter (linearMPC.py:133-176); online loop only, host NumPy."""
+
+    def __init__(self, *, A, B, C, Qw, Rv, xprior):
+        self.A, self.B, self.C, self.Qw, self.Rv = A, B, C, Qw, Rv
+        self.L, _ = dlqe(A, C, Qw, Rv)
+        self.xhat, self.xhat_pred, self.y, self.uprev = [xprior], [], [], []
+
+    def solve(self, y, uprev):
+        pred = self.A @ self.xhat[-1] + self.B @ uprev
+        xhat = pred + self.L @ (y - self.C @ pred)
+        self.xhat.append(xhat)
+        self.xhat_pred.append(pred)
+        self.y.append(y)
+        self.uprev.append(uprev)
+        return xhat
+
+
+# ------------------------------------------------------------------------------ target selector
+class TargetSelector:
+    """Steady-state target problem (linearMPC.py:178-319), solved on the GPU.
+
+        min_(xs,us) |us-usp|^2_Rs + |C xs + Cd dhat - ysp|^2_Qs
+        s.t. [I-A, -B; HC, 0][xs; us] = [Bd dhat; H(ysp - Cd dhat)],  ulb <= us <= uub
+
+    Supported configuration = the one both reference examples use: ``H`` empty
+    (cstrs_parameters.py:278, cdu_parameters.py:78), no output bounds, ``A`` open-loop stable,
+    ``Nu <= 32``.  Then ``xs = Gx us + Gd dhat`` and the problem is an exactly equivalent
+    ``Nu``-dimensional box QP (see csrc/ts.cu).
+    """
+
+    def __init__(self, *, A, B, C, H, Bd, Cd, usp, Rs, Qs, ulb, uub, ylb=None, yub=None, device=None):
+        self.A, self.B, self.C, self.H, self.Bd, self.Cd, self.Rs, self.Qs = A, B, C, H, Bd, Cd, Rs, Qs
+        self.Nx, self.Nu = B.shape
+        self.Ny, self.Nd, self.Nz = C.shape[0], Bd.shape[1], H.shape[0]
+        self.usp = usp
+        self.ysp, self.dhats, self.xs, self.us = [], [], [], []
+        self.ulb, self.uub, self.ylb, self.yub = ulb, uub, ylb, yub
+        if self.Nz != 0 or ylb is not None or yub is not None:
+            raise NotImplementedError("TargetSelector on the GPU supports H empty and input bounds only "
+                                      "(the configuration of both reference examples)")
+        if np.any(np.abs(np.linalg.eigvals(A)) >= 1.0):
+            raise NotImplementedError("TargetSelector on the GPU needs (I - A) invertible with A stable")
+        self._setup_fixed_matrices()
+        self._dev = _device_index(device)
+        self._handle = None
+        self._create()
+
+    def _setup_fixed_matrices(self):
+        """Reference attribute names (linearMPC.py:229-274) + the reduced operators."""
+        nx, nu, ny = self.Nx, self.Nu, self.Ny
+        E = np.vstack([np.eye(nu), -np.eye(nu)])
+        self.F = np.vstack([np.eye(ny), -np.eye(ny)])
+        self.G = np.hstack([np.zeros((2 * nu, nx)), E])
+        self.h = np.vstack([self.uub, -self.ulb])
+        self.tA = np.block([[np.eye(nx) - self.A, -self.B], [self.H @ self.C, np.zeros((self.Nz, nu))]])
+        self.tb = np.block([[np.zeros((nx, ny)), self.Bd], [self.H, -(self.H @ self.Cd)]])
+        self.P = scipy.linalg.block_diag(self.C.T @ (self.Qs @ self.C), self.Rs)
+        ImA = np.eye(nx) - self.A
+        self.Gx = np.linalg.solve(ImA, self.B)
+        self.Gd = np.linalg.solve(ImA, self.Bd)
+        CG = self.C @ self.Gx
+        QsCG = self.Qs @ CG
+        Ht = CG.T @ QsCG + self.Rs
+        self.Ht = 0.5 * (Ht + Ht.T)
+        self.Fy = -QsCG.T                                    # d f / d ysp
+        self.Fd = QsCG.T @ (self.C @ self.Gd + self.Cd)      # d f / d dhat
+        self.f0 = -(self.Rs @ self.usp)
+
+    def _create(self):
+        L = _lib.lib()
+        hnd = C.c_void_p()
+        arrs = [_lib.host(a) for a in (self.Ht, self.Fy, self.Fd if self.Nd else np.zeros((self.Nu, 1)), self.f0,
+                                       self.Gx, self.Gd if self.Nd else np.zeros((self.Nx, 1)), self.ulb, self.uub)]
+        rc = L.nnmpc_ts_create(C.byref(hnd), self.Nx, self.Nu, self.Ny, self.Nd, *[_lib.hptr(a) for a in arrs],
+                               self._dev)
+        _lib.check(rc, "nnmpc_ts_create")
+        self._handle = hnd
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().nnmpc_ts_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_handle"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._create()
+
+    def _setup_changing_matrices(self, ysp, dhats):
+        """linearMPC.py:276-296 (kept for inspection/tests; the GPU path uses Fy, Fd, f0)."""
+        q = np.vstack([-(self.C.T @ (self.Qs @ (ysp - self.Cd @ dhats))), -(self.Rs @ self.usp)])
+        return q, self.h, self.tb @ np.vstack([ysp, dhats])
+
+    def solve_batch(self, YSP, D, return_iters=False):
+        """(B,Ny),(B,Nd) -> xs (B,Nx), us (B,Nu).  torch CUDA tensors stay on the device;
+        NumPy arrays go through the host entry point."""
+        L = _lib.lib()
+        if isinstance(YSP, np.ndarray):
+            YSP, D = _lib.host(YSP), _lib.host(D)
+            Bn = YSP.shape[0]
+            xs, us = np.empty((Bn, self.Nx)), np.empty((Bn, self.Nu))
+            it = np.empty(Bn, dtype=np.int32)
+            rc = L.nnmpc_ts_solve_host(self._handle, Bn, _lib.hptr(YSP), _lib.hptr(D), _lib.hptr(xs), _lib.hptr(us),
+                                       _lib.hptr(it))
+            _lib.check(rc, "nnmpc_ts_solve_host")
+        else:
+            torch = _torch()
+            YSP, D = YSP.contiguous(), D.contiguous()
+            Bn = YSP.shape[0]
+            xs = torch.empty((Bn, self.Nx), dtype=torch.float64, device=YSP.device)
+            us = torch.empty((Bn, self.Nu), dtype=torch.float64, device=YSP.device)
+            it = torch.empty(Bn, dtype=torch.int32, device=YSP.device)
+            rc = L.nnmpc_ts_solve(self._handle, Bn, _lib.dptr(YSP), self.Ny, _lib.dptr(D), self.Nd, _lib.dptr(xs),
+                                  _lib.dptr(us), _lib.dptr(it), _lib.stream_ptr())
+            _lib.check(rc, "nnmpc_ts_solve")
+        return (xs, us, it) if return_iters else (xs, us)
+
+    def solve(self, ysp, dhats):
+        """(Ny,1),(Nd,1) -> (xs (Nx,1), us (Nu,1))   (linearMPC.py:298-311)."""
+        xs, us = self.solve_batch(np.asarray(ysp, float).reshape(1, -1), np.asarray(dhats, float).reshape(1, -1))
+        xs, us = xs.reshape(-1, 1), us.reshape(-1, 1)
+        self.xs.append(xs)
+        self.us.append(us)
+        self.ysp.append(ysp)
+        self.dhats.append(dhats)
+        return xs, us
+
+
+# ------------------------------------------------------------------------------ regulator
+class DenseQPRegulator:
+    """Condensed regulator QP (linearMPC.py:321-517) with a batched GPU solver.
+
+    Keeps the reference attributes (``P, tq, G, tA, tB, Pf, Krep, reparameterize, ulb, uub, x0,
+    useq``); ``tA``/``tB``/``G`` are built lazily because the reference's dense forms are huge at
+    CDU size.  ``solve(x0)`` has the reference signature; ``solve_batch`` is the data-parallel form.
+
+    Solver parameters (additive): ``rho_scale`` multiplies the default ADMM penalty
+    ``0.4 sqrt(lambda_min lambda_max)`` which is spread over the variables proportionally to
+    ``diag(P)``; ``alpha`` is the over-relaxation.
+    """
+
+    def __init__(self, *, A, B, Q, R, M, N, ulb, uub, rho_scale=1.0, alpha=1.8, tol=DEFAULT_TOL,
+                 max_iter=DEFAULT_MAX_ITER, device=None):
+        self.A, self.B, self.Q, self.R, self.M, self.N = A, B, Q, R, M, int(N)
+        self.ulb, self.uub = ulb, uub
+        self.Nx, self.Nu = B.shape
+        self.tol, self.max_iter, self.alpha, self.rho_scale = tol, max_iter, alpha, rho_scale
+        self.Krep, self.Pf = dlqr(A, B, Q, R, M)                       # :356
+        self._reparameterize()
+        self.P, self.tq = condense.condensed_hessian(self.A, self.B, self.Q, self.R, self.M, self.Pf, self.N)
+        self._tA = self._tB = self._G = None
+        self.x0, self.useq = [], []
+        self.last_info = None
+        self._dev = _device_index(device)
+        self._handle = None
+        self._setup_solver()
+
+    def _reparameterize(self):
+        """linearMPC.py:366-382.  The LQR re-parameterised (unstable A) path is not on the GPU yet."""
+        if np.any(np.abs(np.linalg.eigvals(self.A)) >= 1.0):
+            raise NotImplementedError("DenseQPRegulator on the GPU supports the box-constrained path "
+                                      "(open-loop stable A, G = tE); the re-parameterised path "
+                                      "(linearMPC.py:366-382) is listed as future work in DESIGN.md")
+        self.reparameterize = False
+
+    # lazily built reference attributes
+    @property
+    def tA(self):
+        if self._tA is None:
+            self._tA, self._tB = condense.prediction_matrices(self.A, self.B, self.N)
+        return self._tA
+
+    @property
+    def tB(self):
+        if self._tB is None:
+            self._tA, self._tB = condense.prediction_matrices(self.A, self.B, self.N)
+        return self._tB
+
+    @property
+    def G(self):
+        if self._G is None:
+            E = np.vstack([np.eye(self.Nu), -np.eye(self.Nu)])
+            self._G = scipy.linalg.block_diag(*([E] * self.N))
+        return self._G
+
+    @property
+    def tE(self):
+        return self.G
+
+    def _get_h(self, x0):
+        """linearMPC.py:484-493 (box path)."""
+        return np.tile(np.vstack([self.uub, -self.ulb]), (self.N, 1))
+
+    def _setup_solver(self):
+        n = self.N * self.Nu
+        if n % 2:
+            raise NotImplementedError("N*Nu must be even")
+        P = self.P
+        cho = scipy.linalg.cho_factor(P, lower=True)
+        self.Kunc = -scipy.linalg.cho_solve(cho, self.tq)               # unconstrained law u = Kunc x0
+        lmin, lmax = condense.extreme_eigs(P, cho)
+        self.eig_range = (lmin, lmax)
+        dP = np.diag(P)
+        rho0 = 0.4 * np.sqrt(lmin * lmax) * self.rho_scale
+        self.rho_vec = rho0 * dP / np.exp(np.mean(np.log(dP)))
+        Minv = scipy.linalg.inv(P + np.diag(self.rho_vec))
+        Minv = 0.5 * (Minv + Minv.T)
+        self._nxa_ld = (self.Nx + 1) & ~1
+
+        def pad(Mx):
+            if self._nxa_ld == self.Nx:
+                return _lib.host(Mx)
+            out = np.zeros((Mx.shape[0], self._nxa_ld))
+            out[:, :self.Nx] = Mx
+            return out
+        ops = [_lib.host(P), pad(self.tq), _lib.host(Minv * self.rho_vec[None, :]), pad(Minv @ self.tq),
+               pad(self.Kunc)]
+        L = _lib.lib()
+        hnd = C.c_void_p()
+        rc = L.nnmpc_qp_create(C.byref(hnd), n, self._nxa_ld, self.Nu, self.N, *[_lib.hptr(a) for a in ops],
+                               float(self.alpha), self._dev)
+        _lib.check(rc, "nnmpc_qp_create")
+        self._handle = hnd
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().nnmpc_qp_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_handle"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._setup_solver()
+
+    # ---- batched solve -------------------------------------------------------------------
+    def solve_batch(self, X0, LB=None, UB=None, *, warm_state=None, tol=None, max_iter=None, return_info=True):
+        """Solve B regulator QPs.
+
+        X0 (B,Nxa); LB, UB (B,Nu) per-sample stage bounds (default: this object's ulb/uub).
+        Returns U (B,n) in deviation variables and, with ``return_info``, dict(cost, kkt, iters,
+        maxiter_hit).  CUDA tensors in -> CUDA tensors out (no copies); NumPy in -> NumPy out via
+        the host entry point.  ``warm_state`` (CUDA (B,n) tensor) carries the solver state between
+        calls: pass the same tensor again to warm start.
+        """
+        L = _lib.lib()
+        tol = self.tol if tol is None else tol
+        max_iter = self.max_iter if max_iter is None else max_iter
+        n = self.N * self.Nu
+        if isinstance(X0, np.ndarray):
+            Bn = X0.shape[0]
+            X0p = np.zeros((Bn, self._nxa_ld))
+            X0p[:, :self.Nx] = X0
+            LB = np.tile(self.ulb.reshape(1, -1), (Bn, 1)) if LB is None else LB
+            UB = np.tile(self.uub.reshape(1, -1), (Bn, 1)) if UB is None else UB
+            LB, UB = _lib.host(LB), _lib.host(UB)
+            U, cost, kkt = np.empty((Bn, n)), np.empty(Bn), np.empty(Bn)
+            iters = np.empty(Bn, dtype=np.int32)
+            rc = L.nnmpc_qp_solve_host(self._handle, Bn, _lib.hptr(X0p), _lib.hptr(LB), _lib.hptr(UB), _lib.hptr(U),
+                                       _lib.hptr(cost), _lib.hptr(kkt), _lib.hptr(iters), float(tol), int(max_iter))
+            warned = _lib.check(rc, "nnmpc_qp_solve_host")
+        else:
+            torch = _torch()
+            dev = X0.device
+            Bn = X0.shape[0]
+            if X0.shape[1] != self._nxa_ld:
+                X0p = torch.zeros((Bn, self._nxa_ld), dtype=torch.float64, device=dev)
+                X0p[:, :self.Nx] = X0
+            else:
+                X0p = X0.contiguous()
+            if LB is None:
+                LB = torch.as_tensor(self.ulb.reshape(1, -1), device=dev).repeat(Bn, 1)
+            if UB is None:
+                UB = torch.as_tensor(self.uub.reshape(1, -1), device=dev).repeat(Bn, 1)
+            LB, UB = LB.contiguous(), UB.contiguous()
+            U = torch.empty((Bn, n), dtype=torch.float64, device=dev)
+            cost = torch.empty(Bn, dtype=torch.float64, device=dev)
+            kkt = torch.empty(Bn, dtype=torch.float64, device=dev)
+            iters = torch.empty(Bn, dtype=torch.int32, device=dev)
+            warm = 0
+            if warm_state is not None:
+                if tuple(warm_state.shape) != (Bn, n) or not warm_state.is_contiguous():
+                    raise ValueError("warm_state must be a contiguous (B, n) CUDA tensor")
+                warm = 1 if getattr(warm_state, "_nnmpc_valid", False) else 0
+            rc = L.nnmpc_qp_solve(self._handle, Bn, _lib.dptr(X0p), _lib.dptr(LB), _lib.dptr(UB), _lib.dptr(U),
+                                  _lib.dptr(warm_state), warm, _lib.dptr(cost), _lib.dptr(kkt), _lib.dptr(iters),
+                                  float(tol), int(max_iter), _lib.stream_ptr())
+            warned = _lib.check(rc, "nnmpc_qp_solve")
+            if warm_state is not None:
+                warm_state._nnmpc_valid = True
+        info = dict(cost=cost, kkt=kkt, iters=iters, maxiter_hit=warned)
+        self.last_info = info
+        return (U, info) if return_info else U
+
+    def solve(self, x0):
+        """(Nxa,1) -> useq (N*Nu,1), as linearMPC.py:495-512 (bounds = current self.ulb/self.uub)."""
+        x0 = np.asarray(x0, float)
+        U = self.solve_batch(x0.reshape(1, -1), self.ulb.reshape(1, -1), self.uub.reshape(1, -1), return_info=False)
+        useq = U.reshape(-1, 1)
+        self.x0.append(x0)
+        self.useq.append(useq)
+        return useq
+
+
+# ------------------------------------------------------------------------------ controller glue
+class LinearMPCController:
+    """Kalman filter + target selector + regulator (linearMPC.py:519-701)."""
+
+    def __init__(self, *, A, B, C, H, Qwx, Qwd, Rv, xprior, dprior, Rs, Qs, Bd, Cd, usp, uprev, Q, R, S, ulb, uub,
+                 N, device=None):
+        self.A, self.B, self.C, self.H = A, B, C, H
+        self.Qwx, self.Qwd, self.Rv, self.xprior, self.dprior = Qwx, Qwd, Rv, xprior, dprior
+        self.Rs, self.Qs, self.Bd, self.Cd, self.usp = Rs, Qs, Bd, Cd, usp
+        self.uprev = uprev
+        self.useq = np.tile(uprev, (N, 1))
+        self.Q, self.R, self.S, self.ulb, self.uub, self.N = Q, R, S, ulb, uub, N
+        self.Nx, self.Nu, self.Ny, self.Nd = A.shape[0], B.shape[1], C.shape[0], Bd.shape[1]
+        self.filter = LinearMPCController.setup_filter(A=A, B=B, C=C, Bd=Bd, Cd=Cd, Qwx=Qwx, Qwd=Qwd, Rv=Rv,
+                                                       xprior=xprior, dprior=dprior)
+        self.target_selector = LinearMPCController.setup_target_selector(
+            A=A, B=B, C=C, H=H, Bd=Bd, Cd=Cd, usp=usp, Qs=Qs, Rs=Rs, ulb=ulb, uub=uub, device=device)
+        self.regulator = LinearMPCController.setup_regulator(A=A, B=B, Q=Q, R=R, S=S, N=N, ulb=ulb, uub=uub,
+                                                             device=device)
+        _, _, self.Qaug, self.Raug, self.Maug = LinearMPCController.get_augmented_matrices_for_regulator(A, B, Q, R, S)
+        self.average_stage_costs = [np.zeros((1, 1))]
+        self.computation_times = []
+
+    @staticmethod
+    def setup_filter(A, B, C, Bd, Cd, Qwx, Qwd, Rv, xprior, dprior):
+        Aaug, Baug, Caug, Qwaug = LinearMPCController.get_augmented_matrices_for_filter(A, B, C, Bd, Cd, Qwx, Qwd)
+        return KalmanFilter(A=Aaug, B=Baug, C=Caug, Qw=Qwaug, Rv=Rv, xprior=np.concatenate((xprior, dprior)))
+
+    @staticmethod
+    def setup_target_selector(A, B, C, H, Bd, Cd, usp, Qs, Rs, ulb, uub, device=None):
+        return TargetSelector(A=A, B=B, C=C, H=H, Bd=Bd, Cd=Cd, usp=usp, Rs=Rs, Qs=Qs, ulb=ulb, uub=uub,
+                              device=device)
+
+    @staticmethod
+    def setup_regulator(A, B, Q, R, S, N, ulb, uub, device=None, **solver_kwargs):
+        Aaug, Baug, Qaug, Raug, Maug = LinearMPCController.get_augmented_matrices_for_regulator(A, B, Q, R, S)
+        return DenseQPRegulator(A=Aaug, B=Baug, Q=Qaug, R=Raug, N=N, M=Maug, ulb=ulb, uub=uub, device=device,
+                                **solver_kwargs)
+
+    @staticmethod
+    def get_augmented_matrices_for_filter(A, B, C, Bd, Cd, Qwx, Qwd):
+        """Integrating-disturbance augmentation (linearMPC.py:606-624)."""
+        nx, nu, nd = A.shape[0], B.shape[1], Bd.shape[1]
+        Aaug = np.block([[A, Bd], [np.zeros((nd, nx)), np.eye(nd)]])
+        Baug = np.vstack([B, np.zeros((nd, nu))])
+        Caug = np.hstack([C, Cd])
+        Qwaug = scipy.linalg.block_diag(Qwx, Qwd)
+        assert_detectable(Aaug, Caug)
+        return Aaug, Baug, Caug, Qwaug
+
+    @staticmethod
+    def get_augmented_matrices_for_regulator(A, B, Q, R, S):
+        """Rate-of-change augmentation with state [x; uprev] (linearMPC.py:626-644)."""
+        nx, nu = B.shape
+        Aaug = np.zeros((nx + nu, nx + nu))
+        Aaug[:nx, :nx] = A
+        Baug = np.vstack([B, np.eye(nu)])
+        Qaug = scipy.linalg.block_diag(Q, S)
+        Raug = R + S
+        Maug = np.vstack([np.zeros((nx, nu)), -S])
+        return Aaug, Baug, Qaug, Raug, Maug
+
+    def control_law(self, ysp, y):
+        """Measurement -> control input (linearMPC.py:646-669); times only the regulator solve."""
+        xhat, dhat = LinearMPCController.get_state_estimates(self.filter, y, self.uprev, self.Nx)
+        xs, us = LinearMPCController.get_target_pair(self.target_selector, ysp, dhat)
+        tstart = time.time()
+        self.useq = LinearMPCController.get_control_sequence(self.regulator, xhat, self.uprev, xs, us, self.ulb,
+                                                             self.uub)
+        tend = time.time()
+        avg_ell = LinearMPCController.get_updated_average_stage_cost(
+            xhat, self.uprev, xs, us, self.useq[0:self.Nu, :], self.Qaug, self.Raug, self.Maug,
+            self.average_stage_costs[-1], len(self.average_stage_costs))
+        self.average_stage_costs.append(avg_ell)
+        self.uprev = self.useq[0:self.Nu, :]
+        self.computation_times.append(tend - tstart)
+        return self.uprev
+
+    @staticmethod
+    def get_state_estimates(filter, y, uprev, Nx):
+        return np.split(filter.solve(y, uprev), [Nx])
+
+    @staticmethod
+    def get_target_pair(target_selector, ysp, dhat):
+        return target_selector.solve(ysp, dhat)
+
+    @staticmethod
+    def get_control_sequence(regulator, x, uprev, xs, us, ulb, uub):
+        """linearMPC.py:682-689: bounds shifted by us, x0 in deviation variables, us added back."""
+        regulator.ulb = ulb - us
+        regulator.uub = uub - us
+        x0 = np.concatenate((x - xs, uprev - us))
+        return regulator.solve(x0) + np.tile(us, (regulator.N, 1))
+
+    @staticmethod
+    def get_updated_average_stage_cost(x, uprev, xs, us, u, Qaug, Raug, Maug, average_stage_cost, time_index):
+        """Running mean of x'Qx + u'Ru + 2x'Mu in deviation variables (linearMPC.py:691-701)."""
+        xa = np.concatenate((x - xs, uprev - us), axis=0)
+        du = u - us
+        ell = xa.T @ (Qaug @ xa) + du.T @ (Raug @ du) + xa.T @ (Maug @ du) + du.T @ (Maug.T @ xa)
+        return (average_stage_cost * (time_index - 1) + ell) / time_index
+
+
+def online_simulation(plant, controller, *, setpoints=None, disturbances=None, Nsim=None, stdout_filename=None):
+    """Sequential closed loop with a plant object (linearMPC.py:703-718)."""
+    out = open(stdout_filename, "w") if stdout_filename else None
+    measurement = plant.y[0]
+    for i, (sp, dist) in enumerate(zip(setpoints[..., np.newaxis], disturbances[..., np.newaxis])):
+        if i >= Nsim:
+            break
+        u = controller.control_law(sp, measurement)
+        if out:
+            print(f"Simulation Step:{i}\nComputation time:{controller.computation_times[-1]}", file=out)
+        measurement = plant.step(u, dist)
+    if out:
+        out.close()
+    return plant
+
+
+# ------------------------------------------------------------------------------ offline data generation
+def _save_training_data(dictionary, filename):
+    """H5pyTool.save_training_data (lib/python_utils.py:53-58): one dataset per key.  h5py is
+    used when importable; otherwise the same keys go into ``<filename>.npz``."""
+    try:
+        import h5py
+    except ImportError:
+        np.savez(filename + ".npz", **dictionary)
+        return filename + ".npz"
+    with h5py.File(filename, "w") as f:
+        for k, v in dictionary.items():
+            f.create_dataset(k, data=v)
+    return filename
+
+
+def load_training_data(filename):
+    """H5pyTool.load_training_data (lib/python_utils.py:43-50) for either container."""
+    import os
+    if os.path.exists(filename + ".npz"):
+        with np.load(filename + ".npz") as z:
+            return {k: np.asarray(z[k]) for k in z.files}
+    import h5py
+    with h5py.File(filename, "r") as f:
+        return {k: np.asarray(f.get(k)) for k in f.keys()}
+
+
+class ClosedLoopEngine:
+    """Owns the nnmpc_sim handle for one (regulator, target selector, plant) triple."""
+
+    def __init__(self, regulator, target_selector, A, B, Bd):
+        if regulator._dev != target_selector._dev:
+            raise ValueError("regulator and target selector live on different devices")
+        self.regulator, self.target_selector = regulator, target_selector
+        self.nx, self.nu = B.shape
+        self.nd = Bd.shape[1]
+        self.ny = target_selector.Ny
+        self._dev = regulator._dev
+        L = _lib.lib()
+        ABd = _lib.host(np.hstack([A, B, Bd]))
+        hnd = C.c_void_p()
+        rc = L.nnmpc_sim_create(C.byref(hnd), regulator._handle, target_selector._handle, self.nx, self.nu, self.nd,
+                                self.ny, _lib.hptr(ABd), self._dev)
+        _lib.check(rc, "nnmpc_sim_create")
+        self._handle = hnd
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().nnmpc_sim_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def run(self, x0, uprev0, setpoints, disturbances, *, tol=None, max_iter=None):
+        """Advance B trajectories T steps.
+
+        setpoints (B,T,Ny), disturbances (B,T,Nd); x0 (B,Nx), uprev0 (B,Nu) (or column vectors,
+        broadcast to all trajectories).  NumPy in -> dict of NumPy arrays (host entry point, copies
+        inside the call); CUDA tensors in -> dict of CUDA tensors.  Keys as the reference's h5
+        files: x, uprev, xs, us, u with shapes (B,T,.), plus iters, kkt (B,T) and x_final/uprev_final.
+        """
+        L = _lib.lib()
+        reg = self.regulator
+        tol = reg.tol if tol is None else tol
+        max_iter = reg.max_iter if max_iter is None else max_iter
+        Bn, T = setpoints.shape[0], setpoints.shape[1]
+        nx, nu = self.nx, self.nu
+        if isinstance(setpoints, np.ndarray):
+            sp, dist = _lib.host(setpoints), _lib.host(disturbances)
+            xio = _lib.host(np.broadcast_to(np.asarray(x0, float).reshape(-1, nx), (Bn, nx))).copy()
+            uio = _lib.host(np.broadcast_to(np.asarray(uprev0, float).reshape(-1, nu), (Bn, nu))).copy()
+            out = dict(x=np.empty((Bn, T, nx)), uprev=np.empty((Bn, T, nu)), xs=np.empty((Bn, T, nx)),
+                       us=np.empty((Bn, T, nu)), u=np.empty((Bn, T, nu)), iters=np.empty((Bn, T), dtype=np.int32),
+                       kkt=np.empty((Bn, T)))
+            rc = L.nnmpc_sim_run_host(self._handle, Bn, T, _lib.hptr(xio), _lib.hptr(uio), _lib.hptr(sp),
+                                      _lib.hptr(dist), *[_lib.hptr(out[k]) for k in ("x", "uprev", "xs", "us", "u",
+                                                                                      "iters", "kkt")],
+                                      float(tol), int(max_iter))
+            out["maxiter_hit"] = _lib.check(rc, "nnmpc_sim_run_host")
+        else:
+            torch = _torch()
+            dev = setpoints.device
+            sp, dist = setpoints.contiguous(), disturbances.contiguous()
+            f64 = dict(dtype=torch.float64, device=dev)
+            xio = torch.as_tensor(x0, **f64).reshape(-1, nx).expand(Bn, nx).contiguous().clone()
+            uio = torch.as_tensor(uprev0, **f64).reshape(-1, nu).expand(Bn, nu).contiguous().clone()
+            out = dict(x=torch.empty((Bn, T, nx), **f64), uprev=torch.empty((Bn, T, nu), **f64),
+                       xs=torch.empty((Bn, T, nx), **f64), us=torch.empty((Bn, T, nu), **f64),
+                       u=torch.empty((Bn, T, nu), **f64),
+                       iters=torch.empty((Bn, T), dtype=torch.int32, device=dev), kkt=torch.empty((Bn, T), **f64))
+            rc = L.nnmpc_sim_run(self._handle, Bn, T, _lib.dptr(xio), _lib.dptr(uio), _lib.dptr(sp), _lib.dptr(dist),
+                                 *[_lib.dptr(out[k]) for k in ("x", "uprev", "xs", "us", "u", "iters", "kkt")],
+                                 float(tol), int(max_iter), _lib.stream_ptr())
+            out["maxiter_hit"] = _lib.check(rc, "nnmpc_sim_run")
+        out["x_final"], out["uprev_final"] = xio, uio
+        return out
+
+
+def simulate_offline(task_number, process_number, data_filename, x0, uprev0, A, B, Bd, regulator, ulb, uub,
+                     target_selector, setpoints, disturbances):
+    """One trajectory chunk, reference signature (linearMPC.py:827-880); writes
+    ``{task}-{process}-{data_filename}`` with keys x, uprev, xs, us, u, data_gen_time."""
+    t0 = time.time()
+    regulator.ulb, regulator.uub = ulb, uub
+    eng = ClosedLoopEngine(regulator, target_selector, A, B, Bd)
+    res = eng.run(x0, uprev0, np.asarray(setpoints)[None], np.asarray(disturbances)[None])
+    data = {k: res[k][0] for k in ("x", "uprev", "xs", "us", "u")}
+    data["data_gen_time"] = time.time() - t0
+    return _save_training_data(data, f"{task_number}-{process_number}-{data_filename}")
+
+
+class OfflineSimulator:
+    """Offline data generator (linearMPC.py:720-825).
+
+    The reference builds one regulator/target selector per OS process and forks
+    ``num_process_per_task`` processes per task; here one regulator/target selector pair serves
+    every trajectory and all chunks of a task (or of all tasks, ``generate_batch``) advance
+    together as one GPU batch.
+    """
+
+    def __init__(self, *, A, B, C, H, Rs, Qs, Bd, Cd, usp, uprev, Q, R, S, ulb, uub, N, xprior, setpoints,
+                 disturbances, num_data_gen_task, num_process_per_task, device=None, **solver_kwargs):
+        self.A, self.B, self.C, self.H, self.Rs, self.Qs, self.Bd, self.Cd = A, B, C, H, Rs, Qs, Bd, Cd
+        self.usp, self.Q, self.R, self.S, self.ulb, self.uub, self.N = usp, Q, R, S, ulb, uub, N
+        self.num_data_gen_task, self.num_process_per_task = num_data_gen_task, num_process_per_task
+        self.Nx, self.Nu, self.Ny, self.Nd = A.shape[0], B.shape[1], C.shape[0], Bd.shape[1]
+        self.x0, self.uprev0 = xprior, uprev
+        self.target_selector = LinearMPCController.setup_target_selector(
+            A=A, B=B, C=C, H=H, Bd=Bd, Cd=Cd, usp=usp, Qs=Qs, Rs=Rs, ulb=ulb, uub=uub, device=device)
+        self.regulator = LinearMPCController.setup_regulator(A=A, B=B, Q=Q, R=R, S=S, N=N, ulb=ulb, uub=uub,
+                                                             device=device, **solver_kwargs)
+        # reference attribute names: one entry per process (all aliases of the shared pair)
+        self.regulators = [self.regulator] * num_process_per_task
+        self.target_selectors = [self.target_selector] * num_process_per_task
+        self.engine = ClosedLoopEngine(self.regulator, self.target_selector, A, B, Bd)
+        self.setpoints, self.disturbances = self._split_scenarios(setpoints=setpoints, disturbances=disturbances)
+
+    def _split_scenarios(self, *, setpoints, disturbances):
+        """Equal contiguous chunks, remainder dropped; lists indexed [task][process]
+        (linearMPC.py:786-801)."""
+        nproc = self.num_data_gen_task * self.num_process_per_task
+        Lc = int(setpoints.shape[0] / nproc)
+        self.Nsim_each_process = Lc
+        sp = [setpoints[i * Lc:(i + 1) * Lc, :] for i in range(nproc)]
+        ds = [disturbances[i * Lc:(i + 1) * Lc, :] for i in range(nproc)]
+        k = self.num_process_per_task
+        return ([sp[t * k:(t + 1) * k] for t in range(self.num_data_gen_task)],
+                [ds[t * k:(t + 1) * k] for t in range(self.num_data_gen_task)])
+
+    def generate_batch(self, tasks=None):
+        """All chunks of the given tasks (default: all) as one batch; returns the engine's dict
+        with arrays shaped (num_chunks, L, .), chunk order = (task, process) order."""
+        tasks = range(self.num_data_gen_task) if tasks is None else tasks
+        sp = np.stack([c for t in tasks for c in self.setpoints[t]])
+        ds = np.stack([c for t in tasks for c in self.disturbances[t]])
+        return self.engine.run(self.x0, self.uprev0, sp, ds)
+
+    def generate_data(self, *, task_number, data_filename, stdout_filename):
+        """Reference entry point (linearMPC.py:803-825): writes one file per process of the task."""
+        t0 = time.time()
+        res = self.generate_batch([task_number])
+        dt = time.time() - t0
+        with open(stdout_filename, "w") as log:
+            for proc in range(len(self.setpoints[task_number])):
+                print(f"Process:{proc}\nSimulation Steps:{res['x'].shape[1]}\nComputation time:{dt}", file=log)
+        files = []
+        for proc in range(len(self.setpoints[task_number])):
+            data = {k: res[k][proc] for k in ("x", "uprev", "xs", "us", "u")}
+            data["data_gen_time"] = dt
+            files.append(_save_training_data(data, f"{task_number}-{proc}-{data_filename}"))
+        return files

@@ -1,0 +1,210 @@
+"""NumPy float64 restatement of the reference's linear-MPC hot path (TEST INFRASTRUCTURE).
+
+Follows /root/reference/lib/linearMPC.py; every function cites the lines it restates.
+The formulation is built *literally* (dense ``tA``, ``tB``, block diagonals), exactly as the
+reference does, so it is only meant for sizes where that fits (CSTRs N=90; small CDU-like
+cases).  The product package builds the same operators by a block recursion; tests compare
+the two.  The QP itself is solved exactly (``oracle.qp``), because ``cvxopt`` is absent.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+
+from . import qp as _qp
+
+
+# ----------------------------------------------------------------------------- helpers
+def dlqr(A, B, Q, R, M=None):
+    """Discrete LQR with cross term; stage cost x'Qx + 2x'Mu + u'Ru.  linearMPC.py:22-40."""
+    if M is None:
+        At, Qt, M = A, Q, np.zeros(B.shape)
+    else:
+        RiMt = scipy.linalg.solve(R, M.T)
+        At = A - B @ RiMt
+        Qt = Q - M @ RiMt
+    Pi = scipy.linalg.solve_discrete_are(At, B, Qt, R)
+    K = -scipy.linalg.solve(B.T @ Pi @ B + R, B.T @ Pi @ A + M.T)
+    return K, Pi
+
+
+def c2d(A, B, sample_time):
+    """Zero-order-hold discretisation through one matrix exponential.  linearMPC.py:50-64."""
+    nx, nu = B.shape
+    blk = np.zeros((nx + nu, nx + nu))
+    blk[:nx, :nx] = A
+    blk[:nx, nx:] = B
+    E = scipy.linalg.expm(blk * sample_time)
+    return E[:nx, :nx], E[:nx, nx:]
+
+
+def augmented_matrices_for_regulator(A, B, Q, R, S):
+    """Rate-of-change augmentation, state [x; uprev].  linearMPC.py:626-644."""
+    nx, nu = B.shape
+    Aaug = np.zeros((nx + nu, nx + nu))
+    Aaug[:nx, :nx] = A
+    Baug = np.vstack([B, np.eye(nu)])
+    Qaug = scipy.linalg.block_diag(Q, S)
+    Raug = R + S
+    Maug = np.vstack([np.zeros((nx, nu)), -S])
+    return Aaug, Baug, Qaug, Raug, Maug
+
+
+# ----------------------------------------------------------------------------- regulator
+class DenseQPRegulatorOracle:
+    """Literal dense condensing of the regulator QP.  linearMPC.py:321-517.
+
+    min_u 1/2 u'Pu + (tq x0)'u   s.t.  G u <= h(x0)
+    """
+
+    def __init__(self, *, A, B, Q, R, M, N, ulb, uub):
+        self.A, self.B, self.Q, self.R, self.M, self.N = A, B, Q, R, M, int(N)
+        self.ulb, self.uub = ulb, uub
+        self.Nx, self.Nu = B.shape
+        self.Krep, self.Pf = dlqr(A, B, Q, R, M)                      # :356
+        # :366-382 — re-parameterise with u = Kx + v when A is not open-loop stable
+        if np.any(np.abs(np.linalg.eigvals(self.A)) >= 1.0):
+            K = self.Krep
+            self.A = self.A + self.B @ K
+            self.Q = self.Q + K.T @ (self.R @ K)
+            self.Q = self.Q + self.M @ K + K.T @ self.M.T
+            self.M = K.T @ self.R + self.M
+            self.reparameterize = True
+        else:
+            self.reparameterize = False
+        self._build()
+
+    def _build(self):
+        A, B, N, nx, nu = self.A, self.B, self.N, self.Nx, self.Nu
+        # :397-428  tA = [I; A; ...; A^N], tB block lower-triangular Toeplitz
+        pw = [np.eye(nx)]
+        for _ in range(N):
+            pw.append(A @ pw[-1])
+        self.tA = np.vstack(pw)
+        tB = np.zeros(((N + 1) * nx, N * nu))
+        for i in range(1, N + 1):
+            for j in range(i):
+                tB[i * nx:(i + 1) * nx, j * nu:(j + 1) * nu] = pw[i - j - 1] @ B
+        self.tB = tB
+        # :430-465 block diagonals
+        tQ = scipy.linalg.block_diag(*([self.Q] * N + [self.Pf]))
+        tR = scipy.linalg.block_diag(*([self.R] * N))
+        tM = np.vstack([scipy.linalg.block_diag(*([self.M] * N)), np.zeros((nx, N * nu))])
+        E = np.vstack([np.eye(nu), -np.eye(nu)])
+        self.tE = scipy.linalg.block_diag(*([E] * N))
+        self.tK = scipy.linalg.block_diag(*([self.Krep] * N)) if self.reparameterize else None
+        # :467-474
+        self.P = tB.T @ (tQ @ tB) + tR + tB.T @ tM + tM.T @ tB
+        self.tq = (tB.T @ tQ + tM.T) @ self.tA
+        # :476-482
+        if self.reparameterize:
+            self.G = self.tE @ (self.tK @ tB[:N * nx, :]) + self.tE
+        else:
+            self.G = self.tE
+
+    def get_h(self, x0):
+        """:484-493 — per-stage [uub; -ulb], shifted by tE tK tA x0 when re-parameterised."""
+        te = np.tile(np.vstack([self.uub, -self.ulb]), (self.N, 1))
+        if self.reparameterize:
+            return te - self.tE @ (self.tK @ (self.tA[:self.N * self.Nx, :] @ x0))
+        return te
+
+    def solve(self, x0, return_info=False):
+        """:495-512.  Exact solve of the (unique) minimiser; returns useq (n,1)."""
+        q = self.tq @ x0
+        if self.reparameterize:
+            v, info = _qp.solve_general_qp(self.P, q, self.G, self.get_h(x0))
+            nN = self.N * self.Nx
+            useq = self.tK @ (self.tA[:nN, :] @ x0 + self.tB[:nN, :] @ v) + v
+        else:
+            lb = np.tile(self.ulb, (self.N, 1))
+            ub = np.tile(self.uub, (self.N, 1))
+            useq, info = _qp.solve_box_qp(self.P, q, lb, ub)
+        return (useq, info) if return_info else useq
+
+
+# ----------------------------------------------------------------------------- target selector
+class TargetSelectorOracle:
+    """Steady-state target QP in (xs, us).  linearMPC.py:178-319 (input-bound branch :249-251)."""
+
+    def __init__(self, *, A, B, C, H, Bd, Cd, usp, Rs, Qs, ulb, uub):
+        self.A, self.B, self.C, self.H, self.Bd, self.Cd = A, B, C, H, Bd, Cd
+        self.usp, self.Rs, self.Qs, self.ulb, self.uub = usp, Rs, Qs, ulb, uub
+        self.Nx, self.Nu = B.shape
+        self.Ny, self.Nd, self.Nz = C.shape[0], Bd.shape[1], H.shape[0]
+        nx, nu, ny, nz = self.Nx, self.Nu, self.Ny, self.Nz
+        E = np.vstack([np.eye(nu), -np.eye(nu)])
+        self.G = np.hstack([np.zeros((2 * nu, nx)), E])                  # :250
+        self.h = np.vstack([uub, -ulb])                                   # :251
+        self.tA = np.block([[np.eye(nx) - A, -B], [H @ C, np.zeros((nz, nu))]])     # :254-260
+        self.tb = np.block([[np.zeros((nx, ny)), Bd], [H, -(H @ Cd)]])              # :261-267
+        self.P = scipy.linalg.block_diag(C.T @ (Qs @ C), Rs)             # :270-274
+
+    def changing(self, ysp, dhats):
+        """:276-296."""
+        q = np.vstack([-(self.C.T @ (self.Qs @ (ysp - self.Cd @ dhats))), -(self.Rs @ self.usp)])
+        b = self.tb @ np.vstack([ysp, dhats])
+        return q, self.h, b
+
+    def solve(self, ysp, dhats, return_info=False):
+        """:298-311 — returns (xs, us)."""
+        q, _, b = self.changing(ysp, dhats)
+        nx = self.Nx
+        lb = np.vstack([np.full((nx, 1), -np.inf), self.ulb])
+        ub = np.vstack([np.full((nx, 1), np.inf), self.uub])
+        w, info = _qp.solve_eq_box_qp(self.P, q, self.tA, b, lb, ub)
+        xs, us = w[:nx], w[nx:]
+        return ((xs, us), info) if return_info else (xs, us)
+
+
+# ----------------------------------------------------------------------------- controller glue
+def get_control_sequence(regulator, x, uprev, xs, us, ulb, uub):
+    """linearMPC.py:682-689 — bounds shifted by us, x0 in deviation variables, us added back."""
+    regulator.ulb = ulb - us
+    regulator.uub = uub - us
+    x0 = np.vstack([x - xs, uprev - us])
+    return regulator.solve(x0) + np.tile(us, (regulator.N, 1))
+
+
+def updated_average_stage_cost(x, uprev, xs, us, u, Qaug, Raug, Maug, avg, time_index):
+    """linearMPC.py:691-701 — running mean of x'Qx + u'Ru + 2x'Mu (no 1/2 factor)."""
+    xa = np.vstack([x - xs, uprev - us])
+    du = u - us
+    ell = xa.T @ (Qaug @ xa) + du.T @ (Raug @ du) + xa.T @ (Maug @ du) + du.T @ (Maug.T @ xa)
+    return (avg * (time_index - 1) + ell) / time_index
+
+
+def setup_regulator(A, B, Q, R, S, N, ulb, uub):
+    """linearMPC.py:596-604."""
+    Aa, Ba, Qa, Ra, Ma = augmented_matrices_for_regulator(A, B, Q, R, S)
+    return DenseQPRegulatorOracle(A=Aa, B=Ba, Q=Qa, R=Ra, M=Ma, N=N, ulb=ulb, uub=uub)
+
+
+def split_scenarios(setpoints, disturbances, num_processes):
+    """linearMPC.py:786-801 — equal chunks, remainder rows dropped."""
+    L = int(setpoints.shape[0] / num_processes)
+    return ([setpoints[i * L:(i + 1) * L] for i in range(num_processes)],
+            [disturbances[i * L:(i + 1) * L] for i in range(num_processes)])
+
+
+def simulate_offline(*, x0, uprev0, A, B, Bd, regulator, ulb, uub, target_selector,
+                     setpoints, disturbances):
+    """The closed loop of linearMPC.py:827-880 for one chunk.
+
+    Returns dict(x, uprev, xs, us, u) with shapes (L,Nx),(L,Nu),(L,Nx),(L,Nu),(L,Nu);
+    row t holds the state *before* step t (:868-872).
+    """
+    nu = B.shape[1]
+    xt, upt = x0, uprev0
+    rows = dict(x=[], uprev=[], xs=[], us=[], u=[])
+    for t in range(setpoints.shape[0]):
+        ysp = setpoints[t][:, None]
+        d = disturbances[t][:, None]
+        xs, us = target_selector.solve(ysp, d)
+        useq = get_control_sequence(regulator, xt, upt, xs, us, ulb, uub)
+        ut = useq[:nu]
+        for k, v in zip(("x", "uprev", "xs", "us", "u"), (xt, upt, xs, us, ut)):
+            rows[k].append(v[:, 0])
+        xt = A @ xt + B @ ut + Bd @ d
+        upt = ut
+    return {k: np.asarray(v) for k, v in rows.items()}

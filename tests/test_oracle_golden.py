@@ -1,0 +1,188 @@
+"""CPU: the oracle and the product's host-side setup against fixtures generated from the
+reference's own code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import linear_mpc as om
+from oracle import qp as oq
+from industrial_nnmpc_2021_b200 import condense
+from industrial_nnmpc_2021_b200.controller_evaluation import sample_prbs_like
+
+
+@pytest.mark.parametrize("tag", ["cstrs", "cdu_small"])
+def test_oracle_formulation_matches_reference(golden_formulation, tag):
+    g = golden_formulation
+    N = int(g[f"{tag}_N"])
+    reg = om.setup_regulator(g[f"{tag}_A"], g[f"{tag}_B"], g[f"{tag}_Q"], g[f"{tag}_R"], g[f"{tag}_S"], N,
+                             g[f"{tag}_ulb"], g[f"{tag}_uub"])
+    assert bool(g[f"{tag}_reparam"]) == reg.reparameterize
+    for k in ("P", "tq", "G", "tA", "tB", "Pf", "Krep"):
+        ref = g[f"{tag}_{k}"]
+        assert np.allclose(getattr(reg, k), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), k
+    assert np.array_equal(reg.get_h(g[f"{tag}_x0"]), g[f"{tag}_h"])
+    aug = om.augmented_matrices_for_regulator(g[f"{tag}_A"], g[f"{tag}_B"], g[f"{tag}_Q"], g[f"{tag}_R"],
+                                              g[f"{tag}_S"])
+    for k, a in zip(("Aaug", "Baug", "Qaug", "Raug", "Maug"), aug):
+        assert np.array_equal(a, g[f"{tag}_{k}"]), k
+
+
+@pytest.mark.parametrize("tag", ["cstrs", "cdu_small"])
+def test_product_recursion_matches_reference(golden_formulation, tag):
+    """condense.condensed_hessian (block recursion) == the reference's dense formula."""
+    g = golden_formulation
+    N = int(g[f"{tag}_N"])
+    P, tq = condense.condensed_hessian(g[f"{tag}_Aaug"], g[f"{tag}_Baug"], g[f"{tag}_Qaug"], g[f"{tag}_Raug"],
+                                       g[f"{tag}_Maug"], g[f"{tag}_Pf"], N)
+    assert np.allclose(P, g[f"{tag}_P"], rtol=0, atol=1e-13 * np.abs(P).max())
+    assert np.allclose(tq, g[f"{tag}_tq"], rtol=0, atol=1e-13 * np.abs(tq).max())
+    K, Pf = condense.dlqr(g[f"{tag}_Aaug"], g[f"{tag}_Baug"], g[f"{tag}_Qaug"], g[f"{tag}_Raug"], g[f"{tag}_Maug"])
+    assert np.allclose(K, g[f"{tag}_Krep"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(Pf, g[f"{tag}_Pf"], rtol=1e-10, atol=1e-10)
+    tA, tB = condense.prediction_matrices(g[f"{tag}_Aaug"], g[f"{tag}_Baug"], N)
+    assert np.allclose(tA, g[f"{tag}_tA"], atol=1e-13) and np.allclose(tB, g[f"{tag}_tB"], atol=1e-13)
+
+
+def test_full_horizon_cstr_hessian_digest(golden_formulation, cstrs_problem):
+    """N=90 CSTR Hessian from the recursion against probes of the reference's P, tq."""
+    g, p = golden_formulation, cstrs_problem
+    aug = om.augmented_matrices_for_regulator(p.A, p.B, p.Q, p.R, p.S)
+    K, Pf = condense.dlqr(*aug)
+    assert np.allclose(K, g["cstrs_full_Krep"], rtol=1e-9, atol=1e-12)
+    P, tq = condense.condensed_hessian(*aug, Pf, p.N)
+    probe = g["cstrs_full_probe"]
+    assert np.allclose(P @ probe, g["cstrs_full_P_probe"], rtol=1e-11, atol=1e-9)
+    assert np.allclose(tq.T @ probe, g["cstrs_full_tq_probe"], rtol=1e-11, atol=1e-9)
+    assert np.allclose(np.diag(P), g["cstrs_full_P_diag"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["cstrs", "cdu_small"])
+def test_target_selector_formulation(golden_formulation, tag):
+    g = golden_formulation
+    nu = g[f"{tag}_B"].shape[1]
+    ny = g[f"{tag}_C"].shape[0]
+    nd = g[f"{tag}_Bd"].shape[1]
+    ts = om.TargetSelectorOracle(A=g[f"{tag}_A"], B=g[f"{tag}_B"], C=g[f"{tag}_C"], H=np.zeros((0, ny)),
+                                 Bd=g[f"{tag}_Bd"], Cd=np.zeros((ny, nd)), usp=np.zeros((nu, 1)),
+                                 Rs=g[f"{tag}_Rs"], Qs=g[f"{tag}_Qs"], ulb=g[f"{tag}_ulb"], uub=g[f"{tag}_uub"])
+    for k in ("P", "G", "h", "tA", "tb"):
+        assert np.allclose(getattr(ts, k), g[f"{tag}_ts_{k}"], atol=1e-14), k
+    q, h, b = ts.changing(g[f"{tag}_ysp"], g[f"{tag}_d"])
+    assert np.allclose(q, g[f"{tag}_ts_q"], atol=1e-13) and np.allclose(b, g[f"{tag}_ts_b"], atol=1e-13)
+
+
+def test_unstable_reparameterised_formulation(golden_formulation):
+    g = golden_formulation
+    reg = om.DenseQPRegulatorOracle(A=g["unst_A"], B=g["unst_B"], Q=np.eye(2), R=np.eye(1), M=np.zeros((2, 1)),
+                                    N=5, ulb=-np.ones((1, 1)), uub=np.ones((1, 1)))
+    assert reg.reparameterize and bool(g["unst_reparam"])
+    for k in ("P", "tq", "G"):
+        assert np.allclose(getattr(reg, k), g[f"unst_{k}"], atol=1e-12), k
+    assert np.allclose(reg.get_h(g["unst_x0"]), g["unst_h"], atol=1e-13)
+    u = reg.solve(g["unst_x0"])           # general-G path of the oracle runs
+    assert u.shape == (5, 1) and np.all(np.abs(u) <= 1 + 1e-9)
+
+
+def test_stage_cost(golden_formulation):
+    g = golden_formulation
+    for tag in ("cstrs", "cdu_small"):
+        x0 = g[f"{tag}_x0"]
+        nx = g[f"{tag}_A"].shape[0]
+        ell = om.updated_average_stage_cost(x0[:nx], x0[nx:], 0.1 * x0[:nx], 0.2 * x0[nx:], 0.3 * x0[nx:],
+                                            g[f"{tag}_Qaug"], g[f"{tag}_Raug"], g[f"{tag}_Maug"],
+                                            np.array([[0.7]]), 5)
+        assert np.allclose(ell, g[f"{tag}_ell"], rtol=1e-13)
+
+
+def test_prbs_bit_exact(golden_prbs, cstrs_problem):
+    """sample_prbs_like reproduces the reference's scenario arrays bit for bit (seeds 1 and 2)."""
+    g = golden_prbs
+    par = cstrs_problem.extra["parameters"]
+    five = np.array([[5., 20, 20, 20, 20]]).T
+    cases = dict(
+        cstrs_sp=dict(num_change=1250, num_steps=150000, lb=par["lb"]["y"] * 1.02, ub=par["ub"]["y"] * 1.02,
+                      mean_change=120, sigma_change=2, seed=1),
+        cstrs_dist=dict(num_change=2500, num_steps=150000, lb=par["lb"]["p"] * 1.02, ub=par["ub"]["p"] * 1.02,
+                        mean_change=60, sigma_change=5, seed=2),
+        cdu_sp=dict(num_change=894, num_steps=357600, lb=-1.05 * np.ones((4, 1)), ub=1.05 * np.ones((4, 1)),
+                    mean_change=400, sigma_change=1, seed=1),
+        cdu_dist=dict(num_change=1788, num_steps=357600, lb=-1.05 * five, ub=1.05 * five, mean_change=200,
+                      sigma_change=1, seed=2))
+    for k, kw in cases.items():
+        s = sample_prbs_like(**kw)
+        assert tuple(g[k + "_shape"]) == s.shape
+        assert np.array_equal(s[::997], g[k + "_every997"]), k
+        chk = np.array([s.sum(), np.abs(s).sum(), (s * np.arange(1, s.shape[0] + 1)[:, None]).sum()])
+        assert np.array_equal(chk, g[k + "_sum"]), k
+
+
+def test_cstrs_scenarios_are_the_reference_signals(golden_prbs, cstrs_problem):
+    p = cstrs_problem
+    assert p.setpoints.shape == (150000, 12) and p.disturbances.shape == (150000, 5)
+    z = list(p.extra["z_indices"])
+    assert np.array_equal(p.setpoints[::997][:, [0, 3, 7, 8, 11]], golden_prbs["cstrs_sp_every997"][:, [0, 3, 7, 8, 11]])
+    assert np.all(p.setpoints[:, 4] == 0)                       # unexp_z_indices zeroed (cstrs_parameters.py:335)
+    assert np.all(p.setpoints[:, [i for i in range(12) if i not in z]] == 0)
+    assert np.array_equal(p.disturbances[::997], golden_prbs["cstrs_dist_every997"])
+
+
+def test_cstr_model_is_box_path(cstrs_problem):
+    p = cstrs_problem
+    lam = np.abs(np.linalg.eigvals(p.A)).max()
+    assert 0.99 < lam < 1.0       # open-loop stable => G = tE (linearMPC.py:374-382, :481)
+
+
+# ----------------------------------------------------------------------------- oracle solvers
+def test_box_qp_exact_and_lqr_identity(cstrs_problem):
+    p = cstrs_problem
+    reg = om.setup_regulator(p.A, p.B, p.Q, p.R, p.S, 30, p.ulb, p.uub)
+    rng = np.random.default_rng(0)
+    n = reg.P.shape[0]
+    for scale in (1e-3, 0.3, 3.0):
+        x0 = scale * rng.standard_normal((reg.Nx, 1))
+        u, info = reg.solve(x0, return_info=True)
+        assert info["kkt"] <= 1e-11
+        if info["n_active"] == 0:                                  # terminal cost = DARE => LQR law
+            assert np.allclose(u[:reg.Nu], reg.Krep @ x0, atol=1e-11)
+    # tiny x0 is always unconstrained
+    x0 = 1e-4 * rng.standard_normal((reg.Nx, 1))
+    u = reg.solve(x0)
+    assert np.allclose(u[:reg.Nu], reg.Krep @ x0, rtol=1e-9, atol=1e-15)
+
+
+def test_ipm_matches_exact_solver():
+    rng = np.random.default_rng(1)
+    n = 40
+    Mx = rng.standard_normal((n, n))
+    P = Mx @ Mx.T + 0.1 * np.eye(n)
+    q = 3 * rng.standard_normal(n)
+    lb, ub = -0.5 * np.ones(n), 0.7 * np.ones(n)
+    u, info = oq.BoxQP(P).solve(q, lb, ub)
+    assert info["kkt"] < 1e-12 and info["n_active"] > 0
+    G = np.vstack([np.eye(n), -np.eye(n)])
+    h = np.concatenate([ub, -lb])
+    x1, i1 = oq.ipm_qp(P, q, G, h)
+    x2, i2 = oq.ipm_qp(P, q, None, h, diagonal_G=True)
+    assert i1["status"] == "optimal" and i2["status"] == "optimal"
+    assert np.allclose(x1[:, 0], u, atol=1e-5) and np.allclose(x2[:, 0], u, atol=1e-5)
+    x3, _ = oq.solve_general_qp(P, q, G, h)
+    assert np.allclose(x3[:, 0], u, atol=1e-9)
+
+
+@pytest.mark.parametrize("which", ["cstrs", "cdu_small"])
+def test_target_selector_oracle_full_vs_reduced(which, cstrs_problem, cdu_small_problem):
+    p = cstrs_problem if which == "cstrs" else cdu_small_problem
+    ts = om.TargetSelectorOracle(A=p.A, B=p.B, C=p.C, H=p.H, Bd=p.Bd, Cd=p.Cd, usp=p.usp, Rs=p.Rs, Qs=p.Qs,
+                                 ulb=p.ulb, uub=p.uub)
+    for t in (0, 500, 5000, 20000):
+        ysp, d = p.setpoints[t][:, None], p.disturbances[t][:, None]
+        (xs, us), info = ts.solve(ysp, d, return_info=True)
+        assert info["eq_res"] < 1e-10
+        assert np.all(us >= p.ulb - 1e-12) and np.all(us <= p.uub + 1e-12)
+        q, _, b = ts.changing(ysp, d)
+        nx = p.Nx
+        lb = np.concatenate([np.full(nx, -np.inf), p.ulb[:, 0]])
+        ub = np.concatenate([np.full(nx, np.inf), p.uub[:, 0]])
+        w2, _ = oq._eq_box_reduced(ts.P, q[:, 0], ts.tA, b[:, 0], lb, ub)
+        c1 = 0.5 * np.vstack([xs, us]).T @ ts.P @ np.vstack([xs, us]) + q.T @ np.vstack([xs, us])
+        c2 = 0.5 * w2.T @ ts.P @ w2 + q.T @ w2
+        assert abs(c1.item() - c2.item()) <= 1e-9 * max(1.0, abs(c1.item()))
