@@ -77,11 +77,11 @@ struct EpiStructOut {
     const double b1 = __shfl_xor_sync(0xffffffffu, a1, 4);
     if ((pr & 1) || !ok0) return;
     const long long b = pr >> 1;
-    double v0 = p.us[b * p.nu + col] + a0 - b0;
+    double v0 = p.us[b * p.nu + col] + (a0 - b0);   // us + (out1 - out2), the reference order (:58-60)
     if (p.ulb) v0 = fmin(fmax(v0, p.ulb[col]), p.uub[col]);
     p.out[b * p.nu + col] = v0;
     if (ok1) {
-      double v1 = p.us[b * p.nu + col + 1] + a1 - b1;
+      double v1 = p.us[b * p.nu + col + 1] + (a1 - b1);
       if (p.ulb) v1 = fmin(fmax(v1, p.ulb[col + 1]), p.uub[col + 1]);
       p.out[b * p.nu + col + 1] = v1;
     }
@@ -192,6 +192,7 @@ int nnmpc_mlp_destroy(nnmpc_mlp_t* h) {
 int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev, const double* xs,
                       const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
                       void* stream) {
+  if (B == 0 && h) return 0;
   if (!h || !x || !xs || !us || !out) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: null argument");
   if (h->with_uprev && !uprev) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: uprev required");
   if ((ulb == nullptr) != (uub == nullptr)) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: ulb/uub both or none");
@@ -202,6 +203,7 @@ int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double
 
 int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev, const double* xs,
                            const double* us, const double* xscale, const double* ulb, const double* uub, double* out) {
+  if (B == 0 && h) return 0;
   if (!h || !x || !xs || !us || !out) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward_host: null argument");
   if (h->with_uprev && !uprev) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward_host: uprev required");
   if ((ulb == nullptr) != (uub == nullptr))

@@ -329,6 +329,7 @@ int nnmpc_qp_destroy(nnmpc_qp_t* h) {
 int nnmpc_qp_solve(nnmpc_qp_t* h, int B, const double* x0, const double* lb, const double* ub, double* u,
                    double* v_state, int warm, double* cost, double* kkt, int* iters, double tol, int max_iter,
                    void* stream) {
+  if (B == 0 && h) return 0;
   if (!h || !x0 || !lb || !ub || !u) return set_error(NNMPC_ERR_BADARG, "nnmpc_qp_solve: null argument");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_qp_solve: negative batch");
   DeviceGuard dg(h->device);
@@ -338,6 +339,7 @@ int nnmpc_qp_solve(nnmpc_qp_t* h, int B, const double* x0, const double* lb, con
 
 int nnmpc_qp_solve_host(nnmpc_qp_t* h, int B, const double* x0, const double* lb, const double* ub, double* u,
                         double* cost, double* kkt, int* iters, double tol, int max_iter) {
+  if (B == 0 && h) return 0;
   if (!h || !x0 || !lb || !ub || !u) return set_error(NNMPC_ERR_BADARG, "nnmpc_qp_solve_host: null argument");
   if (B <= 0) return B == 0 ? 0 : set_error(NNMPC_ERR_BADARG, "nnmpc_qp_solve_host: negative batch");
   DeviceGuard dg(h->device);

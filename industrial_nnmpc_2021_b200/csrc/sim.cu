@@ -183,6 +183,7 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, const double* setpoints,
                   const double* disturbances, double* x, double* uprev, double* xs, double* us, double* u, int* iters,
                   double* kkt, double tol, int max_iter, void* stream) {
+  if ((B == 0 || T == 0) && h) return 0;
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: null argument");
   if (B < 0 || T < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: negative size");
@@ -194,6 +195,7 @@ int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, 
 int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, const double* setpoints,
                        const double* disturbances, double* x, double* uprev, double* xs, double* us, double* u,
                        int* iters, double* kkt, double tol, int max_iter) {
+  if ((B == 0 || T == 0) && h) return 0;
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: null argument");
   if (B <= 0 || T <= 0) return (B == 0 || T == 0) ? 0 : set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: negative size");

@@ -265,6 +265,7 @@ int nnmpc_ts_destroy(nnmpc_ts_t* h) {
 
 int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride, const double* d,
                    long long d_stride, double* xs, double* us, int* iters, void* stream) {
+  if (B == 0 && h) return 0;
   if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: null argument");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: negative batch");
   DeviceGuard dg(h->device);
@@ -274,6 +275,7 @@ int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride
 
 int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d, double* xs, double* us,
                         int* iters) {
+  if (B == 0 && h) return 0;
   if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve_host: null argument");
   if (B <= 0) return B == 0 ? 0 : set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve_host: negative batch");
   DeviceGuard dg(h->device);
