@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Headline benchmark: CDU linear-MPC closed-loop offline data generation (BASELINE.json metric
+"CDU linear-MPC QP solves/sec & sim-steps/sec at 1/2/4/8 B200 vs host-CPU ref").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
+
+Workload (config 3 of BASELINE.json): the crude-distillation linear MPC of the reference
+(252 states, 32 inputs, 90 outputs, horizon N = 140 -> 4480 decision variables per QP,
+cdu_parameters.py:94-102) on the documented synthetic stand-in plant (CDU_Model.mat is not shipped),
+driven by PRBS set-point/disturbance signals with the reference's statistics
+(cdu_parameters.py:115-143).  `--traj` independent closed-loop trajectories per GPU (the reference's
+OS processes, lib/linearMPC.py:786-825) advance together; one bench "step" advances every
+trajectory by `--slab` simulation steps: target-selector QP -> regulator QP -> plant step
+(lib/linearMPC.py:845-866), i.e. traj x slab samples of the training set per GPU per step.
+
+Numbers on the JSON line
+  value       closed-loop sim-steps/s (= regulator QP solves/s; each sim step also solves one
+              target-selector QP), all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e         same metric through the reference-facing host API (ClosedLoopEngine.run with NumPy
+              arrays in pinned host memory -> nnmpc_sim_run_host): host->device copies of the
+              slab's set-points/disturbances and device->host copies of the generated dataset
+              rows are inside the timed region
+  roofline    the regulator-QP iteration GEMM (FP64 tensor cores), timed live with CUDA events
+  cpu_baseline  the reference-style CPU path (oracle port: cvxopt-like dense interior point) timed
+              on this host on a bounded sample
+The reference arm (--impl reference) times that same CPU path with every host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cdu_closed_loop_sim_steps_per_s"
+UNIT = "sim-steps/s"
+KKT_TOL = 1e-8
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thr.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _scenarios(traj, steps, seed):
+    """PRBS-like set-points / disturbances with the reference's hold statistics, split into `traj`
+    contiguous chunks of `steps` rows (lib/linearMPC.py:786-801) -> (traj, steps, .) arrays."""
+    from industrial_nnmpc_2021_b200.plants import get_cdu_problem
+    p = get_cdu_problem(Nsim=traj * steps, seed=seed)
+    sp = p.setpoints.reshape(traj, steps, p.Ny)
+    ds = p.disturbances.reshape(traj, steps, p.Nd)
+    return p, sp, ds
+
+
+# ------------------------------------------------------------------------------------------ CPU path
+def _cpu_worker(args):
+    """One reference-style process: closed-loop steps of one trajectory on the CPU, every QP by
+    the cvxopt-like dense interior point (oracle.qp.ipm_qp), operators re-materialised per call as
+    the reference does (lib/linearMPC.py:15-20, :503)."""
+    seed, nsteps, threads, horizon = args
+    import threadpoolctl
+    import scipy.linalg
+    from oracle import linear_mpc as om, qp as oq
+    from industrial_nnmpc_2021_b200 import condense
+    with threadpoolctl.threadpool_limits(limits=threads):
+        p, sp, ds = _scenarios(1, max(nsteps, 4000), seed)
+        Aa, Ba, Qa, Ra, Ma = om.augmented_matrices_for_regulator(p.A, p.B, p.Q, p.R, p.S)
+        _, Pf = om.dlqr(Aa, Ba, Qa, Ra, Ma)
+        P, tq = condense.condensed_hessian(Aa, Ba, Qa, Ra, Ma, Pf, horizon)   # setup, untimed
+        E = np.vstack([np.eye(p.Nu), -np.eye(p.Nu)])
+        G = scipy.linalg.block_diag(*([E] * horizon))                          # dense tE (:459-460)
+        ots = om.TargetSelectorOracle(A=p.A, B=p.B, C=p.C, H=p.H, Bd=p.Bd, Cd=p.Cd, usp=p.usp, Rs=p.Rs,
+                                      Qs=p.Qs, ulb=p.ulb, uub=p.uub)
+        x, up = p.xprior.copy(), p.uprev.copy()
+        iters, t0 = [], time.time()
+        for t in range(nsteps):
+            ysp, d = sp[0, t][:, None], ds[0, t][:, None]
+            xs, us = ots.solve(ysp, d)
+            x0 = np.vstack([x - xs, up - us])
+            h = np.tile(np.vstack([p.uub - us, -(p.ulb - us)]), (horizon, 1))
+            useq, info = oq.ipm_qp(P, tq @ x0, G, h)
+            iters.append(info["iters"])
+            u = useq[:p.Nu] + us
+            x = p.A @ x + p.B @ u + p.Bd @ d
+            up = u
+        return t0, time.time(), iters
+
+
+def cpu_reference_rate(nsteps, horizon=140, seed=11):
+    """sim-steps/s of the CPU path using every host core: `workers` processes (the reference's
+    num_parallel) x `threads` BLAS threads each."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    threads = min(cores, 8)
+    mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2**30
+    workers = max(1, min(cores // threads, int(mem_gb // 4), 32))
+    t0 = time.perf_counter()
+    if workers == 1:
+        res = [_cpu_worker((seed, nsteps, threads, horizon))]
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            res = pool.map(_cpu_worker, [(seed + 2 * w, nsteps, threads, horizon) for w in range(workers)])
+    wall = time.perf_counter() - t0
+    loop = max(r[1] for r in res) - min(r[0] for r in res)   # first loop start -> last loop end (setup excluded)
+    rate = workers * nsteps / loop
+    iters = [i for r in res for i in r[2]]
+    info = dict(cores=workers * threads, workers=workers, threads_per_worker=threads, host_cores=cores,
+                sample=f"{workers} trajectories x {nsteps} closed-loop steps (CDU, N={horizon}, n={horizon * 32}), "
+                       f"cold-start dense interior point per QP, mean {np.mean(iters):.1f} IPM iterations",
+                seconds_per_qp=loop / nsteps, loop_s=loop, wall_s=wall)
+    return rate, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r, info = cpu_reference_rate(args.ref_steps, horizon=args.horizon)
+    runs = [r]
+    # keep the whole arm within a few minutes whatever the host: as many of the W+K runs as fit in 240 s
+    total = min(args.warmup + args.steps, max(1, int(240 // max(info["wall_s"], 1e-3))))
+    for _ in range(total - 1):
+        r, info = cpu_reference_rate(args.ref_steps, horizon=args.horizon)
+        runs.append(r)
+    rates = runs[min(args.warmup, total - 1):]
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(rates), "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_steps * info["workers"] / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(args, info["workers"], args.ref_steps),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                         "sample": info["sample"], "seconds_per_qp": info["seconds_per_qp"],
+                         "host_cores": info["host_cores"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CPU path = oracle port of lib/linearMPC.py simulate_offline with a cvxopt-like dense "
+                "interior point (cvxopt itself is not installable here); paper: 35 s/QP, 3.57 steps/s on 149 procs",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(args, traj, slab):
+    return {"workload": "CDU linear-MPC closed-loop offline data generation (BASELINE.json configs[2]): synthetic "
+                        "CDU stand-in 252x32x90, reference tuning, PRBS scenarios",
+            "Nx": 252, "Nu": 32, "Ny": 90, "horizon": args.horizon, "qp_vars": args.horizon * 32,
+            "trajectories_per_gpu": traj, "sim_steps_per_step": slab, "tol_kkt": KKT_TOL,
+            "l2": "no flush: operators (2 x 161 MB) + solver state exceed the 126 MB L2 every iteration",
+            "parallelism": f"trajectories sharded over {args.gpus} GPU(s), no collective on the solve path"}
+
+
+# ------------------------------------------------------------------------------------------ GPU path
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        from industrial_nnmpc_2021_b200 import build
+        build.build()
+    if world > 1:
+        dist.barrier()
+    from industrial_nnmpc_2021_b200 import _lib
+    from industrial_nnmpc_2021_b200.linearMPC import LinearMPCController, ClosedLoopEngine
+    L = _lib.lib()
+
+    K, W, B, Ts = args.steps, max(args.warmup, 3), args.traj, args.slab
+    nslab = 2 * (W + K)                      # device-resident phase, then the end-to-end phase
+    p, sp, ds = _scenarios(B, nslab * Ts, seed=101 + 2 * rank)
+    if args.horizon != p.N:
+        p.N = args.horizon
+    t_setup = time.perf_counter()
+    ts = LinearMPCController.setup_target_selector(p.A, p.B, p.C, p.H, p.Bd, p.Cd, p.usp, p.Qs, p.Rs, p.ulb, p.uub,
+                                                   device=dev)
+    reg = LinearMPCController.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub, device=dev)
+    eng = ClosedLoopEngine(reg, ts, p.A, p.B, p.Bd)
+    t_setup = time.perf_counter() - t_setup
+    n, nx, nu, ny, nd = p.N * p.Nu, p.Nx, p.Nu, p.Ny, p.Nd
+
+    f64 = dict(dtype=torch.float64, device=dev)
+    slabs = [(torch.tensor(np.ascontiguousarray(sp[:, i * Ts:(i + 1) * Ts]), **f64),
+              torch.tensor(np.ascontiguousarray(ds[:, i * Ts:(i + 1) * Ts]), **f64)) for i in range(W + K)]
+    out_d = dict(x=torch.empty((B, Ts, nx), **f64), uprev=torch.empty((B, Ts, nu), **f64),
+                 xs=torch.empty((B, Ts, nx), **f64), us=torch.empty((B, Ts, nu), **f64),
+                 u=torch.empty((B, Ts, nu), **f64), iters=torch.empty((B, Ts), dtype=torch.int32, device=dev),
+                 kkt=torch.empty((B, Ts), **f64))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxrank(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], **f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident phase -------------------------------------------------------------
+    x, up = p.xprior, p.uprev
+    hit = False
+    kkt_acc = torch.zeros((), **f64)
+    it_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    it_acc = torch.zeros((), dtype=torch.int32, device=dev)
+    for i in range(W):
+        r = eng.run(x, up, *slabs[i], resume=i > 0, out=out_d)
+        x, up = r["x_final"], r["uprev_final"]
+    barrier()
+    _lib.prof_enable(True)
+    _lib.prof_read(reset=True)
+    launches0 = L.nnmpc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for i in range(W, W + K):
+            r = eng.run(x, up, *slabs[i], resume=True, out=out_d)
+            x, up = r["x_final"], r["uprev_final"]
+            hit |= bool(r["maxiter_hit"])
+            # validity of the timed work itself (device-side reductions, read after the timing)
+            kkt_acc = torch.maximum(kkt_acc, r["kkt"].max())
+            it_sum = it_sum + r["iters"].sum(dtype=torch.int64)
+            it_acc = torch.maximum(it_acc, r["iters"].max())
+        ev1.record()
+        barrier()
+    ms_dev = maxrank(ev0.elapsed_time(ev1))
+    launches = L.nnmpc_launch_count() - launches0
+    gemm_ms, gemm_flops, gemm_launches = _lib.prof_read(reset=True)
+    _lib.prof_enable(False)
+    kkt_max, it_sum, it_max = float(kkt_acc), int(it_sum), int(it_acc)
+    clocks = clk.summary()
+    value = world * B * Ts * K / (ms_dev * 1e-3)
+
+    # ---- end-to-end phase: host buffers through the reference-facing API -----------------
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+    out_h = dict(x=pinned((B, Ts, nx)), uprev=pinned((B, Ts, nu)), xs=pinned((B, Ts, nx)), us=pinned((B, Ts, nu)),
+                 u=pinned((B, Ts, nu)), iters=pinned((B, Ts), torch.int32), kkt=pinned((B, Ts)))
+    sp_h, ds_h = pinned((B, Ts, ny)), pinned((B, Ts, nd))
+    xh, uph = x.cpu().numpy(), up.cpu().numpy()
+    e2e_kkt = 0.0
+    barrier()
+    t_e2e = None
+    for i in range(W + K, 2 * (W + K)):
+        if i == 2 * W + K:
+            barrier()
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            t_e2e = time.perf_counter()
+        sp_h[...] = sp[:, i * Ts:(i + 1) * Ts]          # this step's inputs staged in pinned host memory
+        ds_h[...] = ds[:, i * Ts:(i + 1) * Ts]
+        r = eng.run(xh, uph, sp_h, ds_h, resume=True, out=out_h)
+        xh, uph = r["x_final"], r["uprev_final"]
+        e2e_kkt = max(e2e_kkt, float(out_h["kkt"].max()))      # the device->host result is read every step
+        hit |= bool(r["maxiter_hit"])
+    ee1.record()
+    barrier()
+    wall_e2e = time.perf_counter() - t_e2e
+    ms_e2e = maxrank(max(ee0.elapsed_time(ee1), 1e3 * wall_e2e))
+    e2e_value = world * B * Ts * K / (ms_e2e * 1e-3)
+    h2d = (sp_h.nbytes + ds_h.nbytes + xh.nbytes + uph.nbytes) * world
+    d2h = (sum(v.nbytes for v in out_h.values()) + xh.nbytes + uph.nbytes) * world
+
+    if kkt_max > KKT_TOL or e2e_kkt > KKT_TOL or hit:
+        raise SystemExit(f"bench.py: timed solves missed the tolerance (kkt {kkt_max:.2e}/{e2e_kkt:.2e}, "
+                         f"maxiter_hit={hit}); number rejected")
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks, peak_src = _peaks()
+    a = torch.randn((6144, 6144), **f64); b = torch.randn((6144, 6144), **f64)
+    for _ in range(3):
+        torch.matmul(a, b)
+    best = 0.0
+    for _ in range(5):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(); torch.matmul(a, b); g1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * 6144 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12)
+    del a, b
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAdmm> (regulator-QP iteration, FP64 DMMA)",
+                "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+                "traffic": None, "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+                "share_of_step": gemm_ms / (ms_dev if world == 1 else ev0.elapsed_time(ev1)),
+                "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (FP64 has no tcgen05 kind; "
+                               f"MEASURED_PEAKS.json carries bf16 {peaks.get('bf16_tflops')} TF/s and HBM "
+                               f"{peaks.get('hbm_gbs')} GB/s only, {peak_src})",
+                "flops_per_launch": "active samples x 2 n^2 (n = 4480: 40.14 MFLOP per sample-iteration)"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, info = cpu_reference_rate(1, horizon=args.horizon)
+            cpu = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                   "seconds_per_qp": info["seconds_per_qp"], "host_cores": info["host_cores"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": _config(args, B, Ts),
+            "qp_solves_per_s": {"regulator": value, "target_selector": value},
+            "iterations": {"mean": it_sum / (B * Ts * K), "max": it_max, "kkt_max": kkt_max},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K, "kkt_max": e2e_kkt},
+            "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--traj", type=int, default=1024, help="closed-loop trajectories per GPU")
+    ap.add_argument("--slab", type=int, default=4, help="simulation steps every trajectory advances per bench step")
+    ap.add_argument("--horizon", type=int, default=140)
+    ap.add_argument("--ref-steps", type=int, default=1, help="closed-loop steps per worker per reference step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,13 @@ const char* nnmpc_last_error(void);
 long long nnmpc_launch_count(void);
 /* sum over all solved samples of the Douglas-Rachford iterations they used (for flop accounting) */
 long long nnmpc_iteration_count(void);
+/* Live timing of the dominant kernel (the regulator-QP iteration GEMM) for bench.py's roofline:
+ * when enabled, every group of back-to-back iteration launches is bracketed by CUDA events on the
+ * stream it is launched on.  nnmpc_prof_read synchronises those events and returns the summed
+ * device time [ms], the algorithmic flops (active samples x 2 n^2 per launch) and the number of
+ * launches since the last reset.  Disabled by default (no events are recorded). */
+int nnmpc_prof_enable(int on);
+int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset);
 
 /* ---- regulator QP:  DenseQPRegulator (lib/linearMPC.py:321-517) -------------------------------
  *   min_u 1/2 u'Pu + (tq x0)'u   s.t.  lb <= u_k <= ub  for every stage k     (box path, :481)
@@ -90,18 +97,21 @@ int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d
  * Inputs  setpoints dev [B][T][ny], disturbances dev [B][T][nd]  (chunk-major, as _split_scenarios)
  * Outputs x,xs dev [B][T][nx]; uprev,us,u dev [B][T][nu]  (row t = state BEFORE step t, :868-872)
  *         iters dev [B][T] int, kkt dev [B][T] (nullable)
- *   x_io, uprev_io dev B x nx / B x nu: in = initial state (:837-838), out = state after T steps */
+ *   x_io, uprev_io dev B x nx / B x nu: in = initial state (:837-838), out = state after T steps
+ *   resume != 0: the call continues the SAME B trajectories as the previous call on this handle
+ *   (long trajectories advanced in slabs); the solver then warm-starts step 0 from the state it
+ *   kept.  It only changes iteration counts, never which optimum is returned. */
 int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, int nu, int nd,
                      int ny, const double* ABd_host, int device);
 int nnmpc_sim_destroy(nnmpc_sim_t* h);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                   const double* setpoints, const double* disturbances, double* x, double* uprev,
                   double* xs, double* us, double* u, int* iters, double* kkt, double tol,
-                  int max_iter, void* stream);
+                  int max_iter, int resume, void* stream);
 int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                        const double* setpoints, const double* disturbances, double* x, double* uprev,
                        double* xs, double* us, double* u, int* iters, double* kkt, double tol,
-                       int max_iter);
+                       int max_iter, int resume);
 
 /* ---- structured network: RegulatorLayerWithUprev / WithoutUprev (lib/LinearMPCLayers.py:15-115)
  * and its NumPy deployment form NeuralNetworkController (lib/controller_evaluation.py:863-892).

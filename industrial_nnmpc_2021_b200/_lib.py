@@ -24,6 +24,8 @@ SIGNATURES = {
     "nnmpc_last_error": (C.c_char_p, []),
     "nnmpc_launch_count": (C.c_longlong, []),
     "nnmpc_iteration_count": (C.c_longlong, []),
+    "nnmpc_prof_enable": (C.c_int, [C.c_int]),
+    "nnmpc_prof_read": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "nnmpc_qp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                   C.c_double, C.c_int]),
     "nnmpc_qp_destroy": (C.c_int, [vp]),
@@ -37,9 +39,9 @@ SIGNATURES = {
     "nnmpc_sim_create": (C.c_int, [C.POINTER(vp), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
     "nnmpc_sim_destroy": (C.c_int, [vp]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
-                                C.c_int, vp]),
+                                C.c_int, C.c_int, vp]),
     "nnmpc_sim_run_host": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
-                                     C.c_int]),
+                                     C.c_int, C.c_int]),
     "nnmpc_mlp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(vp),
                                    C.POINTER(vp), C.c_int]),
     "nnmpc_mlp_destroy": (C.c_int, [vp]),
@@ -100,6 +102,18 @@ def dptr(t):
     if not t.is_cuda or not t.is_contiguous():
         raise NnmpcError("expected a contiguous CUDA tensor")
     return vp(t.data_ptr())
+
+
+def prof_enable(on=True):
+    """Switch the live CUDA-event timing of the iteration GEMM on/off (bench.py roofline)."""
+    check(lib().nnmpc_prof_enable(int(bool(on))), "nnmpc_prof_enable")
+
+
+def prof_read(reset=True):
+    """(device ms, algorithmic flops, launches) of the iteration GEMM since the last reset."""
+    ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+    check(lib().nnmpc_prof_read(C.byref(ms), C.byref(fl), C.byref(n), int(bool(reset))), "nnmpc_prof_read")
+    return ms.value, fl.value, n.value
 
 
 def stream_ptr():

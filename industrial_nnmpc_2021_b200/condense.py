@@ -101,23 +101,24 @@ def prediction_matrices(A, B, N):
     return tA, tB
 
 
-def extreme_eigs(P, cho=None, iters=200, seed=0):
-    """(lambda_min, lambda_max) of a symmetric positive definite matrix by (inverse) power
-    iteration; cheap relative to a full eigendecomposition at n = 4480."""
+def extreme_eigs(P, cho=None, seed=0):
+    """(lambda_min, lambda_max) of a symmetric positive definite matrix: Lanczos on P for the
+    largest and on P^-1 (two triangular solves with the Cholesky factor per apply) for the
+    smallest eigenvalue; ~1 s at n = 4480 against ~20 s for a full eigendecomposition."""
     n = P.shape[0]
     if n <= 1024:
         w = np.linalg.eigvalsh(P)
         return float(w[0]), float(w[-1])
-    rng = np.random.default_rng(seed)
-    v = rng.standard_normal(n)
-    for _ in range(iters):
-        v = P @ v
-        v /= np.linalg.norm(v)
-    lmax = float(v @ (P @ v))
-    cho = scipy.linalg.cho_factor(P, lower=True) if cho is None else cho
-    v = rng.standard_normal(n)
-    for _ in range(iters):
-        v = scipy.linalg.cho_solve(cho, v)
-        v /= np.linalg.norm(v)
-    lmin = float(v @ (P @ v))
-    return lmin, lmax
+    import scipy.sparse.linalg as sla
+    v0 = np.random.default_rng(seed).standard_normal(n)
+    lmax = float(sla.eigsh(P, k=1, which="LA", v0=v0, tol=1e-3, return_eigenvectors=False)[0])
+    cho = scipy.linalg.cho_factor(P, lower=True, check_finite=False) if cho is None else cho
+    L = np.tril(cho[0]) if cho[1] else np.triu(cho[0]).T
+
+    def pinv_apply(x):
+        y = scipy.linalg.solve_triangular(L, x, lower=True, check_finite=False)
+        return scipy.linalg.solve_triangular(L, y, lower=True, trans="T", check_finite=False)
+
+    op = sla.LinearOperator((n, n), matvec=pinv_apply, dtype=np.float64)
+    imax = float(sla.eigsh(op, k=1, which="LA", v0=v0, tol=1e-3, maxiter=2000, return_eigenvectors=False)[0])
+    return 1.0 / imax, lmax

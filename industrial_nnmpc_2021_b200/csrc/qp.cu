@@ -15,12 +15,42 @@
 // is verified with the true Hessian, g = P z + q (one more GEMM, epilogue reduces
 // ||z - clip(z - g)||_inf and the cost per sample); samples that pass leave the active row list.
 #include "qp.cuh"
+#include <mutex>
+#include <vector>
 
 namespace nnmpc {
 
 thread_local char g_last_error[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_iterations{0};
+
+// ---- live timing of the iteration GEMM (bench.py roofline) ------------------------------------
+struct ProfSpan { cudaEvent_t a, b; double flops; long long launches; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof_spans;   // recorded since the last reset
+static std::vector<ProfSpan> g_prof_pool;    // events to reuse
+
+static bool prof_begin(ProfSpan* sp, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return false;
+  if (!g_prof_pool.empty()) {
+    *sp = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else if (cudaEventCreate(&sp->a) != cudaSuccess || cudaEventCreate(&sp->b) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaEventRecord(sp->a, st);
+  return true;
+}
+static void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches) {
+  cudaEventRecord(sp.b, st);
+  sp.flops = flops;
+  sp.launches = launches;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_spans.push_back(sp);
+}
 
 // ------------------------------------------------------------------------------------ epilogues
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -238,12 +268,15 @@ int qp_solve_device(nnmpc_qp* h, int B, const double* x0, const double* lb, cons
     ++chunk_idx;
     GemmOperands gi{};
     gi.lda = n; gi.Bt = h->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = rows_c; gi.m_count = cnt_c;
+    ProfSpan span;
+    const bool prof = prof_begin(&span, st);
     for (int k = 0; k < chunk; ++k) {
       gi.A = Wc;
       EpiAdmm::Params ep{V, h->C.p, Wn, u, lb, ub, n, nu, h->alpha, k == chunk - 1 ? 1 : 0};
       NNMPC_TRY(gemm_auto<EpiAdmm>(gi, ep, st));
       double* t = Wc; Wc = Wn; Wn = t;
     }
+    if (prof) prof_end(span, st, 2.0 * n * (double)n * active * chunk, chunk);
     it += chunk;
     // verify with the true Hessian: g = P z + q
     GemmOperands gv = gi;
@@ -283,6 +316,34 @@ int nnmpc_version(void) { return 100; }
 const char* nnmpc_last_error(void) { return g_last_error; }
 long long nnmpc_launch_count(void) { return g_launches.load(); }
 long long nnmpc_iteration_count(void) { return g_iterations.load(); }
+
+int nnmpc_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t = 0.0, f = 0.0;
+  long long l = 0;
+  for (const ProfSpan& sp : g_prof_spans) {
+    float e = 0.f;
+    if (cudaEventSynchronize(sp.b) != cudaSuccess || cudaEventElapsedTime(&e, sp.a, sp.b) != cudaSuccess)
+      return set_error(NNMPC_ERR_CUDA, "nnmpc_prof_read: %s", cudaGetErrorString(cudaGetLastError()));
+    t += e;
+    f += sp.flops;
+    l += sp.launches;
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (launches) *launches = l;
+  if (reset) {
+    for (const ProfSpan& sp : g_prof_spans) g_prof_pool.push_back(sp);
+    g_prof_spans.clear();
+  }
+  return 0;
+}
 
 int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N, const double* P_host, const double* tq_host,
                     const double* Top_host, const double* Mtq_host, const double* Kunc_host, double alpha,

@@ -20,6 +20,8 @@ struct nnmpc_sim {
   int nxa_ld;    // = qp->nxa
   double* ABd;   // device nx x kin_ld
   long long cap;
+  long long warm_B;   // batch size whose solver state (Va/Vb, us_prev) is valid for `resume`; 0 = none
+  double* warm_V;     // which of Va/Vb holds it
   nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, Va, Vb, U, xin, xcur, upcur;
   // staging for the host entry point
   nnmpc::DevBuf<double> h_sp, h_dist, h_x, h_uprev, h_xs, h_us, h_u, h_kkt, h_xio, h_upio;
@@ -82,22 +84,25 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
   NNMPC_TRY(h->xcur.ensure(B * h->nx));
   NNMPC_TRY(h->upcur.ensure(B * h->nu));
   h->cap = B;
+  h->warm_B = 0;
   return 0;
 }
 
 static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* uprev_io, const double* sp,
                           const double* dist, double* ox, double* ouprev, double* oxs, double* ous, double* ou,
-                          int* oiters, double* okkt, double tol, int max_iter, cudaStream_t st) {
+                          int* oiters, double* okkt, double tol, int max_iter, int resume, cudaStream_t st) {
   if (B <= 0 || T <= 0) return 0;
   NNMPC_TRY(sim_ensure(h, B));
+  const bool cont = resume && h->warm_B == B;
+  h->warm_B = 0;
   const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = h->qp->n;
   const long long sx = (long long)T * nx, su = (long long)T * nu;
   int rc_warn = 0;
   NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
-  NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
-  double* Vold = h->Va.p;
-  double* Vnew = h->Vb.p;
+  if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
+  double* Vold = cont ? h->warm_V : h->Va.p;
+  double* Vnew = Vold == h->Va.p ? h->Vb.p : h->Va.p;
   const int ew_blocks = 148 * 16;
   for (int t = 0; t < T; ++t) {
     TsFused F{};
@@ -109,7 +114,7 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
                               (long long)T * nd, oxs + (long long)t * nx, sx, ous + (long long)t * nu, su, nullptr, 0,
                               &F, st));
     int warm = 0;
-    if (t > 0) {
+    if (t > 0 || cont) {
       k_warm_shift<<<ew_blocks, 256, 0, st>>>(Vold, Vnew, h->dus.p, (long long)B * n, n, nu);
       count_launch();
       warm = 1;
@@ -129,6 +134,8 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   NNMPC_CUDA(cudaMemcpyAsync(x_io, h->xcur.p, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(uprev_io, h->upcur.p, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaGetLastError());
+  h->warm_B = B;
+  h->warm_V = Vold;   // after the final swap: the state the last solve left behind
   return rc_warn;
 }
 
@@ -153,6 +160,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   const int kin = nx + nu + nd;
   h->kin_ld = (kin + 1) & ~1;
   h->cap = 0;
+  h->warm_B = 0;
+  h->warm_V = nullptr;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
   double* tmp = new (std::nothrow) double[(size_t)nx * h->kin_ld];
   if (!tmp) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
@@ -182,19 +191,19 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
 
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, const double* setpoints,
                   const double* disturbances, double* x, double* uprev, double* xs, double* us, double* u, int* iters,
-                  double* kkt, double tol, int max_iter, void* stream) {
+                  double* kkt, double tol, int max_iter, int resume, void* stream) {
   if ((B == 0 || T == 0) && h) return 0;
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: null argument");
   if (B < 0 || T < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: negative size");
   DeviceGuard dg(h->device);
   return sim_run_device(h, B, T, x_io, uprev_io, setpoints, disturbances, x, uprev, xs, us, u, iters, kkt, tol,
-                        max_iter, (cudaStream_t)stream);
+                        max_iter, resume, (cudaStream_t)stream);
 }
 
 int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, const double* setpoints,
                        const double* disturbances, double* x, double* uprev, double* xs, double* us, double* u,
-                       int* iters, double* kkt, double tol, int max_iter) {
+                       int* iters, double* kkt, double tol, int max_iter, int resume) {
   if ((B == 0 || T == 0) && h) return 0;
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: null argument");
@@ -219,7 +228,7 @@ int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev
   NNMPC_CUDA(cudaMemcpyAsync(h->h_xio.p, x_io, (size_t)B * nx * 8, cudaMemcpyHostToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->h_upio.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyHostToDevice, st));
   int rc = sim_run_device(h, B, T, h->h_xio.p, h->h_upio.p, h->h_sp.p, h->h_dist.p, h->h_x.p, h->h_uprev.p, h->h_xs.p,
-                          h->h_us.p, h->h_u.p, h->h_iters.p, h->h_kkt.p, tol, max_iter, st);
+                          h->h_us.p, h->h_u.p, h->h_iters.p, h->h_kkt.p, tol, max_iter, resume, st);
   if (rc < 0) return rc;
   NNMPC_CUDA(cudaMemcpyAsync(x, h->h_x.p, bt * nx * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(xs, h->h_xs.p, bt * nx * 8, cudaMemcpyDeviceToHost, st));

@@ -570,8 +570,25 @@ class ClosedLoopEngine:
         except Exception:
             pass
 
-    def run(self, x0, uprev0, setpoints, disturbances, *, tol=None, max_iter=None):
+    def _check_out(self, out, Bn, T, kind):
+        shapes = dict(x=(Bn, T, self.nx), uprev=(Bn, T, self.nu), xs=(Bn, T, self.nx), us=(Bn, T, self.nu),
+                      u=(Bn, T, self.nu), iters=(Bn, T), kkt=(Bn, T))
+        for k, shp in shapes.items():
+            a = out.get(k)
+            if not isinstance(a, kind) or tuple(a.shape) != shp:
+                raise ValueError(f"out[{k!r}] must be a {kind.__name__} of shape {shp}")
+            contiguous = a.flags["C_CONTIGUOUS"] if isinstance(a, np.ndarray) else a.is_contiguous()
+            if not contiguous:
+                raise ValueError(f"out[{k!r}] must be contiguous")
+        return {k: out[k] for k in shapes}
+
+    def run(self, x0, uprev0, setpoints, disturbances, *, tol=None, max_iter=None, resume=False, out=None):
         """Advance B trajectories T steps.
+
+        ``resume=True`` says these are the same B trajectories as in the previous call (a long
+        trajectory advanced slab by slab): step 0 is then warm-started from the kept solver
+        state.  ``out`` may hold preallocated result arrays (e.g. pinned host memory) under the
+        keys x, uprev, xs, us, u, iters, kkt.
 
         setpoints (B,T,Ny), disturbances (B,T,Nd); x0 (B,Nx), uprev0 (B,Nu) (or column vectors,
         broadcast to all trajectories).  NumPy in -> dict of NumPy arrays (host entry point, copies
@@ -588,13 +605,14 @@ class ClosedLoopEngine:
             sp, dist = _lib.host(setpoints), _lib.host(disturbances)
             xio = _lib.host(np.broadcast_to(np.asarray(x0, float).reshape(-1, nx), (Bn, nx))).copy()
             uio = _lib.host(np.broadcast_to(np.asarray(uprev0, float).reshape(-1, nu), (Bn, nu))).copy()
-            out = dict(x=np.empty((Bn, T, nx)), uprev=np.empty((Bn, T, nu)), xs=np.empty((Bn, T, nx)),
+            res = dict(x=np.empty((Bn, T, nx)), uprev=np.empty((Bn, T, nu)), xs=np.empty((Bn, T, nx)),
                        us=np.empty((Bn, T, nu)), u=np.empty((Bn, T, nu)), iters=np.empty((Bn, T), dtype=np.int32),
-                       kkt=np.empty((Bn, T)))
+                       kkt=np.empty((Bn, T))) if out is None else self._check_out(out, Bn, T, np.ndarray)
+            out = dict(res)
             rc = L.nnmpc_sim_run_host(self._handle, Bn, T, _lib.hptr(xio), _lib.hptr(uio), _lib.hptr(sp),
                                       _lib.hptr(dist), *[_lib.hptr(out[k]) for k in ("x", "uprev", "xs", "us", "u",
                                                                                       "iters", "kkt")],
-                                      float(tol), int(max_iter))
+                                      float(tol), int(max_iter), int(bool(resume)))
             out["maxiter_hit"] = _lib.check(rc, "nnmpc_sim_run_host")
         else:
             torch = _torch()
@@ -603,13 +621,15 @@ class ClosedLoopEngine:
             f64 = dict(dtype=torch.float64, device=dev)
             xio = torch.as_tensor(x0, **f64).reshape(-1, nx).expand(Bn, nx).contiguous().clone()
             uio = torch.as_tensor(uprev0, **f64).reshape(-1, nu).expand(Bn, nu).contiguous().clone()
-            out = dict(x=torch.empty((Bn, T, nx), **f64), uprev=torch.empty((Bn, T, nu), **f64),
+            res = dict(x=torch.empty((Bn, T, nx), **f64), uprev=torch.empty((Bn, T, nu), **f64),
                        xs=torch.empty((Bn, T, nx), **f64), us=torch.empty((Bn, T, nu), **f64),
                        u=torch.empty((Bn, T, nu), **f64),
-                       iters=torch.empty((Bn, T), dtype=torch.int32, device=dev), kkt=torch.empty((Bn, T), **f64))
+                       iters=torch.empty((Bn, T), dtype=torch.int32, device=dev),
+                       kkt=torch.empty((Bn, T), **f64)) if out is None else self._check_out(out, Bn, T, torch.Tensor)
+            out = dict(res)
             rc = L.nnmpc_sim_run(self._handle, Bn, T, _lib.dptr(xio), _lib.dptr(uio), _lib.dptr(sp), _lib.dptr(dist),
                                  *[_lib.dptr(out[k]) for k in ("x", "uprev", "xs", "us", "u", "iters", "kkt")],
-                                 float(tol), int(max_iter), _lib.stream_ptr())
+                                 float(tol), int(max_iter), int(bool(resume)), _lib.stream_ptr())
             out["maxiter_hit"] = _lib.check(rc, "nnmpc_sim_run")
         out["x_final"], out["uprev_final"] = xio, uio
         return out

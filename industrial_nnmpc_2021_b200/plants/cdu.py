@@ -109,9 +109,13 @@ def get_cdu_problem(*, N=140, Nsim=357600, seed=1, conservative_factor=1.05,
         sp_ub = (Hsel @ ub["y"]) * conservative_factor
         d_lb = (np.take(lb["u"], dist_idx) * dist_scaling * conservative_factor).reshape(-1, 1)
         d_ub = (np.take(ub["u"], dist_idx) * dist_scaling * conservative_factor).reshape(-1, 1)
-        sp = sample_prbs_like(num_change=894, num_steps=Nsim, lb=sp_lb, ub=sp_ub,
+        # the reference's 894 / 1788 change points over 357 600 steps (mean hold 400 / 200); other
+        # Nsim keep the same hold statistics
+        nch_sp = 894 if Nsim == 357600 else max(2, Nsim // 400)
+        nch_d = 1788 if Nsim == 357600 else max(2, Nsim // 200)
+        sp = sample_prbs_like(num_change=nch_sp, num_steps=Nsim, lb=sp_lb, ub=sp_ub,
                               mean_change=400, sigma_change=1, seed=seed)
         prob.setpoints = np.hstack([np.zeros((Nsim, Ny - NZ)), sp])
-        prob.disturbances = sample_prbs_like(num_change=1788, num_steps=Nsim, lb=d_lb, ub=d_ub,
+        prob.disturbances = sample_prbs_like(num_change=nch_d, num_steps=Nsim, lb=d_lb, ub=d_ub,
                                              mean_change=200, sigma_change=1, seed=seed + 1)
     return prob
