@@ -277,7 +277,7 @@ def run_native(args):
     it_sum = torch.zeros((), dtype=torch.int64, device=dev)
     it_acc = torch.zeros((), dtype=torch.int32, device=dev)
     for i in range(W):
-        r = eng.run(x, up, *slabs[i], resume=i > 0, out=out_d)
+        r = eng.run(x, up, *slabs[i], resume=i > 0, out=out_d, max_iter=args.max_iter)
         x, up = r["x_final"], r["uprev_final"]
     barrier()
     _lib.prof_enable(True)
@@ -287,7 +287,7 @@ def run_native(args):
     with ClockSampler(local) as clk:
         ev0.record()
         for i in range(W, W + K):
-            r = eng.run(x, up, *slabs[i], resume=True, out=out_d)
+            r = eng.run(x, up, *slabs[i], resume=True, out=out_d, max_iter=args.max_iter)
             x, up = r["x_final"], r["uprev_final"]
             hit |= bool(r["maxiter_hit"])
             # validity of the timed work itself (device-side reductions, read after the timing)
@@ -322,7 +322,7 @@ def run_native(args):
             t_e2e = time.perf_counter()
         sp_h[...] = sp[:, i * Ts:(i + 1) * Ts]          # this step's inputs staged in pinned host memory
         ds_h[...] = ds[:, i * Ts:(i + 1) * Ts]
-        r = eng.run(xh, uph, sp_h, ds_h, resume=True, out=out_h)
+        r = eng.run(xh, uph, sp_h, ds_h, resume=True, out=out_h, max_iter=args.max_iter)
         xh, uph = r["x_final"], r["uprev_final"]
         e2e_kkt = max(e2e_kkt, float(out_h["kkt"].max()))      # the device->host result is read every step
         hit |= bool(r["maxiter_hit"])
@@ -393,6 +393,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=140)
     ap.add_argument("--ref-steps", type=int, default=1, help="closed-loop steps per worker per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-iter", type=int, default=3000, help="per-QP iteration cap (a hit rejects the number)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

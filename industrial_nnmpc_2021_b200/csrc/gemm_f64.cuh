@@ -29,6 +29,9 @@ struct GemmOperands {
   int M, N, K;
   const int* rows;      // optional: logical row i of A/C -> physical row rows[i]
   const int* m_count;   // optional: device-side logical row count (<= M)
+  // device-side tile-shape selection: the launch does nothing unless m_lo < row count <= m_hi, so
+  // several tile shapes can be enqueued for a row list whose length only the device knows
+  int m_lo = 0, m_hi = 0x7fffffff;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -75,12 +78,13 @@ gemm_f64_kernel(GemmOperands g, typename Epi::Params ep) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / T::WN, wn = warp % T::WN;
   const int gq = lane >> 2, tq = lane & 3;     // fragment coordinates
-  const int Mact = g.m_count ? min(*g.m_count, g.M) : g.M;
+  const int Mraw = g.m_count ? *g.m_count : g.M;   // the tile-shape window tests the true row count
+  const int Mact = min(Mraw, g.M);
   // linearised grid, column tiles fastest: CTAs resident together share A row panels and sweep Bt
   const int ntn = (g.N + T::BN - 1) / T::BN;
   const int bn = blockIdx.x % ntn, bm = blockIdx.x / ntn;
   const int m0 = bm * T::BM, n0 = bn * T::BN;
-  if (m0 >= Mact) return;
+  if (m0 >= Mact || Mraw <= g.m_lo || Mraw > g.m_hi) return;
 
   double* As = smem;
   double* Bs = smem + T::STAGES * T::A_ELEMS;

@@ -15,6 +15,7 @@
 // is verified with the true Hessian, g = P z + q (one more GEMM, epilogue reduces
 // ||z - clip(z - g)||_inf and the cost per sample); samples that pass leave the active row list.
 #include "qp.cuh"
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -25,13 +26,18 @@ std::atomic<long long> g_launches{0};
 std::atomic<long long> g_iterations{0};
 
 // ---- live timing of the iteration GEMM (bench.py roofline) ------------------------------------
-struct ProfSpan { cudaEvent_t a, b; double flops; long long launches; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof_spans;   // recorded since the last reset
 static std::vector<ProfSpan> g_prof_pool;    // events to reuse
+static double g_prof_extra_flops = 0.0;
 
-static bool prof_begin(ProfSpan* sp, cudaStream_t st) {
+void prof_add_flops(double flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_on) g_prof_extra_flops += flops;
+}
+
+bool prof_begin(ProfSpan* sp, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_prof_on) return false;
   if (!g_prof_pool.empty()) {
@@ -44,103 +50,13 @@ static bool prof_begin(ProfSpan* sp, cudaStream_t st) {
   cudaEventRecord(sp->a, st);
   return true;
 }
-static void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches) {
+void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches) {
   cudaEventRecord(sp.b, st);
   sp.flops = flops;
   sp.launches = launches;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_spans.push_back(sp);
 }
-
-// ------------------------------------------------------------------------------------ epilogues
-__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
-
-// x = acc - c ; Douglas-Rachford update; writes v (in place), next GEMM operand w, optionally z
-struct EpiAdmm {
-  struct Params {
-    double* V;
-    const double* C;
-    double* Wn;
-    double* Z;  // written when write_z
-    const double* lb;
-    const double* ub;  // B x nu
-    int n, nu;
-    double alpha;
-    int write_z;
-  };
-  Params p;
-  __device__ EpiAdmm(const Params& p_, int, int) : p(p_) {}
-  __device__ void begin_row() {}
-  __device__ void apply(int pr, int, int col, double a0, double a1, bool ok0, bool ok1) {
-    if (!ok0) return;
-    const long long off = (long long)pr * p.n + col;
-    const double* lbr = p.lb + (long long)pr * p.nu;
-    const double* ubr = p.ub + (long long)pr * p.nu;
-    const int k0 = col % p.nu;
-    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;
-    if (ok1) {
-      double2 v = *reinterpret_cast<const double2*>(p.V + off);
-      double2 c = *reinterpret_cast<const double2*>(p.C + off);
-      double l0 = lbr[k0], u0 = ubr[k0], l1 = lbr[k1], u1 = ubr[k1];
-      double vn0 = v.x + p.alpha * ((a0 - c.x) - clipd(v.x, l0, u0));
-      double vn1 = v.y + p.alpha * ((a1 - c.y) - clipd(v.y, l1, u1));
-      double z0 = clipd(vn0, l0, u0), z1 = clipd(vn1, l1, u1);
-      *reinterpret_cast<double2*>(p.V + off) = make_double2(vn0, vn1);
-      *reinterpret_cast<double2*>(p.Wn + off) = make_double2(2.0 * z0 - vn0, 2.0 * z1 - vn1);
-      if (p.write_z) *reinterpret_cast<double2*>(p.Z + off) = make_double2(z0, z1);
-    } else {
-      double v = p.V[off], c = p.C[off], l0 = lbr[k0], u0 = ubr[k0];
-      double vn = v + p.alpha * ((a0 - c) - clipd(v, l0, u0));
-      double z = clipd(vn, l0, u0);
-      p.V[off] = vn;
-      p.Wn[off] = 2.0 * z - vn;
-      if (p.write_z) p.Z[off] = z;
-    }
-  }
-  __device__ void finish_row(int, int, int, bool) {}
-};
-
-// acc = (P z) ; g = acc + q ; per-row partial KKT residual (max) and cost (sum)
-struct EpiVerify {
-  struct Params {
-    const double* Z;
-    const double* Ql;
-    const double* lb;
-    const double* ub;
-    double* part_max;
-    double* part_sum;
-    int n, nu, nslots;
-  };
-  Params p;
-  double rmax, rsum;
-  __device__ EpiVerify(const Params& p_, int, int) : p(p_), rmax(0.0), rsum(0.0) {}
-  __device__ void begin_row() { rmax = 0.0; rsum = 0.0; }
-  __device__ void one(int pr, int col, double a) {
-    const long long off = (long long)pr * p.n + col;
-    const int k = col % p.nu;
-    double z = p.Z[off], q = p.Ql[off];
-    double l = p.lb[(long long)pr * p.nu + k], u = p.ub[(long long)pr * p.nu + k];
-    double g = a + q;
-    rmax = fmax(rmax, fabs(z - clipd(z - g, l, u)));
-    rsum += z * (0.5 * a + q);
-  }
-  __device__ void apply(int pr, int, int col, double a0, double a1, bool ok0, bool ok1) {
-    if (ok0) one(pr, col, a0);
-    if (ok1) one(pr, col + 1, a1);
-  }
-  __device__ void finish_row(int, int lr, int slot, bool rok) {
-    // the 4 lanes of a fragment row hold disjoint column pairs: fixed-order butterfly
-    double m = rmax, s = rsum;
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (rok && (threadIdx.x & 3) == 0) {
-      p.part_max[(long long)lr * p.nslots + slot] = m;
-      p.part_sum[(long long)lr * p.nslots + slot] = s;
-    }
-  }
-};
 
 // ------------------------------------------------------------------------------------ small kernels
 __global__ void k_init_lists(int* rows, int* counts, unsigned long long* iter_sum, int B) {
@@ -204,7 +120,7 @@ __global__ void k_status(const int* __restrict__ rows_cur, const int* __restrict
   }
 }
 
-static int ensure_scratch(nnmpc_qp* h, long long B) {
+int qp_ensure_scratch(nnmpc_qp* h, long long B) {
   const long long n = h->n;
   const int nslots = row_slots_auto(B, h->n);
   if (B <= h->cap && nslots <= h->nslots_cap) return 0;
@@ -229,7 +145,7 @@ int qp_solve_device(nnmpc_qp* h, int B, const double* x0, const double* lb, cons
                     long long* iter_sum_out) {
   if (B <= 0) return 0;
   if (max_iter < 1) max_iter = 1;
-  NNMPC_TRY(ensure_scratch(h, B));
+  NNMPC_TRY(qp_ensure_scratch(h, B));
   const int n = h->n, nu = h->nu, nxa = h->nxa;
   double* V = v_state ? v_state : h->V.p;
   double* Wc = h->W0.p;
@@ -272,7 +188,7 @@ int qp_solve_device(nnmpc_qp* h, int B, const double* x0, const double* lb, cons
     const bool prof = prof_begin(&span, st);
     for (int k = 0; k < chunk; ++k) {
       gi.A = Wc;
-      EpiAdmm::Params ep{V, h->C.p, Wn, u, lb, ub, n, nu, h->alpha, k == chunk - 1 ? 1 : 0};
+      EpiAdmm::Params ep{V, h->C.p, Wn, u, lb, ub, n, nu, h->alpha, k == chunk - 1 ? 1 : 0, nullptr};
       NNMPC_TRY(gemm_auto<EpiAdmm>(gi, ep, st));
       double* t = Wc; Wc = Wn; Wn = t;
     }
@@ -325,7 +241,7 @@ int nnmpc_prof_enable(int on) {
 
 int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double t = 0.0, f = 0.0;
+  double t = 0.0, f = g_prof_extra_flops;
   long long l = 0;
   for (const ProfSpan& sp : g_prof_spans) {
     float e = 0.f;
@@ -341,6 +257,7 @@ int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {
   if (reset) {
     for (const ProfSpan& sp : g_prof_spans) g_prof_pool.push_back(sp);
     g_prof_spans.clear();
+    g_prof_extra_flops = 0.0;
   }
   return 0;
 }
@@ -362,6 +279,12 @@ int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N, const doubl
   if (!h) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
   h->n = n; h->nxa = nxa; h->nu = nu; h->N = N; h->device = device; h->alpha = alpha;
   h->cap = 0; h->nslots_cap = 0;
+  h->p_norm_inf = 0.0;
+  for (int r = 0; r < n; ++r) {
+    double a = 0.0;
+    for (int c = 0; c < n; ++c) a += fabs(P_host[(size_t)r * n + c]);
+    if (a > h->p_norm_inf) h->p_norm_inf = a;
+  }
   NNMPC_TRY(upload(&h->P, P_host, (size_t)n * n));
   NNMPC_TRY(upload(&h->Top, Top_host, (size_t)n * n));
   NNMPC_TRY(upload(&h->tq, tq_host, (size_t)n * nxa));

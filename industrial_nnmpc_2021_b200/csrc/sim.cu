@@ -1,16 +1,36 @@
-// Closed-loop offline data generation for B trajectories at once.
+// Closed-loop offline data generation for B trajectories at once, as a continuously batched engine.
 //
 // Replaces simulate_offline (/root/reference/lib/linearMPC.py:827-880) run in one OS process per
-// trajectory chunk (:803-825).  Per time step, for all trajectories together:
-//   1. k_target_selector (fused): (ysp_t, d_t) -> (xs, us); dataset rows x, uprev, xs, us;
-//      regulator inputs x0 = [x-xs; uprev-us], lb = ulb-us, ub = uub-us       (:851-855, :685-688)
-//   2. k_warm_shift: previous solver state shifted one stage and re-centred on the new target
-//      (the reference cold-starts cvxopt every step; consecutive QPs are near-identical)
-//   3. qp_solve_device: batched regulator QP                                   (:853, :495-512)
-//   4. k_advance: u = useq[0:nu] + us -> dataset row u; plant input [x | u | d]  (:856, :689)
-//   5. plant step x+ = [x|u|d] [A|B|Bd]' through the FP64 tensor-core GEMM     (:860-861)
+// trajectory chunk (:803-825).  Every trajectory ("slot") repeats, at its own pace,
+//     target selector (:851) -> regulator QP (:853) -> u = useq[0:nu] (:856) -> x+ = Ax+Bu+Bd d (:860)
+// and the only coupling between slots is that they share the dense operators.  The reference (and a
+// lock-step batch) waits for the slowest QP of a step; here a slot whose QP has converged
+// immediately advances to its next time step and keeps iterating in place, so the iteration GEMM
+// always runs over every live trajectory (full tiles) and the cost per sample is the MEAN iteration
+// count, not the maximum over the batch.
+//
+// One engine loop (all launches stream ordered, row lists and their lengths live on the device):
+//   1. iteration GEMM over the active list (EpiAdmm: DR update + ||d||_inf per row)
+//   2. k_select:   rows with kappa*||d||_inf <= tol (or at max_iter) become candidates
+//   3. k_make_z + verification GEMM on the candidates: exact KKT residual with P in FP64
+//   4. k_retire:   candidates that pass are done (iters/kkt rows written), the rest keep iterating
+//   5. k_advance + plant-step GEMM on the done rows: dataset row u, x+ = [x|u|d][A|B|Bd]'
+//   6. k_step:     t += 1; finished trajectories leave; the rest form the renew list
+//   7. target selector (fused: dataset rows x,uprev,xs,us; x0, lb, ub; warm-start shift dus),
+//      q-build GEMMs (c = Mtq x0, q = tq x0) and k_warm_shift on the renew rows
+// The host only polls a finished-trajectories counter with a two-loop lag, so the GPU never waits
+// for it.  Per-row results do not depend on which other rows are in the batch: every GEMM tile
+// shape accumulates in the same order and every decision uses the row's own data.
 #include "qp.cuh"
 #include "ts.cuh"
+
+namespace nnmpc {
+int qp_ensure_scratch(nnmpc_qp* h, long long B);
+
+enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4 };
+enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_COUNTERS = 8 };
+constexpr int POLL_RING = 4;
+}  // namespace nnmpc
 
 struct nnmpc_sim {
   nnmpc_qp* qp;
@@ -19,10 +39,16 @@ struct nnmpc_sim {
   int kin_ld;    // nx+nu+nd rounded up to even
   int nxa_ld;    // = qp->nxa
   double* ABd;   // device nx x kin_ld
+  double kappa0, kappa_max;
   long long cap;
-  long long warm_B;   // batch size whose solver state (Va/Vb, us_prev) is valid for `resume`; 0 = none
-  double* warm_V;     // which of Va/Vb holds it
-  nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, Va, Vb, U, xin, xcur, upcur;
+  long long warm_B;   // batch size whose solver state (V, us_prev, kappa) is valid for `resume`; 0 = none
+  nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, V, Z, xin, xcur, upcur, kappa, dtrig;
+  nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 4 x cap (active, cand, done, renew)
+  nnmpc::DevBuf<unsigned long long> dres, kres;
+  int* counts;                      // device, N_COUNTERS ints
+  unsigned long long* rowiters;     // device: total row-iterations executed (flop accounting)
+  int* pin;                         // pinned: POLL_RING x N_COUNTERS ints + 2 x u64
+  cudaEvent_t poll_ev[nnmpc::POLL_RING];
   // staging for the host entry point
   nnmpc::DevBuf<double> h_sp, h_dist, h_x, h_uprev, h_xs, h_us, h_u, h_kkt, h_xio, h_upio;
   nnmpc::DevBuf<int> h_iters;
@@ -30,61 +56,293 @@ struct nnmpc_sim {
 
 namespace nnmpc {
 
-// v_new[j] = v_old[j+nu] + dus[j % nu]  (last stage repeated)
-__global__ void k_warm_shift(const double* __restrict__ Vo, double* __restrict__ Vn, const double* __restrict__ dus,
-                             long long total, int n, int nu) {
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    long long r = i / n;
-    int j = (int)(i - r * n);
-    int js = j + nu < n ? j + nu : j;
-    Vn[i] = Vo[r * n + js] + dus[r * nu + (j % nu)];
+// acc = P z ; g = acc + q ; exact KKT residual ||z - clip(z - g)||_inf folded per row with atomicMax
+struct EpiVerifyMax {
+  struct Params {
+    const double* Z;
+    const double* Ql;
+    const double* lb;
+    const double* ub;
+    unsigned long long* kres;
+    int n, nu;
+  };
+  Params p;
+  double rmax;
+  __device__ EpiVerifyMax(const Params& p_, int, int) : p(p_), rmax(0.0) {}
+  __device__ void begin_row() { rmax = 0.0; }
+  __device__ void one(int pr, int col, double a) {
+    const long long off = (long long)pr * p.n + col;
+    const int k = col % p.nu;
+    const double z = p.Z[off], g = a + p.Ql[off];
+    double r = fabs(z - clipd(z - g, p.lb[(long long)pr * p.nu + k], p.ub[(long long)pr * p.nu + k]));
+    if (!(r <= 1.7e308)) r = __longlong_as_double(0x7ff0000000000000ll);
+    rmax = fmax(rmax, r);
+  }
+  __device__ void apply(int pr, int, int col, double a0, double a1, bool ok0, bool ok1) {
+    if (ok0) one(pr, col, a0);
+    if (ok1) one(pr, col + 1, a1);
+  }
+  __device__ void finish_row(int pr, int, int, bool rok) {
+    double m = rmax;
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if (rok && (threadIdx.x & 3) == 0) atomicMax(p.kres + pr, (unsigned long long)__double_as_longlong(m));
+  }
+};
+
+// ---- single-block list builders --------------------------------------------------------------
+// Ordered (ascending position) compaction by one 1024-thread block: entries with keep != 0 are
+// appended to out[] in input order; returns the new length to every thread.
+__device__ int block_append(bool keep, int value, int* out, int base) {
+  __shared__ int warp_tot[32];
+  __shared__ int total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_tot[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    warp_tot[lane] = v;   // inclusive
+    if (lane == 31) total = v;
+  }
+  __syncthreads();
+  const int woff = warp ? warp_tot[warp - 1] : 0;
+  if (keep) out[base + woff + __popc(m & ((1u << lane) - 1u))] = value;
+  const int t = total;
+  __syncthreads();
+  return base + t;
+}
+
+struct EngineArrays {
+  int* state; int* tcur; int* it;
+  double* kappa; double* dtrig;
+  unsigned long long* dres; unsigned long long* kres;
+  int* l_active; int* l_cand; int* l_done; int* l_renew;
+  int* counts; unsigned long long* rowiters;
+};
+
+// after an iteration: bump iteration counters, pick the rows worth an exact KKT check
+__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter) {
+  const int na = e.counts[N_ACTIVE];
+  int base = 0;
+  for (int i0 = 0; i0 < na; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    bool cand = false;
+    int s = 0;
+    if (i < na) {
+      s = e.l_active[i];
+      const int it = e.it[s] + 1;
+      e.it[s] = it;
+      const double d = __longlong_as_double((long long)e.dres[s]);
+      e.dres[s] = 0ull;
+      cand = (e.kappa[s] * d <= tol) || it >= max_iter;
+      if (cand) {
+        e.state[s] = SLOT_CAND;
+        e.dtrig[s] = d;
+        e.kres[s] = 0ull;
+      }
+    }
+    base = block_append(cand, s, e.l_cand, base);
+  }
+  if (threadIdx.x == 0) {
+    e.counts[N_CAND] = base;
+    *e.rowiters += (unsigned long long)na;
   }
 }
 
-// first move + dataset row u + plant-step input [x | u | d | 0-pad]
-__global__ void k_advance(const double* __restrict__ U, const double* __restrict__ us, long long us_stride,
-                          const double* __restrict__ xcur, const double* __restrict__ d, long long d_stride,
-                          double* __restrict__ row_u, long long row_stride_u, double* __restrict__ upcur,
-                          double* __restrict__ xin, int B, int n, int nx, int nu, int nd, int kin_ld) {
-  long long total = (long long)B * kin_ld;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    long long b = i / kin_ld;
-    int c = (int)(i - b * kin_ld);
+// z = clip(v) for the candidate rows (one CTA per row)
+__global__ void k_make_z(const int* __restrict__ rows, const int* __restrict__ count, const double* __restrict__ V,
+                         double* __restrict__ Z, const double* __restrict__ lb, const double* __restrict__ ub,
+                         int n, int nu) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  const double* v = V + s * n;
+  double* z = Z + s * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int k = j % nu;
+    z[j] = clipd(v[j], lb[s * nu + k], ub[s * nu + k]);
+  }
+}
+
+// candidates whose exact KKT residual passes (or that ran out of iterations) are done
+__global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int max_iter, int T, int* out_iters,
+                                                 double* out_kkt, double kappa_max) {
+  const int nc = e.counts[N_CAND];
+  int base = 0;
+  for (int i0 = 0; i0 < nc; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    bool done = false;
+    int s = 0;
+    if (i < nc) {
+      s = e.l_cand[i];
+      const double r = __longlong_as_double((long long)e.kres[s]);
+      const double d = e.dtrig[s];
+      const int it = e.it[s];
+      // recalibrate this trajectory's trigger from what the exact check saw (consecutive QPs are alike)
+      if (d > 1e-300 && r <= 1.7e308) {
+        double k = fmax(1.3 * r / d, 0.7 * e.kappa[s]);
+        e.kappa[s] = fmin(fmax(k, 1e-6), kappa_max);
+      }
+      done = r <= tol || it >= max_iter;
+      if (done) {
+        e.state[s] = SLOT_DONE;
+        const long long o = (long long)s * T + e.tcur[s];
+        if (out_iters) out_iters[o] = it;
+        if (out_kkt) out_kkt[o] = r;
+        if (!(r <= tol)) e.counts[F_MAXITER] = 1;
+      } else {
+        e.state[s] = SLOT_ITER;
+      }
+    }
+    base = block_append(done, s, e.l_done, base);
+  }
+  if (threadIdx.x == 0) e.counts[N_DONE] = base;
+}
+
+// first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows
+__global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
+                          int T, const double* __restrict__ Z, const double* __restrict__ us,
+                          const double* __restrict__ xcur, const double* __restrict__ dist,
+                          double* __restrict__ row_u, double* __restrict__ upcur, double* __restrict__ xin, int n,
+                          int nx, int nu, int nd, int kin_ld) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  const long long o = s * T + tcur[s];
+  for (int c = threadIdx.x; c < kin_ld; c += blockDim.x) {
     double v;
     if (c < nx) {
-      v = xcur[b * nx + c];
+      v = xcur[s * nx + c];
     } else if (c < nx + nu) {
-      int k = c - nx;
-      v = U[b * n + k] + us[b * us_stride + k];
-      row_u[b * row_stride_u + k] = v;
-      upcur[b * nu + k] = v;
+      const int k = c - nx;
+      v = Z[s * n + k] + us[o * nu + k];
+      row_u[o * nu + k] = v;
+      upcur[s * nu + k] = v;
     } else if (c < nx + nu + nd) {
-      v = d[b * d_stride + (c - nx - nu)];
+      v = dist[o * nd + (c - nx - nu)];
     } else {
       v = 0.0;
     }
-    xin[i] = v;
+    xin[s * kin_ld + c] = v;
+  }
+}
+
+// done rows move to their next time step; finished trajectories leave; rebuild renew + active lists
+__global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
+  const int nd = e.counts[N_DONE];
+  int base = 0, fin = 0;
+  for (int i0 = 0; i0 < nd; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    bool renew = false;
+    int s = 0;
+    if (i < nd) {
+      s = e.l_done[i];
+      const int t = e.tcur[s] + 1;
+      e.tcur[s] = t;
+      renew = t < T;
+      e.state[s] = renew ? SLOT_RENEW : SLOT_IDLE;
+    }
+    fin += __syncthreads_count(i < nd && !renew);
+    base = block_append(renew, s, e.l_renew, base);
+  }
+  int na = 0;
+  if (nd > 0) {   // only a finished trajectory changes the active list, but rebuilding is cheap
+    for (int i0 = 0; i0 < S; i0 += 1024) {
+      const int s = i0 + threadIdx.x;
+      const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW);
+      na = block_append(live, s, e.l_active, na);
+    }
+  }
+  if (threadIdx.x == 0) {
+    e.counts[N_RENEW] = base;
+    e.counts[N_FINISHED] += fin;
+    if (nd > 0) e.counts[N_ACTIVE] = na;
+  }
+}
+
+// renew rows: v <- shifted previous solution re-centred on the new target (or the cold-start law
+// already in V), w = 2 clip(v) - v into the operand buffer the next iteration reads
+__global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
+                             int* __restrict__ it, unsigned long long* __restrict__ dres, double* __restrict__ V,
+                             double* __restrict__ Zs, double* __restrict__ W, const double* __restrict__ dus,
+                             const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu, int cold) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  double* v = V + s * n;
+  double* z = Zs + s * n;
+  double* w = W + s * n;
+  if (!cold) {
+    // v_new[j] = v_old[j+nu] + dus[j % nu] (last stage repeated), staged through the free z row
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int js = j + nu < n ? j + nu : j;
+      z[j] = v[js] + dus[s * nu + (j % nu)];
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double vn = cold ? v[j] : z[j];
+    const int k = j % nu;
+    if (!cold) v[j] = vn;
+    w[j] = 2.0 * clipd(vn, lb[s * nu + k], ub[s * nu + k]) - vn;
+  }
+  if (threadIdx.x == 0) {
+    state[s] = SLOT_ITER;
+    it[s] = 0;
+    dres[s] = 0ull;
+  }
+}
+
+__global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kappa0) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) {
+    e.state[s] = SLOT_RENEW;
+    e.tcur[s] = 0;
+    e.it[s] = 0;
+    e.dres[s] = 0ull;
+    e.kres[s] = 0ull;
+    e.dtrig[s] = 0.0;
+    if (!keep_kappa) e.kappa[s] = kappa0;
+    e.l_active[s] = s;
+    e.l_renew[s] = s;
+  }
+  if (s == 0) {
+    e.counts[N_ACTIVE] = S;
+    e.counts[N_CAND] = 0;
+    e.counts[N_DONE] = 0;
+    e.counts[N_RENEW] = S;
+    e.counts[N_FINISHED] = 0;
+    e.counts[F_MAXITER] = 0;
+    *e.rowiters = 0ull;
   }
 }
 
 static int sim_ensure(nnmpc_sim* h, long long B) {
   if (B <= h->cap) return 0;
   const long long n = h->qp->n;
+  h->warm_B = 0;
   NNMPC_TRY(h->x0.ensure(B * h->nxa_ld));
   NNMPC_TRY(h->lb.ensure(B * h->nu));
   NNMPC_TRY(h->ub.ensure(B * h->nu));
   NNMPC_TRY(h->us_prev.ensure(B * h->nu));
   NNMPC_TRY(h->dus.ensure(B * h->nu));
-  NNMPC_TRY(h->Va.ensure(B * n));
-  NNMPC_TRY(h->Vb.ensure(B * n));
-  NNMPC_TRY(h->U.ensure(B * n));
+  NNMPC_TRY(h->V.ensure(B * n));
+  NNMPC_TRY(h->Z.ensure(B * n));
   NNMPC_TRY(h->xin.ensure(B * h->kin_ld));
   NNMPC_TRY(h->xcur.ensure(B * h->nx));
   NNMPC_TRY(h->upcur.ensure(B * h->nu));
+  NNMPC_TRY(h->kappa.ensure(B));
+  NNMPC_TRY(h->dtrig.ensure(B));
+  NNMPC_TRY(h->state.ensure(B));
+  NNMPC_TRY(h->tcur.ensure(B));
+  NNMPC_TRY(h->it.ensure(B));
+  NNMPC_TRY(h->lists.ensure(4 * B));
+  NNMPC_TRY(h->dres.ensure(B));
+  NNMPC_TRY(h->kres.ensure(B));
   h->cap = B;
-  h->warm_B = 0;
   return 0;
 }
 
@@ -92,50 +350,129 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
                           const double* dist, double* ox, double* ouprev, double* oxs, double* ous, double* ou,
                           int* oiters, double* okkt, double tol, int max_iter, int resume, cudaStream_t st) {
   if (B <= 0 || T <= 0) return 0;
+  if (max_iter < 1) max_iter = 1;
   NNMPC_TRY(sim_ensure(h, B));
+  nnmpc_qp* q = h->qp;
+  NNMPC_TRY(qp_ensure_scratch(q, B));
   const bool cont = resume && h->warm_B == B;
   h->warm_B = 0;
-  const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = h->qp->n;
-  const long long sx = (long long)T * nx, su = (long long)T * nu;
-  int rc_warn = 0;
+  const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = q->n, nxa = h->nxa_ld;
   NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
-  double* Vold = cont ? h->warm_V : h->Va.p;
-  double* Vnew = Vold == h->Va.p ? h->Vb.p : h->Va.p;
-  const int ew_blocks = 148 * 16;
-  for (int t = 0; t < T; ++t) {
+
+  EngineArrays e{};
+  e.state = h->state.p; e.tcur = h->tcur.p; e.it = h->it.p; e.kappa = h->kappa.p; e.dtrig = h->dtrig.p;
+  e.dres = h->dres.p; e.kres = h->kres.p;
+  e.l_active = h->lists.p; e.l_cand = h->lists.p + B; e.l_done = h->lists.p + 2 * (long long)B;
+  e.l_renew = h->lists.p + 3 * (long long)B;
+  e.counts = h->counts; e.rowiters = h->rowiters;
+  k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0);
+  count_launch();
+
+  double* Wc = q->W0.p;   // operand the next iteration reads
+  double* Wn = q->W1.p;
+
+  // target selector + regulator inputs + solver (re)start for the rows of the renew list
+  auto renew = [&](int first) -> int {
     TsFused F{};
-    F.x = h->xcur.p; F.uprev = h->upcur.p; F.x0 = h->x0.p; F.nxa_ld = h->nxa_ld; F.lb = h->lb.p; F.ub = h->ub.p;
+    F.x = h->xcur.p; F.uprev = h->upcur.p; F.x0 = h->x0.p; F.nxa_ld = nxa; F.lb = h->lb.p; F.ub = h->ub.p;
     F.us_prev = h->us_prev.p; F.dus = h->dus.p;
-    F.row_x = ox + (long long)t * nx; F.row_uprev = ouprev + (long long)t * nu;
-    F.row_stride_x = sx; F.row_stride_u = su;
-    NNMPC_TRY(ts_solve_device(h->ts, B, sp + (long long)t * ny, (long long)T * ny, dist + (long long)t * nd,
-                              (long long)T * nd, oxs + (long long)t * nx, sx, ous + (long long)t * nu, su, nullptr, 0,
-                              &F, st));
-    int warm = 0;
-    if (t > 0 || cont) {
-      k_warm_shift<<<ew_blocks, 256, 0, st>>>(Vold, Vnew, h->dus.p, (long long)B * n, n, nu);
+    F.row_x = ox; F.row_uprev = ouprev; F.row_stride_x = nx; F.row_stride_u = nu;
+    TsIndex ix{e.l_renew, e.counts + N_RENEW, e.tcur, T};
+    NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, st));
+    GemmOperands g{};
+    g.A = h->x0.p; g.lda = nxa; g.ldb = nxa; g.M = B; g.N = n; g.K = nxa; g.rows = e.l_renew;
+    g.m_count = e.counts + N_RENEW;
+    g.Bt = q->Mtq;
+    cudaError_t ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{q->C.p, n, nullptr, 0}, st);
+    g.Bt = q->tq;
+    if (ce == cudaSuccess) ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{q->Ql.p, n, nullptr, 0}, st);
+    const int cold = first && !cont;
+    if (cold && ce == cudaSuccess) {   // cold start: the unconstrained (LQR) law v0 = Kunc x0
+      g.Bt = q->Kunc;
+      ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{h->V.p, n, nullptr, 0}, st);
       count_launch();
-      warm = 1;
     }
-    QpOutputs out{nullptr, okkt ? okkt + t : nullptr, oiters ? oiters + t : nullptr, T};
-    int rc = qp_solve_device(h->qp, B, h->x0.p, h->lb.p, h->ub.p, h->U.p, Vnew, warm, out, tol, max_iter, st, nullptr);
-    if (rc < 0) return rc;
-    rc_warn |= rc;
-    k_advance<<<ew_blocks, 256, 0, st>>>(h->U.p, ous + (long long)t * nu, su, h->xcur.p, dist + (long long)t * nd,
-                                         (long long)T * nd, ou + (long long)t * nu, su, h->upcur.p, h->xin.p, B, n, nx,
-                                         nu, nd, h->kin_ld);
+    count_launch(2);
+    if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
+    k_warm_shift<<<B, 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
+                                    h->dus.p, h->lb.p, h->ub.p, n, nu, cold);
     count_launch();
-    GemmOperands g{h->xin.p, h->kin_ld, h->ABd, h->kin_ld, B, nx, h->kin_ld, nullptr, nullptr};
-    NNMPC_TRY(gemm_auto<EpiStore>(g, EpiStore::Params{h->xcur.p, nx, nullptr, 0}, st));
-    double* tmp = Vold; Vold = Vnew; Vnew = tmp;
+    return 0;
+  };
+  NNMPC_TRY(renew(1));
+
+  const long long max_loops = (long long)T * ((long long)max_iter + 2) + 8;
+  int rc_warn = 0;
+  bool finished = false;
+  long long loop = 0;
+  for (; loop < max_loops && !finished; ++loop) {
+    // 1. one Douglas-Rachford iteration for every live trajectory
+    {
+      GemmOperands gi{};
+      gi.A = Wc; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = e.l_active;
+      gi.m_count = e.counts + N_ACTIVE;
+      EpiAdmm::Params ep{h->V.p, q->C.p, Wn, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres};
+      ProfSpan span;
+      const bool prof = prof_begin(&span, st);
+      NNMPC_TRY(gemm_by_count<EpiAdmm>(gi, ep, st));
+      if (prof) prof_end(span, st, 0.0, 1);
+      double* t = Wc; Wc = Wn; Wn = t;
+    }
+    // 2-4. candidates -> exact KKT check -> done list
+    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter);
+    k_make_z<<<B, 256, 0, st>>>(e.l_cand, e.counts + N_CAND, h->V.p, h->Z.p, h->lb.p, h->ub.p, n, nu);
+    count_launch(2);
+    {
+      GemmOperands gv{};
+      gv.A = h->Z.p; gv.lda = n; gv.Bt = q->P; gv.ldb = n; gv.M = B; gv.N = n; gv.K = n; gv.rows = e.l_cand;
+      gv.m_count = e.counts + N_CAND;
+      EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu};
+      NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
+    }
+    k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
+    // 5. first move, dataset row, plant step for the done rows
+    k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, T, h->Z.p, ous, h->xcur.p, dist, ou,
+                                 h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld);
+    count_launch(2);
+    {
+      GemmOperands gp{};
+      gp.A = h->xin.p; gp.lda = h->kin_ld; gp.Bt = h->ABd; gp.ldb = h->kin_ld; gp.M = B; gp.N = nx; gp.K = h->kin_ld;
+      gp.rows = e.l_done; gp.m_count = e.counts + N_DONE;
+      cudaError_t ce = launch_gemm<TileSmall, EpiStore>(gp, EpiStore::Params{h->xcur.p, nx, nullptr, 0}, st);
+      count_launch();
+      if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
+    }
+    // 6-7. next time step for the done rows
+    k_step<<<1, 1024, 0, st>>>(e, T, B);
+    count_launch();
+    NNMPC_TRY(renew(0));
+    // poll the finished counter with a two-loop lag (the GPU never waits for the host)
+    const int slot = (int)(loop % POLL_RING);
+    NNMPC_CUDA(cudaMemcpyAsync(h->pin + slot * N_COUNTERS, h->counts, N_COUNTERS * sizeof(int),
+                               cudaMemcpyDeviceToHost, st));
+    NNMPC_CUDA(cudaEventRecord(h->poll_ev[slot], st));
+    if (loop >= 2) {
+      const int k = (int)((loop - 2) % POLL_RING);
+      NNMPC_CUDA(cudaEventSynchronize(h->poll_ev[k]));
+      if (h->pin[k * N_COUNTERS + N_FINISHED] >= B) finished = true;
+    }
   }
+  // drain: the last loops may not have been polled yet
+  unsigned long long* pin64 = reinterpret_cast<unsigned long long*>(h->pin + POLL_RING * N_COUNTERS);
+  NNMPC_CUDA(cudaMemcpyAsync(h->pin, h->counts, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NNMPC_CUDA(cudaMemcpyAsync(pin64, h->rowiters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(x_io, h->xcur.p, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(uprev_io, h->upcur.p, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
+  NNMPC_CUDA(cudaStreamSynchronize(st));
   NNMPC_CUDA(cudaGetLastError());
+  if (h->pin[N_FINISHED] < B)
+    return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], B);
+  if (h->pin[F_MAXITER]) rc_warn = NNMPC_WARN_MAXITER;
+  g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
+  prof_add_flops(2.0 * n * (double)n * (double)*pin64);
   h->warm_B = B;
-  h->warm_V = Vold;   // after the final swap: the state the last solve left behind
   return rc_warn;
 }
 
@@ -161,7 +498,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->kin_ld = (kin + 1) & ~1;
   h->cap = 0;
   h->warm_B = 0;
-  h->warm_V = nullptr;
+  h->kappa0 = 0.25 * qp->p_norm_inf;
+  h->kappa_max = 8.0 * qp->p_norm_inf;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
   double* tmp = new (std::nothrow) double[(size_t)nx * h->kin_ld];
   if (!tmp) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
@@ -172,6 +510,10 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   int rc = upload(&h->ABd, tmp, (size_t)nx * h->kin_ld);
   delete[] tmp;
   if (rc < 0) return rc;
+  NNMPC_CUDA(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)));
+  NNMPC_CUDA(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)));
+  NNMPC_CUDA(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 2 * sizeof(unsigned long long)));
+  for (int i = 0; i < POLL_RING; ++i) NNMPC_CUDA(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -180,8 +522,13 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   if (!h) return 0;
   DeviceGuard dg(h->device);
   cudaFree(h->ABd);
-  h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->Va.release();
-  h->Vb.release(); h->U.release(); h->xin.release(); h->xcur.release(); h->upcur.release();
+  cudaFree(h->counts);
+  cudaFree(h->rowiters);
+  cudaFreeHost(h->pin);
+  for (int i = 0; i < POLL_RING; ++i) cudaEventDestroy(h->poll_ev[i]);
+  h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
+  h->Z.release(); h->xin.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
+  h->state.release(); h->tcur.release(); h->it.release(); h->lists.release(); h->dres.release(); h->kres.release();
   h->h_sp.release(); h->h_dist.release(); h->h_x.release(); h->h_uprev.release(); h->h_xs.release();
   h->h_us.release(); h->h_u.release(); h->h_kkt.release(); h->h_xio.release(); h->h_upio.release();
   h->h_iters.release();

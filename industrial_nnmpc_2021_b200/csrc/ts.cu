@@ -28,6 +28,8 @@ struct TsParams {
   int* iters; long long iters_stride;
   int fused;
   TsFused f;
+  int indexed;
+  TsIndex ix;
 };
 
 __device__ __forceinline__ double warp_min_d(double v) {
@@ -56,9 +58,13 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
   const double hi = act ? p.uub[lane] : 0.0;
   const int maxit = 10 * nu + 20;
 
-  for (int b = blockIdx.x * TS_WARPS + warp; b < p.B; b += gridDim.x * TS_WARPS) {
-    const double* ysp = p.ysp + (long long)b * p.ysp_stride;
-    const double* dd = p.d + (long long)b * p.d_stride;
+  const int Bn = p.indexed && p.ix.count ? min(*p.ix.count, p.B) : p.B;
+  for (int lb_ = blockIdx.x * TS_WARPS + warp; lb_ < Bn; lb_ += gridDim.x * TS_WARPS) {
+    // s: per-slot buffers; b: position in the strided sample arrays
+    const long long s = p.indexed ? (long long)p.ix.rows[lb_] : (long long)lb_;
+    const long long b = p.indexed ? s * p.ix.T + p.ix.tcur[s] : s;
+    const double* ysp = p.ysp + b * p.ysp_stride;
+    const double* dd = p.d + b * p.d_stride;
     double f = 0.0;
     if (act) {
       f = p.f0[lane];
@@ -179,22 +185,22 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
       for (int k = 0; k < nd; ++k) acc += gd[k] * dd[k];
       p.xs[(long long)b * p.xs_stride + r] = acc;
       if (p.fused) {
-        const double xv = F.x[(long long)b * nx + r];
-        F.x0[(long long)b * F.nxa_ld + r] = xv - acc;
+        const double xv = F.x[s * nx + r];
+        F.x0[s * F.nxa_ld + r] = xv - acc;
         F.row_x[(long long)b * F.row_stride_x + r] = xv;
       }
     }
     if (p.fused) {
       if (act) {
-        const double up = F.uprev[(long long)b * nu + lane];
-        F.x0[(long long)b * F.nxa_ld + nx + lane] = up - u;
+        const double up = F.uprev[s * nu + lane];
+        F.x0[s * F.nxa_ld + nx + lane] = up - u;
         F.row_uprev[(long long)b * F.row_stride_u + lane] = up;
-        F.lb[(long long)b * nu + lane] = lo - u;
-        F.ub[(long long)b * nu + lane] = hi - u;
-        F.dus[(long long)b * nu + lane] = F.us_prev[(long long)b * nu + lane] - u;
-        F.us_prev[(long long)b * nu + lane] = u;
+        F.lb[s * nu + lane] = lo - u;
+        F.ub[s * nu + lane] = hi - u;
+        F.dus[s * nu + lane] = F.us_prev[s * nu + lane] - u;
+        F.us_prev[s * nu + lane] = u;
       }
-      for (int c = nx + nu + lane; c < F.nxa_ld; c += 32) F.x0[(long long)b * F.nxa_ld + c] = 0.0;
+      for (int c = nx + nu + lane; c < F.nxa_ld; c += 32) F.x0[s * F.nxa_ld + c] = 0.0;
     }
     __syncwarp();
   }
@@ -202,7 +208,8 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
 
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
                     long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
-                    int* iters, long long iters_stride, const TsFused* fused, cudaStream_t st) {
+                    int* iters, long long iters_stride, const TsFused* fused, const TsIndex* index,
+                    cudaStream_t st) {
   if (B <= 0) return 0;
   TsParams p{};
   p.B = B; p.nx = h->nx; p.nu = h->nu; p.ny = h->ny; p.nd = h->nd;
@@ -212,6 +219,8 @@ int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride,
   p.iters = iters; p.iters_stride = iters_stride;
   p.fused = fused ? 1 : 0;
   if (fused) p.f = *fused;
+  p.indexed = index ? 1 : 0;
+  if (index) p.ix = *index;
   int blocks = (B + TS_WARPS - 1) / TS_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_target_selector<<<blocks, TS_WARPS * 32, 0, st>>>(p);
@@ -269,7 +278,7 @@ int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride
   if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: null argument");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: negative batch");
   DeviceGuard dg(h->device);
-  return ts_solve_device(h, B, ysp, ysp_stride, d, d_stride, xs, h->nx, us, h->nu, iters, 1, nullptr,
+  return ts_solve_device(h, B, ysp, ysp_stride, d, d_stride, xs, h->nx, us, h->nu, iters, 1, nullptr, nullptr,
                          (cudaStream_t)stream);
 }
 
@@ -289,7 +298,7 @@ int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d
   NNMPC_CUDA(cudaMemcpyAsync(h->hysp.p, ysp, b * h->ny * 8, cudaMemcpyHostToDevice, st));
   if (h->nd > 0) NNMPC_CUDA(cudaMemcpyAsync(h->hd.p, d, b * h->nd * 8, cudaMemcpyHostToDevice, st));
   NNMPC_TRY(ts_solve_device(h, B, h->hysp.p, h->ny, h->hd.p, h->nd, h->hxs.p, h->nx, h->hus.p, h->nu, h->hiters.p, 1,
-                            nullptr, st));
+                            nullptr, nullptr, st));
   NNMPC_CUDA(cudaMemcpyAsync(xs, h->hxs.p, b * h->nx * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(us, h->hus.p, b * h->nu * 8, cudaMemcpyDeviceToHost, st));
   if (iters) NNMPC_CUDA(cudaMemcpyAsync(iters, h->hiters.p, b * 4, cudaMemcpyDeviceToHost, st));

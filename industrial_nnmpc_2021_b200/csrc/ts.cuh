@@ -29,8 +29,20 @@ struct TsFused {
   long long row_stride_x, row_stride_u;
 };
 
+// Optional indirection for the closed-loop engine: logical sample b is trajectory slot rows[b]
+// (b < *count), at its own time index tcur[slot]; the strided arrays (ysp, d, xs, us, iters and the
+// dataset rows of TsFused) are then indexed by slot*T + tcur[slot], the per-slot buffers of TsFused
+// (x, uprev, x0, lb, ub, us_prev, dus) by slot.
+struct TsIndex {
+  const int* rows;
+  const int* count;
+  const int* tcur;
+  int T;
+};
+
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
                     long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
-                    int* iters, long long iters_stride, const TsFused* fused, cudaStream_t st);
+                    int* iters, long long iters_stride, const TsFused* fused, const TsIndex* index,
+                    cudaStream_t st);
 
 }  // namespace nnmpc

@@ -267,6 +267,56 @@ def test_generate_data_files_and_sharding_invariance(torch_cuda, cdu_small_probl
             assert np.array_equal(d[k], all4[k][2 + proc]), k     # bitwise: batching does not change results
 
 
+def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem):
+    """Many trajectories of different lengths-to-convergence in one continuously batched run: the
+    batch crosses all three GEMM tile shapes (<=48, <=384, >384 rows) as trajectories finish, and
+    every trajectory must come out bitwise identical to the same trajectory run in a small batch,
+    and equal to the oracle's closed loop within the north-star tolerance."""
+    from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
+    p = cdu_small_problem
+    Bn, T = 450, 5
+    sp, ds = p.setpoints[:Bn * T], p.disturbances[:Bn * T]
+    sim = OfflineSimulator(**p.controller_kwargs(), xprior=p.xprior, setpoints=sp, disturbances=ds,
+                           num_data_gen_task=1, num_process_per_task=Bn)
+    big = sim.generate_batch()
+    assert not big["maxiter_hit"] and float(big["kkt"].max()) <= KKT_TOL and big["iters"].min() >= 1
+    spc = np.stack(sim.setpoints[0]); dsc = np.stack(sim.disturbances[0])
+    for sel in (slice(0, 40), slice(100, 230), slice(449, 450)):
+        sub = sim.engine.run(p.xprior, p.uprev, spc[sel], dsc[sel])
+        for k in ("x", "uprev", "xs", "us", "u", "iters"):
+            assert np.array_equal(sub[k], big[k][sel]), (sel, k)
+    oreg = om.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub)
+    ots = om.TargetSelectorOracle(A=p.A, B=p.B, C=p.C, H=p.H, Bd=p.Bd, Cd=p.Cd, usp=p.usp, Rs=p.Rs, Qs=p.Qs,
+                                  ulb=p.ulb, uub=p.uub)
+    for c in (0, 77, 301, 449):
+        od = om.simulate_offline(x0=p.xprior, uprev0=p.uprev, A=p.A, B=p.B, Bd=p.Bd, regulator=oreg, ulb=p.ulb,
+                                 uub=p.uub, target_selector=ots, setpoints=spc[c], disturbances=dsc[c])
+        for k in ("x", "xs", "us", "u"):
+            assert np.max(np.abs(big[k][c] - od[k])) / max(1.0, np.max(np.abs(od[k]))) <= 1e-6, (c, k)
+
+
+def test_closed_loop_resume_in_slabs(torch_cuda, cdu_small_problem):
+    """A trajectory advanced slab by slab (resume=True keeps the solver state) reproduces the
+    single-call run within tolerance and needs no more iterations on the slab boundaries."""
+    from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
+    p = cdu_small_problem
+    Bn, T = 6, 24
+    sim = OfflineSimulator(**p.controller_kwargs(), xprior=p.xprior, setpoints=p.setpoints[:Bn * T],
+                           disturbances=p.disturbances[:Bn * T], num_data_gen_task=1, num_process_per_task=Bn)
+    whole = sim.generate_batch()
+    spc = np.stack(sim.setpoints[0]); dsc = np.stack(sim.disturbances[0])
+    x, up, parts = p.xprior, p.uprev, []
+    for i in range(0, T, 8):
+        r = sim.engine.run(x, up, spc[:, i:i + 8], dsc[:, i:i + 8], resume=i > 0)
+        x, up = r["x_final"], r["uprev_final"]
+        parts.append(r)
+    for k in ("x", "uprev", "xs", "us", "u"):
+        cat = np.concatenate([r[k] for r in parts], axis=1)
+        assert np.max(np.abs(cat - whole[k])) <= 1e-7 * max(1.0, np.max(np.abs(whole[k]))), k
+    it_cat = np.concatenate([r["iters"] for r in parts], axis=1)
+    assert it_cat[:, 8].max() <= whole["iters"][:, 8].max() + 5
+
+
 # ------------------------------------------------------------------------------------ structured NN
 def _random_weights(rng, dims):
     ws = []

@@ -1,0 +1,14 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+for cfg in "1024 4" "2688 2" "4096 2"; do
+  set -- $cfg
+  timeout 600 python bench.py --steps 3 --warmup 3 --traj $1 --slab $2 --no-cpu-baseline > gpurun_out/bench_b_$1.json 2> gpurun_out/bench_b_$1.err
+  tail -3 gpurun_out/bench_b_$1.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_b_$1.json").read().strip().splitlines()[-1])
+print("traj $1", "value", round(d["value"]), "ms/step", round(d["ms_per_step"],1), "iters", d["iterations"], "roof", round(d["roofline"]["achieved"],2), round(d["roofline"]["frac"],3), "share", round(d["roofline"]["share_of_step"],3), "e2e", round(d["e2e"]["value"]), "launches", d["gpu_launches"])
+PY
+done
