@@ -334,6 +334,24 @@ def run_native(args):
     h2d = (sp_h.nbytes + ds_h.nbytes + xh.nbytes + uph.nbytes) * world
     d2h = (sum(v.nbytes for v in out_h.values()) + xh.nbytes + uph.nbytes) * world
 
+    # ---- dataset gather over NCCL/NVLink (outside `value`; the solve path has no collective) ----
+    gather = None
+    if world > 1:
+        from industrial_nnmpc_2021_b200 import distributed as nd_
+        local = {k: out_d[k] for k in nd_.DATASET_KEYS}
+        nd_.gather_chunks(local, world * B)          # warm-up (NCCL communicator set-up)
+        barrier()
+        gv0, gv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gv0.record()
+        full = nd_.gather_chunks(local, world * B)
+        gv1.record()
+        barrier()
+        g_ms = maxrank(gv0.elapsed_time(gv1))
+        g_bytes = sum(v.numel() * v.element_size() for v in full.values())
+        gather = {"ms": g_ms, "bytes_gathered_per_rank": g_bytes, "algbw_GBs": g_bytes / (g_ms * 1e-3) / 1e9,
+                  "what": "all_gather_into_tensor of one step's dataset rows (x, uprev, xs, us, u) from every rank"}
+        del full
+
     if kkt_max > KKT_TOL or e2e_kkt > KKT_TOL or hit:
         raise SystemExit(f"bench.py: timed solves missed the tolerance (kkt {kkt_max:.2e}/{e2e_kkt:.2e}, "
                          f"maxiter_hit={hit}); number rejected")
@@ -374,7 +392,7 @@ def run_native(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K, "kkt_max": e2e_kkt},
-            "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup,
+            "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup, "gather": gather,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -388,8 +406,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--traj", type=int, default=1024, help="closed-loop trajectories per GPU")
-    ap.add_argument("--slab", type=int, default=4, help="simulation steps every trajectory advances per bench step")
+    ap.add_argument("--traj", type=int, default=2688,
+                    help="closed-loop trajectories per GPU (2688 = 21 row tiles x 35 column tiles = 4.97 waves of 148 SMs)")
+    ap.add_argument("--slab", type=int, default=32, help="simulation steps every trajectory advances per bench step")
     ap.add_argument("--horizon", type=int, default=140)
     ap.add_argument("--ref-steps", type=int, default=1, help="closed-loop steps per worker per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -48,18 +48,21 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16>
 struct GemmTile {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
-  static constexpr int BK = 16, LDS = BK + 4;
+  static constexpr int BK = BK_, LDS = BK + 4;
+  static constexpr int KC = BK / 2;                          // 16-byte chunks per tile row
   static constexpr int THREADS = 32 * WM * WN;
   static constexpr int MT = BM / WM / 8, NT = BN / WN / 8;
   static constexpr int A_ELEMS = BM * LDS, B_ELEMS = BN * LDS;
   static constexpr int SMEM_BYTES = STAGES * (A_ELEMS + B_ELEMS) * 8;
-  static constexpr int A_CHUNKS = BM * (BK / 2) / THREADS;   // 16-byte chunks per thread
-  static constexpr int B_CHUNKS = BN * (BK / 2) / THREADS;
+  static constexpr int A_CHUNKS = BM * KC / THREADS;         // 16-byte chunks per thread
+  static constexpr int B_CHUNKS = BN * KC / THREADS;
   static_assert(BM % (WM * 8) == 0 && BN % (WN * 8) == 0, "warp tiling");
-  static_assert((BM * (BK / 2)) % THREADS == 0 && (BN * (BK / 2)) % THREADS == 0, "loader tiling");
+  static_assert((BM * KC) % THREADS == 0 && (BN * KC) % THREADS == 0, "loader tiling");
+  static_assert(THREADS % KC == 0, "every chunk of a thread must share its k offset");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
 // Epilogue concept:
@@ -96,7 +99,7 @@ gemm_f64_kernel(GemmOperands g, typename Epi::Params ep) {
 #pragma unroll
   for (int i = 0; i < T::A_CHUNKS; ++i) {
     int c = tid + i * T::THREADS;
-    int r = c >> 3, kc = c & 7;
+    int r = c / T::KC, kc = c % T::KC;
     int lr = m0 + r;
     a_ok[i] = lr < Mact;
     long long pr = a_ok[i] ? (g.rows ? (long long)g.rows[lr] : (long long)lr) : 0;
@@ -109,13 +112,13 @@ gemm_f64_kernel(GemmOperands g, typename Epi::Params ep) {
 #pragma unroll
   for (int i = 0; i < T::B_CHUNKS; ++i) {
     int c = tid + i * T::THREADS;
-    int r = c >> 3, kc = c & 7;
+    int r = c / T::KC, kc = c % T::KC;
     int col = n0 + r;
     b_ok[i] = col < g.N;
     b_src[i] = g.Bt + (long long)(b_ok[i] ? col : 0) * g.ldb + kc * 2;
     b_dst[i] = r * T::LDS + kc * 2;
   }
-  const int kcoff = (tid & 7) * 2;   // every chunk of this thread has the same kc (THREADS % 8 == 0)
+  const int kcoff = (tid % T::KC) * 2;   // every chunk of this thread has the same kc (THREADS % KC == 0)
 
   auto load_stage = [&](int stage, int kt) {
     const int k0 = kt * T::BK;

@@ -8,11 +8,16 @@ namespace nnmpc {
 // CTA tiles of the FP64 tensor-core GEMM.  Every shape accumulates each output element over k in
 // the same order (sequential DMMA.8x8x4 steps, no split-K), so results are bitwise independent of
 // the tile shape a sample happens to be computed with.
-using TileBig = GemmTile<128, 128, 2, 4, 4>;    // full batches
-using TileSmall = GemmTile<64, 64, 2, 2, 4>;    // 48 < rows <= 384
-using TileSkinny = GemmTile<32, 32, 2, 2, 6>;   // rows <= 48: 140 CTAs stream the operator once
+// Shapes and row-count windows were ranked on a B200 with tools/probes/gemm_tiles.py (n = 4480):
+//   rows <= 48: 16x32 (280 CTAs stream the operator once; 83 us at 40 rows)   <= 512: 32x64 (23 TF/s)
+//   <= 896: 64x64 (24.6 TF/s at 600 rows, 128x128 would run 17.9)              above: 128x128 (30-32 TF/s)
+using TileBig = GemmTile<128, 128, 2, 4, 4>;
+using TileMid = GemmTile<64, 64, 2, 2, 4>;
+using TileSmall = GemmTile<32, 64, 2, 2, 6>;
+using TileSkinny = GemmTile<16, 32, 1, 4, 8>;
 constexpr int SKINNY_MAX_ROWS = 48;
-constexpr int SMALL_MAX_ROWS = 384;
+constexpr int SMALL_MAX_ROWS = 512;
+constexpr int MID_MAX_ROWS = 896;
 inline bool use_big_tile(long long M, int N) { return M > 64 && N > 64; }
 
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -159,13 +164,13 @@ struct EpiVerify {
 template <class Epi>
 inline int gemm_auto(const GemmOperands& g, const typename Epi::Params& ep, cudaStream_t st) {
   cudaError_t e = use_big_tile(g.M, g.N) ? launch_gemm<TileBig, Epi>(g, ep, st)
-                                         : launch_gemm<TileSmall, Epi>(g, ep, st);
+                                         : launch_gemm<TileMid, Epi>(g, ep, st);
   count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 inline int row_slots_auto(long long M, int N) {
-  return use_big_tile(M, N) ? gemm_row_slots<TileBig>(N) : gemm_row_slots<TileSmall>(N);
+  return use_big_tile(M, N) ? gemm_row_slots<TileBig>(N) : gemm_row_slots<TileMid>(N);
 }
 
 // Row list whose length lives on the device (g.m_count, at most g.M rows): enqueue one launch per
@@ -183,17 +188,17 @@ inline int gemm_by_count(GemmOperands g, const typename Epi::Params& ep, cudaStr
     count_launch();
   }
   if (e == cudaSuccess && Mmax > SMALL_MAX_ROWS) {
-    g.m_lo = SMALL_MAX_ROWS; g.m_hi = 0x7fffffff; g.M = Mmax;
+    g.m_lo = SMALL_MAX_ROWS; g.m_hi = MID_MAX_ROWS; g.M = Mmax < MID_MAX_ROWS ? Mmax : MID_MAX_ROWS;
+    e = launch_gemm<TileMid, Epi>(g, ep, st);
+    count_launch();
+  }
+  if (e == cudaSuccess && Mmax > MID_MAX_ROWS) {
+    g.m_lo = MID_MAX_ROWS; g.m_hi = 0x7fffffff; g.M = Mmax;
     e = launch_gemm<TileBig, Epi>(g, ep, st);
     count_launch();
   }
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
   return 0;
-}
-// per-row partial slots an epilogue with row reductions needs when any of the three shapes may run
-inline int row_slots_any(int N) {
-  int a = gemm_row_slots<TileSkinny>(N), b = gemm_row_slots<TileSmall>(N), c = gemm_row_slots<TileBig>(N);
-  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 struct QpOutputs {

@@ -385,13 +385,13 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     g.A = h->x0.p; g.lda = nxa; g.ldb = nxa; g.M = B; g.N = n; g.K = nxa; g.rows = e.l_renew;
     g.m_count = e.counts + N_RENEW;
     g.Bt = q->Mtq;
-    cudaError_t ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{q->C.p, n, nullptr, 0}, st);
+    cudaError_t ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{q->C.p, n, nullptr, 0}, st);
     g.Bt = q->tq;
-    if (ce == cudaSuccess) ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{q->Ql.p, n, nullptr, 0}, st);
+    if (ce == cudaSuccess) ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{q->Ql.p, n, nullptr, 0}, st);
     const int cold = first && !cont;
     if (cold && ce == cudaSuccess) {   // cold start: the unconstrained (LQR) law v0 = Kunc x0
       g.Bt = q->Kunc;
-      ce = launch_gemm<TileSmall, EpiStore>(g, EpiStore::Params{h->V.p, n, nullptr, 0}, st);
+      ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{h->V.p, n, nullptr, 0}, st);
       count_launch();
     }
     count_launch(2);
@@ -440,7 +440,7 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
       GemmOperands gp{};
       gp.A = h->xin.p; gp.lda = h->kin_ld; gp.Bt = h->ABd; gp.ldb = h->kin_ld; gp.M = B; gp.N = nx; gp.K = h->kin_ld;
       gp.rows = e.l_done; gp.m_count = e.counts + N_DONE;
-      cudaError_t ce = launch_gemm<TileSmall, EpiStore>(gp, EpiStore::Params{h->xcur.p, nx, nullptr, 0}, st);
+      cudaError_t ce = launch_gemm<TileMid, EpiStore>(gp, EpiStore::Params{h->xcur.p, nx, nullptr, 0}, st);
       count_launch();
       if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
     }

@@ -686,13 +686,31 @@ class OfflineSimulator:
         return ([sp[t * k:(t + 1) * k] for t in range(self.num_data_gen_task)],
                 [ds[t * k:(t + 1) * k] for t in range(self.num_data_gen_task)])
 
-    def generate_batch(self, tasks=None):
+    def generate_batch(self, tasks=None, distributed=None):
         """All chunks of the given tasks (default: all) as one batch; returns the engine's dict
-        with arrays shaped (num_chunks, L, .), chunk order = (task, process) order."""
+        with arrays shaped (num_chunks, L, .), chunk order = (task, process) order.
+
+        Under an initialised ``torch.distributed`` group with more than one rank (one process per
+        GPU; ``distributed=None`` auto-detects) the chunks are sharded in contiguous blocks over the
+        ranks - no collective on the solve path - and the dataset arrays x, uprev, xs, us, u are
+        all-gathered over NCCL so every rank returns the full dataset (CUDA tensors) in the
+        reference's concatenation order (controller_evaluation.py:281-292)."""
+        from . import distributed as _d
         tasks = range(self.num_data_gen_task) if tasks is None else tasks
         sp = np.stack([c for t in tasks for c in self.setpoints[t]])
         ds = np.stack([c for t in tasks for c in self.disturbances[t]])
-        return self.engine.run(self.x0, self.uprev0, sp, ds)
+        if distributed is None:
+            distributed = _d.is_distributed()
+        if not distributed:
+            return self.engine.run(self.x0, self.uprev0, sp, ds)
+        torch = _torch()
+        dev = torch.device("cuda", self.engine._dev)
+
+        def run_local(sp_l, ds_l):
+            f64 = dict(dtype=torch.float64, device=dev)
+            return self.engine.run(self.x0, self.uprev0, torch.as_tensor(np.ascontiguousarray(sp_l), **f64),
+                                   torch.as_tensor(np.ascontiguousarray(ds_l), **f64))
+        return _d.generate_sharded(run_local, sp, ds, device=dev)
 
     def generate_data(self, *, task_number, data_filename, stdout_filename):
         """Reference entry point (linearMPC.py:803-825): writes one file per process of the task."""
