@@ -47,6 +47,9 @@ long long nnmpc_iteration_count(void);
  * launches since the last reset.  Disabled by default (no events are recorded). */
 int nnmpc_prof_enable(int on);
 int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset);
+/* Same with two channels (arrays of 2): [0] the iteration passes (FP64 DMMA GEMM, or the tcgen05 pass
+ * of the mixed-precision mode), [1] the FP64 anchor / exact-check GEMMs of the mixed-precision mode. */
+int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset);
 
 /* ---- regulator QP:  DenseQPRegulator (lib/linearMPC.py:321-517) -------------------------------
  *   min_u 1/2 u'Pu + (tq x0)'u   s.t.  lb <= u_k <= ub  for every stage k     (box path, :481)
@@ -104,6 +107,18 @@ int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d
 int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, int nu, int nd,
                      int ny, const double* ABd_host, int device);
 int nnmpc_sim_destroy(nnmpc_sim_t* h);
+/* Arithmetic of the regulator-QP iteration inside the closed loop ("FP64 DMMA, or FP32 with FP64
+ * residual refinement" of the north star).  Either way every returned solution has passed a KKT check
+ * evaluated with P in FP64 (lib/linearMPC.py:503 is replaced by a certified optimum, not an estimate).
+ *   NNMPC_PRECISION_F64    every iteration is an FP64 tensor-core (DMMA) GEMM with Top
+ *   NNMPC_PRECISION_MIXED  iterations run on the tcgen05 tensor cores: fp16 increments of the operand
+ *                          against a two-term fp16 split of Top, fp32 accumulation in TMEM, all solver
+ *                          state in FP64; FP64 "anchor" GEMMs x = Top w - c start every QP and repair
+ *                          the drift whenever an exact check fails */
+enum { NNMPC_PRECISION_F64 = 0, NNMPC_PRECISION_MIXED = 1 };
+int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode);
+/* cumulative since create: out4 = {row-iterations, FP64 anchors, exact KKT checks, QPs solved} */
+int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                   const double* setpoints, const double* disturbances, double* x, double* uprev,
                   double* xs, double* us, double* u, int* iters, double* kkt, double tol,
@@ -131,7 +146,12 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
                            const double* xs, const double* us, const double* xscale,
                            const double* ulb, const double* uub, double* out);
 
-/* ---- self test: C = A * Bt^T through the same GEMM kernel (used by tests) ---------------------- */
+/* ---- self tests (used by tests/) -----------------------------------------------------------------
+ * nnmpc_lp_gemm_test: the tcgen05 split-operator GEMM, C[M x N] = fp16(A)[M x K] (T1 + T2)[N x K]^T / s with
+ * (T1, T2, s) the two-term fp16 split of the square FP64 operator Bt (N == K, bt_max = max |Bt|);
+ * A, Bt, C are dense row-major FP64 device matrices. */
+int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, void* stream);
+/* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,
                   long long ldb, double* C, long long ldc, const int* rows, void* stream);
 

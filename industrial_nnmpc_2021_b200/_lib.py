@@ -26,6 +26,7 @@ SIGNATURES = {
     "nnmpc_iteration_count": (C.c_longlong, []),
     "nnmpc_prof_enable": (C.c_int, [C.c_int]),
     "nnmpc_prof_read": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
+    "nnmpc_prof_read2": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "nnmpc_qp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                   C.c_double, C.c_int]),
     "nnmpc_qp_destroy": (C.c_int, [vp]),
@@ -38,6 +39,8 @@ SIGNATURES = {
     "nnmpc_ts_solve_host": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "nnmpc_sim_create": (C.c_int, [C.POINTER(vp), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
     "nnmpc_sim_destroy": (C.c_int, [vp]),
+    "nnmpc_sim_set_precision": (C.c_int, [vp, C.c_int]),
+    "nnmpc_sim_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
                                 C.c_int, C.c_int, vp]),
     "nnmpc_sim_run_host": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
@@ -47,6 +50,7 @@ SIGNATURES = {
     "nnmpc_mlp_destroy": (C.c_int, [vp]),
     "nnmpc_mlp_forward": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_mlp_forward_host": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nnmpc_lp_gemm_test": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, vp, vp]),
     "nnmpc_gemm_tn": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong,
                                 vp, vp]),
 }
@@ -114,6 +118,17 @@ def prof_read(reset=True):
     ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
     check(lib().nnmpc_prof_read(C.byref(ms), C.byref(fl), C.byref(n), int(bool(reset))), "nnmpc_prof_read")
     return ms.value, fl.value, n.value
+
+
+def prof_read2(reset=True):
+    """Two-channel form: [(ms, flops, launches) of the iteration passes, (...) of the FP64 anchor /
+    exact-check GEMMs of the mixed-precision mode]."""
+    ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+    check(lib().nnmpc_prof_read2(ms, fl, n, int(bool(reset))), "nnmpc_prof_read2")
+    return [(ms[i], fl[i], n[i]) for i in range(2)]
+
+
+PRECISION = {"f64": 0, "mixed": 1}
 
 
 def stream_ptr():

@@ -1,0 +1,158 @@
+// Host-side glue of the tcgen05 split-operator GEMM: fp16 operator split of a regulator handle,
+// tensor maps, and the self-test entry point.
+#include "lp_iter.cuh"
+#include <cmath>
+#include <vector>
+
+namespace nnmpc {
+
+int device_sm_count(int device) {
+  static int cache[64] = {};
+  if (cache[device & 63] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    cache[device & 63] = v;
+  }
+  return cache[device & 63];
+}
+
+int lp_state_ensure(LpState* s, long long B, int n) {
+  if (B <= s->cap && n == s->n) return 0;
+  const long long cap = B > s->cap ? B : s->cap;
+  s->n = n;
+  s->ldd = ((long long)n + 63) / 64 * 64;
+  NNMPC_TRY(s->X.ensure((size_t)cap * n));
+  NNMPC_TRY(s->E.ensure((size_t)cap * n));
+  NNMPC_TRY(s->sc_in.ensure((size_t)cap));
+  NNMPC_TRY(s->sc_out.ensure((size_t)cap));
+  // rows and columns padded to whole TMA boxes (zeros), so no tile ever reaches outside the tensor
+  const long long cap_pad = (cap + lp::BM - 1) / lp::BM * lp::BM;
+  for (int b = 0; b < 2; ++b) {
+    NNMPC_TRY(s->D[b].ensure((size_t)cap_pad * s->ldd));
+    NNMPC_CUDA(cudaMemset(s->D[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half)));
+    if (!lp::make_tmap_f16(&s->tmD[b], s->D[b].p, cap_pad, s->ldd, s->ldd, lp::BM))
+      return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the increment buffers");
+  }
+  s->cap = cap;
+  s->cur = 0;
+  return 0;
+}
+
+int lp_anchor_prep(const int* rows, const int* count, int max_rows, const double* V, double* W, LpState* s,
+                   const double* lb, const double* ub, int nu, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  k_anchor_prep<<<max_rows, 256, 0, st>>>(rows, count, V, W, s->E.p, lb, ub, s->n, nu);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double* W, const double* Top, const double* C,
+                   LpState* s, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  GemmOperands g{};
+  g.A = W; g.lda = s->n; g.Bt = Top; g.ldb = s->n; g.M = max_rows; g.N = s->n; g.K = s->n; g.rows = rows; g.m_count = count;
+  return gemm_by_count<EpiAnchor>(g, EpiAnchor::Params{s->X.p, C, s->n}, st);
+}
+
+int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
+                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  k_dr_first<<<max_rows, 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
+                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lp_iterate(const LpOperator* op, LpState* s, int B, double* V, const double* lb, const double* ub, const int* state,
+               int iter_state, unsigned long long* dres, int nu, double alpha, int device, cudaStream_t st) {
+  if (B <= 0) return 0;
+  EpiDelta::Params ep{};
+  ep.X = s->X.p; ep.V = V; ep.E = s->E.p; ep.Dn = s->D[s->cur ^ 1].p; ep.ldd = s->ldd; ep.lb = lb; ep.ub = ub;
+  ep.state = state; ep.iter_state = iter_state; ep.sc_in = s->sc_in.p; ep.sc_out = s->sc_out.p; ep.dres = dres;
+  ep.n = s->n; ep.nu = nu; ep.alpha = alpha; ep.inv_sT = 1.0 / op->scale;
+  lp::LpShape g{B, s->n, s->n};
+  cudaError_t e = lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
+  count_launch();
+  if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));
+  s->cur ^= 1;
+  return 0;
+}
+
+// T (n x n FP64 on the device, max |T| = tmax) -> two fp16 matrices with leading dimension ldh and their
+// tensor maps (boxes of BN rows).  The scale is the power of two that puts max |s T| in [512, 1024).
+int lp_split_operator(const double* T_dev, int n, double tmax, LpOperator* op, cudaStream_t st) {
+  op->n = n;
+  op->ldh = ((long long)n + 63) / 64 * 64;
+  int ex = 0;
+  frexp(tmax > 0.0 ? tmax : 1.0, &ex);
+  op->scale = ldexp(1.0, 10 - ex);
+  const long long rows_pad = ((long long)n + LpTileN128::BN - 1) / LpTileN128::BN * LpTileN128::BN;
+  NNMPC_TRY(op->T1.ensure((size_t)rows_pad * op->ldh));
+  NNMPC_TRY(op->T2.ensure((size_t)rows_pad * op->ldh));
+  NNMPC_CUDA(cudaMemsetAsync(op->T1.p, 0, (size_t)rows_pad * op->ldh * sizeof(__half), st));
+  NNMPC_CUDA(cudaMemsetAsync(op->T2.p, 0, (size_t)rows_pad * op->ldh * sizeof(__half), st));
+  k_split_f16<<<148 * 8, 256, 0, st>>>(T_dev, n, op->ldh, op->scale, op->T1.p, op->T2.p);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  if (!lp::make_tmap_f16(&op->tm1, op->T1.p, rows_pad, op->ldh, op->ldh, LpTileN128::BN) ||
+      !lp::make_tmap_f16(&op->tm2, op->T2.p, rows_pad, op->ldh, op->ldh, LpTileN128::BN))
+    return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fp16 operator split");
+  op->ready = true;
+  return 0;
+}
+
+__global__ void k_to_half(const double* __restrict__ A, long long rows, int cols, long long ld, __half* __restrict__ H) {
+  const long long total = rows * ld;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / ld;
+    const int c = (int)(i - r * ld);
+    H[i] = __double2half(c < cols ? A[r * cols + c] : 0.0);
+  }
+}
+
+}  // namespace nnmpc
+
+using namespace nnmpc;
+
+extern "C" {
+
+// Self test of the tcgen05 path:  C[M x N] = fp16(A)[M x K] * (T1 + T2)[N x K]^T / s  with (T1, T2, s) the
+// two-term fp16 split of Bt.  A, Bt, C are FP64 device matrices (row-major, dense).
+int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, void* stream) {
+  if (!A || !Bt || !C || M <= 0 || N <= 0 || K <= 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_lp_gemm_test: bad argument");
+  if (N != K) return set_error(NNMPC_ERR_BADARG, "nnmpc_lp_gemm_test: the operator must be square (N == K)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  NNMPC_CUDA(cudaGetDevice(&dev));
+  LpOperator op;
+  int rc = lp_split_operator(Bt, N, bt_max, &op, st);
+  DevBuf<__half> Ah;
+  const long long m_pad = ((long long)M + lp::BM - 1) / lp::BM * lp::BM;
+  if (rc == 0) rc = Ah.ensure((size_t)m_pad * op.ldh);
+  if (rc == 0) {
+    cudaMemsetAsync(Ah.p, 0, (size_t)m_pad * op.ldh * sizeof(__half), st);
+    k_to_half<<<148 * 4, 256, 0, st>>>(A, M, K, op.ldh, Ah.p);
+    count_launch();
+    CUtensorMap tmA;
+    if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
+      rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    } else {
+      lp::LpShape g{M, N, K};
+      cudaError_t e = lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, EpiLpStore::Params{C, N, 1.0 / op.scale},
+                                                                 device_sm_count(dev), st);
+      count_launch();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaStreamSynchronize(st);
+  Ah.release();
+  op.T1.release();
+  op.T2.release();
+  return rc;
+}
+
+}  // extern "C"

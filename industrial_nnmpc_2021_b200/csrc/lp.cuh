@@ -1,0 +1,53 @@
+// Host-visible interface of the mixed-precision (tcgen05 fp16 increments + FP64 anchors) iteration
+// of the regulator QP; device code lives in lp_gemm.cuh / lp_iter.cuh and is compiled in lp.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "qp.cuh"
+
+namespace nnmpc {
+
+// per-sample state of the mixed-precision iteration for up to `cap` rows (see lp_iter.cuh)
+struct LpState {
+  long long cap = 0;
+  int n = 0;
+  long long ldd = 0;                 // leading dimension of the fp16 increment buffers
+  DevBuf<double> X, sc_in, sc_out;
+  DevBuf<float> E;
+  DevBuf<__half> D[2];               // double buffered: the TMA reads D[cur], the epilogue writes D[cur ^ 1]
+  CUtensorMap tmD[2];
+  int cur = 0;
+  void release() { X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release(); cap = 0; }
+};
+
+#ifdef __CUDACC__
+// largest power of two s with s * est in [8, 16], clamped to 2^+-60 (est = 0, NaN or Inf -> 2^60 / 2^-60)
+__device__ __forceinline__ double pow2_scale(double est) {
+  if (!(est > 0.0)) return 1152921504606846976.0;                 // 2^60
+  if (!(est <= 1.7e308)) return 8.673617379884035e-19;            // 2^-60
+  int ex;
+  frexp(est, &ex);                                                // est = m 2^ex, m in [0.5, 1)
+  int sh = 4 - ex;
+  sh = sh > 60 ? 60 : (sh < -60 ? -60 : sh);
+  return ldexp(1.0, sh);
+}
+#endif
+
+int device_sm_count(int device);
+int lp_split_operator(const double* T_dev, int n, double tmax, LpOperator* op, cudaStream_t st);
+int lp_state_ensure(LpState* s, long long B, int n);
+
+// rows listed in rows[0..*count): w = 2 clip(v) - v into W (the FP64 anchor GEMM operand), E = 0
+int lp_anchor_prep(const int* rows, const int* count, int max_rows, const double* V, double* W, LpState* s,
+                   const double* lb, const double* ub, int nu, cudaStream_t st);
+// FP64 anchor GEMM x = Top w - c over the listed rows (DMMA kernel, tile shape picked by the device-side count)
+int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double* W, const double* Top, const double* C,
+                   LpState* s, cudaStream_t st);
+// listed rows: one FP64 Douglas-Rachford step from the exact x, first fp16 increment, state := iter_state
+int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
+                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, cudaStream_t st);
+// one tensor-core pass over rows [0, B) whose state == iter_state; flips s->cur
+int lp_iterate(const LpOperator* op, LpState* s, int B, double* V, const double* lb, const double* ub, const int* state,
+               int iter_state, unsigned long long* dres, int nu, double alpha, int device, cudaStream_t st);
+
+}  // namespace nnmpc

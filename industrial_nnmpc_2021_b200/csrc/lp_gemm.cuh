@@ -1,0 +1,341 @@
+// Split-operator tensor-core GEMM on the 5th-generation (tcgen05) tensor cores, sm_100a.
+//
+//   acc[M x N] (fp32, TMEM) = A[M x K] * (B1 + B2)[N x K]^T          A, B1, B2 fp16, K-contiguous
+//
+// This is the low-precision half of the regulator-QP iteration ("FP32 with FP64 residual
+// refinement"): the shared operator Top = (P + D)^-1 D is held as a two-term fp16 split
+// B1 + B2 ~ s_T Top (22 significant bits), A holds the per-sample INCREMENT dw of the
+// Douglas-Rachford operand (quantised to fp16 with a per-row power-of-two scale, the quantisation
+// residual is fed forward exactly), and the epilogue keeps every piece of solver state in FP64:
+//     x += acc / (s_T s_row);  d = x - clip(v);  v += alpha d;  dw+ = (2 clip(v) - v) - w_lp
+// The increments shrink with the iteration, so the low-precision error is relative to a vanishing
+// quantity; what error accumulates is removed by FP64 "anchor" GEMMs (x = Top w - c re-evaluated
+// with the FP64 tensor-core kernel) and every returned point is verified with P in FP64.
+// Replaces, like gemm_f64.cuh, the per-sample cvxopt solves of
+// /root/reference/lib/linearMPC.py:503-504.
+//
+// Kernel structure (one CTA per SM, persistent over output tiles, warp specialised):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of A, B1, B2 into a
+//              STAGES-deep shared-memory ring, completion on mbarriers
+//   warp 1     TMEM allocation + single-thread tcgen05.mma issue (M = 128, N = BN, K = 16 per
+//              instruction; the B1 and B2 products accumulate into the same TMEM tile),
+//              tcgen05.commit releases ring slots and publishes finished accumulators
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> FP64 update on
+//              registers -> global; TMEM accumulators are double buffered so the epilogue of tile
+//              i overlaps the MMAs of tile i+1
+#pragma once
+#include <cuda.h>   // CUtensorMap and its enums (types only: the encoder is fetched through cudart)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nnmpc {
+namespace lp {
+
+constexpr int BM = 128;          // rows (samples) per tile = TMEM lanes
+constexpr int BK = 64;           // fp16 elements per k-block = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 192;
+constexpr int ACC_STAGES = 2;
+
+template <int BN_, int STAGES_>
+struct LpTile {
+  static constexpr int BN = BN_, STAGES = STAGES_;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*1 KB alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// 2D tile load global -> shared, completion (bytes) on an mbarrier; c0 = innermost (k) coordinate
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 TMEM lanes (this warp's quarter) x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile written by TMA with 128-byte swizzle:
+// rows of 128 bytes (64 fp16), 8-row groups 1024 bytes apart (SBO), tile base 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address        bits [ 0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset  bits [16,30): unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                     // layout type SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: kind::f16, A = B = fp16 (0), D = fp32 (1), both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+struct LpShape {
+  int M;   // rows of A / of the output (samples)
+  int N;   // rows of B1/B2 = output columns
+  int K;   // contraction length (TMA zero-fills beyond it)
+};
+
+// Epilogue concept:
+//   struct Epi { struct Params {...};
+//     __device__ Epi(const Params&);
+//     // one thread owns output row `row` (may be >= M: then ok == false) and 32 consecutive columns
+//     __device__ void begin_row(int row, bool in_range);
+//     __device__ void chunk(int row, int col0, const uint32_t (&acc)[32] /*fp32 bit patterns*/, int N);
+//     __device__ void end_row(int row);
+//   };
+template <class T, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmB2, LpShape g, typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (128B-swizzle atoms span 8 rows x 128 B)
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + T::STAGES * T::STAGE_BYTES);
+  uint64_t* full = bars;                               // [STAGES]      TMA -> MMA
+  uint64_t* empty = bars + T::STAGES;                  // [STAGES]      MMA -> TMA
+  uint64_t* acc_full = bars + 2 * T::STAGES;           // [ACC_STAGES]  MMA -> epilogue
+  uint64_t* acc_empty = acc_full + ACC_STAGES;         // [ACC_STAGES]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntn = (g.N + T::BN - 1) / T::BN;
+  const int ntm = (g.M + BM - 1) / BM;
+  const int tiles = ntn * ntm;
+  const int KB = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmB2);
+    for (int s = 0; s < T::STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, T::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int bn = t % ntn, bm = t / ntn;     // column tiles fastest: resident CTAs share A row panels
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          uint8_t* st = ring + s * T::STAGE_BYTES;
+          mbar_expect_tx(full + s, T::STAGE_BYTES);
+          tma_load_2d(st, &tmA, full + s, kb * BK, bm * BM);
+          tma_load_2d(st + T::A_BYTES, &tmB1, full + s, kb * BK, bn * T::BN);
+          tma_load_2d(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN);
+          if (++s == T::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, T::BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+        const int as = i & 1;
+        const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(acc_empty + as, aph ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * T::BN);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + s * T::STAGE_BYTES);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db1 = make_sw128_kmajor_desc(sa + T::A_BYTES);
+          const uint64_t db2 = make_sw128_kmajor_desc(sa + T::A_BYTES + T::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
+            umma_f16(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+          umma_commit(empty + s);                 // ring slot free once these MMAs have read it
+          if (++s == T::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(acc_full + as);               // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    Epi epi(ep);
+    int i = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int bn = t % ntn, bm = t / ntn;
+      const int as = i & 1;
+      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+      const int row = bm * BM + q * 32 + lane;
+      epi.begin_row(row, row < g.M);
+      mbar_wait(acc_full + as, aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * T::BN);
+#pragma unroll 1
+      for (int cc = 0; cc < T::BN / 32; ++cc) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tacc + (uint32_t)(cc * 32), acc);
+        tmem_ld_wait();
+        epi.chunk(row, bn * T::BN + cc * 32, acc, g.N);
+      }
+      epi.end_row(row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, T::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+// cuTensorMapEncodeTiled fetched through the runtime (libnnmpc links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 row-major matrix [rows][cols] with leading dimension ld (elements, multiple of 8) -> tensor map with
+// boxes of box_rows x 64 elements, 128-byte swizzle, zero fill outside [rows] x [cols]
+inline bool make_tmap_f16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <class T, class Epi>
+inline cudaError_t launch_lp_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
+                                  const LpShape& g, const typename Epi::Params& ep, int num_sms, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(lp_gemm_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = true;
+  }
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
+  const long long tiles = (long long)((g.N + T::BN - 1) / T::BN) * ((g.M + BM - 1) / BM);
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+  lp_gemm_kernel<T, Epi><<<grid, THREADS, T::SMEM_BYTES, st>>>(tmA, tmB1, tmB2, g, ep);
+  return cudaGetLastError();
+}
+
+}  // namespace lp
+}  // namespace nnmpc

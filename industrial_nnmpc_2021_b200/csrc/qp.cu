@@ -30,11 +30,11 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof_spans;   // recorded since the last reset
 static std::vector<ProfSpan> g_prof_pool;    // events to reuse
-static double g_prof_extra_flops = 0.0;
+static double g_prof_extra_flops[2] = {0.0, 0.0};
 
-void prof_add_flops(double flops) {
+void prof_add_flops(double flops, int chan) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (g_prof_on) g_prof_extra_flops += flops;
+  if (g_prof_on) g_prof_extra_flops[chan & 1] += flops;
 }
 
 bool prof_begin(ProfSpan* sp, cudaStream_t st) {
@@ -50,10 +50,11 @@ bool prof_begin(ProfSpan* sp, cudaStream_t st) {
   cudaEventRecord(sp->a, st);
   return true;
 }
-void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches) {
+void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches, int chan) {
   cudaEventRecord(sp.b, st);
   sp.flops = flops;
   sp.launches = launches;
+  sp.chan = chan & 1;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_spans.push_back(sp);
 }
@@ -239,26 +240,40 @@ int nnmpc_prof_enable(int on) {
   return 0;
 }
 
-int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {
+// ms/flops/launches: arrays of 2 (channel 0 = iteration passes, channel 1 = FP64 anchors and exact checks)
+int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double t = 0.0, f = g_prof_extra_flops;
-  long long l = 0;
+  double t[2] = {0.0, 0.0}, f[2] = {g_prof_extra_flops[0], g_prof_extra_flops[1]};
+  long long l[2] = {0, 0};
   for (const ProfSpan& sp : g_prof_spans) {
     float e = 0.f;
     if (cudaEventSynchronize(sp.b) != cudaSuccess || cudaEventElapsedTime(&e, sp.a, sp.b) != cudaSuccess)
       return set_error(NNMPC_ERR_CUDA, "nnmpc_prof_read: %s", cudaGetErrorString(cudaGetLastError()));
-    t += e;
-    f += sp.flops;
-    l += sp.launches;
+    t[sp.chan] += e;
+    f[sp.chan] += sp.flops;
+    l[sp.chan] += sp.launches;
   }
-  if (ms) *ms = t;
-  if (flops) *flops = f;
-  if (launches) *launches = l;
+  for (int c = 0; c < 2; ++c) {
+    if (ms) ms[c] = t[c];
+    if (flops) flops[c] = f[c];
+    if (launches) launches[c] = l[c];
+  }
   if (reset) {
     for (const ProfSpan& sp : g_prof_spans) g_prof_pool.push_back(sp);
     g_prof_spans.clear();
-    g_prof_extra_flops = 0.0;
+    g_prof_extra_flops[0] = g_prof_extra_flops[1] = 0.0;
   }
+  return 0;
+}
+
+int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {
+  double t[2], f[2];
+  long long l[2];
+  int rc = nnmpc_prof_read2(t, f, l, reset);
+  if (rc < 0) return rc;
+  if (ms) *ms = t[0];
+  if (flops) *flops = f[0];
+  if (launches) *launches = l[0];
   return 0;
 }
 
@@ -280,9 +295,14 @@ int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N, const doubl
   h->n = n; h->nxa = nxa; h->nu = nu; h->N = N; h->device = device; h->alpha = alpha;
   h->cap = 0; h->nslots_cap = 0;
   h->p_norm_inf = 0.0;
+  h->top_max = 0.0;
   for (int r = 0; r < n; ++r) {
     double a = 0.0;
-    for (int c = 0; c < n; ++c) a += fabs(P_host[(size_t)r * n + c]);
+    for (int c = 0; c < n; ++c) {
+      a += fabs(P_host[(size_t)r * n + c]);
+      const double t = fabs(Top_host[(size_t)r * n + c]);
+      if (t > h->top_max) h->top_max = t;
+    }
     if (a > h->p_norm_inf) h->p_norm_inf = a;
   }
   NNMPC_TRY(upload(&h->P, P_host, (size_t)n * n));
@@ -306,6 +326,7 @@ int nnmpc_qp_destroy(nnmpc_qp_t* h) {
   h->part_max.release(); h->part_sum.release(); h->rows0.release(); h->rows1.release();
   h->hx0.release(); h->hlb.release(); h->hub.release(); h->hu.release(); h->hcost.release(); h->hkkt.release();
   h->hiters.release();
+  h->lpop.release();
   delete h;
   return 0;
 }

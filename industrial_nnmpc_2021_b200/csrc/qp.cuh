@@ -1,5 +1,7 @@
 // Internal interface of the batched regulator-QP solver (shared by qp.cu, sim.cu and mlp.cu).
 #pragma once
+#include <cuda.h>        // CUtensorMap (type only)
+#include <cuda_fp16.h>
 #include "nnmpc_common.cuh"
 #include "gemm_f64.cuh"
 
@@ -213,11 +215,24 @@ int qp_solve_device(nnmpc_qp* h, int B, const double* x0, const double* lb, cons
                     long long* iter_sum_out);
 
 // live timing of the iteration GEMM (bench.py roofline); spans are recorded only while enabled
-struct ProfSpan { cudaEvent_t a, b; double flops; long long launches; };
+// channel 0: the iteration passes (FP64 DMMA GEMM, or the tcgen05 pass in mixed mode);
+// channel 1: the FP64 anchor / exact-check GEMMs of the mixed mode
+struct ProfSpan { cudaEvent_t a, b; double flops; long long launches; int chan; };
 bool prof_begin(ProfSpan* sp, cudaStream_t st);
-void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches);
+void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches, int chan = 0);
 // flops of spans whose row counts only the device knew at launch time (added once they are read back)
-void prof_add_flops(double flops);
+void prof_add_flops(double flops, int chan = 0);
+
+// two-term fp16 split of a shared n x n operator, with the tensor maps the TMA producer reads it through
+struct LpOperator {
+  int n = 0;
+  long long ldh = 0;       // leading dimension of T1/T2 (elements, multiple of 64)
+  double scale = 1.0;      // T1 + T2 ~ scale * T
+  DevBuf<__half> T1, T2;
+  CUtensorMap tm1, tm2;
+  bool ready = false;
+  void release() { T1.release(); T2.release(); ready = false; }
+};
 
 }  // namespace nnmpc
 
@@ -226,6 +241,8 @@ struct nnmpc_qp {
   double alpha;
   double p_norm_inf;                  // ||P||_inf (max absolute row sum), scale of the convergence trigger
   double *P, *Top, *tq, *Mtq, *Kunc;  // device operators
+  double top_max;                     // max |Top|
+  nnmpc::LpOperator lpop;             // fp16 split of Top, built on first use by the mixed-precision iteration
   // scratch, sized for `cap` samples
   long long cap;
   int nslots_cap;

@@ -23,12 +23,13 @@
 // shape accumulates in the same order and every decision uses the row's own data.
 #include "qp.cuh"
 #include "ts.cuh"
+#include "lp.cuh"
 
 namespace nnmpc {
 int qp_ensure_scratch(nnmpc_qp* h, long long B);
 
-enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4 };
-enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_COUNTERS = 8 };
+enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4, SLOT_ANCHOR = 5 };
+enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_ANCHOR = 6, N_COUNTERS = 8 };
 constexpr int POLL_RING = 4;
 }  // namespace nnmpc
 
@@ -43,7 +44,12 @@ struct nnmpc_sim {
   long long cap;
   long long warm_B;   // batch size whose solver state (V, us_prev, kappa) is valid for `resume`; 0 = none
   nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, V, Z, xin, xcur, upcur, kappa, dtrig;
-  nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 4 x cap (active, cand, done, renew)
+  nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 5 x cap (active, cand, done, renew, anchor)
+  // mixed-precision iteration (tcgen05 fp16 increments + FP64 anchors), see lp_iter.cuh
+  int mixed;
+  nnmpc::LpState lps;
+  unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks
+  long long tot_rowiters, tot_anchors, tot_verifies, tot_qps;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
   int* counts;                      // device, N_COUNTERS ints
   unsigned long long* rowiters;     // device: total row-iterations executed (flop accounting)
@@ -122,8 +128,10 @@ struct EngineArrays {
   int* state; int* tcur; int* it;
   double* kappa; double* dtrig;
   unsigned long long* dres; unsigned long long* kres;
-  int* l_active; int* l_cand; int* l_done; int* l_renew;
+  int* l_active; int* l_cand; int* l_done; int* l_renew; int* l_anchor;
   int* counts; unsigned long long* rowiters;
+  // mixed-precision mode
+  int mixed; double* sc_in; double* sc_out; unsigned long long* stats; double alpha;
 };
 
 // after an iteration: bump iteration counters, pick the rows worth an exact KKT check
@@ -140,6 +148,10 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
       e.it[s] = it;
       const double d = __longlong_as_double((long long)e.dres[s]);
       e.dres[s] = 0ull;
+      if (e.mixed) {   // the operand written by this pass was quantised with sc_out; pick the next scale from ||d||
+        e.sc_in[s] = e.sc_out[s];
+        e.sc_out[s] = pow2_scale(3.0 * e.alpha * d);
+      }
       cand = (e.kappa[s] * d <= tol) || it >= max_iter;
       if (cand) {
         e.state[s] = SLOT_CAND;
@@ -152,6 +164,10 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
   if (threadIdx.x == 0) {
     e.counts[N_CAND] = base;
     *e.rowiters += (unsigned long long)na;
+    if (e.mixed) {
+      e.stats[0] += (unsigned long long)e.counts[N_ANCHOR];   // anchors served at the top of this loop
+      e.stats[1] += (unsigned long long)base;
+    }
   }
 }
 
@@ -173,10 +189,10 @@ __global__ void k_make_z(const int* __restrict__ rows, const int* __restrict__ c
 __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int max_iter, int T, int* out_iters,
                                                  double* out_kkt, double kappa_max) {
   const int nc = e.counts[N_CAND];
-  int base = 0;
+  int base = 0, nfail = 0;
   for (int i0 = 0; i0 < nc; i0 += 1024) {
     const int i = i0 + threadIdx.x;
-    bool done = false;
+    bool done = false, fail = false;
     int s = 0;
     if (i < nc) {
       s = e.l_cand[i];
@@ -184,11 +200,14 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
       const double d = e.dtrig[s];
       const int it = e.it[s];
       // recalibrate this trajectory's trigger from what the exact check saw (consecutive QPs are alike)
+      done = r <= tol || it >= max_iter;
       if (d > 1e-300 && r <= 1.7e308) {
         double k = fmax(1.3 * r / d, 0.7 * e.kappa[s]);
+        // mixed mode: a failed check may be drift of the fp16 path (removed by the anchor that follows),
+        // not a trigger that is too loose, so the trigger tightens by at most 2x per failure
+        if (e.mixed && !done) k = fmin(k, 2.0 * e.kappa[s]);
         e.kappa[s] = fmin(fmax(k, 1e-6), kappa_max);
       }
-      done = r <= tol || it >= max_iter;
       if (done) {
         e.state[s] = SLOT_DONE;
         const long long o = (long long)s * T + e.tcur[s];
@@ -196,12 +215,17 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
         if (out_kkt) out_kkt[o] = r;
         if (!(r <= tol)) e.counts[F_MAXITER] = 1;
       } else {
-        e.state[s] = SLOT_ITER;
+        fail = true;
+        e.state[s] = e.mixed ? SLOT_ANCHOR : SLOT_ITER;
       }
     }
     base = block_append(done, s, e.l_done, base);
+    if (e.mixed) nfail = block_append(fail, s, e.l_anchor, nfail);
   }
-  if (threadIdx.x == 0) e.counts[N_DONE] = base;
+  if (threadIdx.x == 0) {
+    e.counts[N_DONE] = base;
+    e.counts[N_ANCHOR] = nfail;   // k_step appends the renewed rows
+  }
 }
 
 // first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows
@@ -235,6 +259,9 @@ __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ 
 __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
   const int nd = e.counts[N_DONE];
   int base = 0, fin = 0;
+  const int na0 = e.mixed ? e.counts[N_ANCHOR] : 0;
+  int nanch = na0;
+  __syncthreads();
   for (int i0 = 0; i0 < nd; i0 += 1024) {
     const int i = i0 + threadIdx.x;
     bool renew = false;
@@ -248,17 +275,19 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
     }
     fin += __syncthreads_count(i < nd && !renew);
     base = block_append(renew, s, e.l_renew, base);
+    if (e.mixed) nanch = block_append(renew, s, e.l_anchor, nanch);
   }
   int na = 0;
   if (nd > 0) {   // only a finished trajectory changes the active list, but rebuilding is cheap
     for (int i0 = 0; i0 < S; i0 += 1024) {
       const int s = i0 + threadIdx.x;
-      const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW);
+      const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW || e.state[s] == SLOT_ANCHOR);
       na = block_append(live, s, e.l_active, na);
     }
   }
   if (threadIdx.x == 0) {
     e.counts[N_RENEW] = base;
+    if (e.mixed) e.counts[N_ANCHOR] = nanch;
     e.counts[N_FINISHED] += fin;
     if (nd > 0) e.counts[N_ACTIVE] = na;
   }
@@ -269,7 +298,8 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
 __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
                              int* __restrict__ it, unsigned long long* __restrict__ dres, double* __restrict__ V,
                              double* __restrict__ Zs, double* __restrict__ W, const double* __restrict__ dus,
-                             const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu, int cold) {
+                             const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu, int cold,
+                             int next_state, int write_w) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   double* v = V + s * n;
@@ -287,16 +317,17 @@ __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict
     const double vn = cold ? v[j] : z[j];
     const int k = j % nu;
     if (!cold) v[j] = vn;
-    w[j] = 2.0 * clipd(vn, lb[s * nu + k], ub[s * nu + k]) - vn;
+    if (write_w) w[j] = 2.0 * clipd(vn, lb[s * nu + k], ub[s * nu + k]) - vn;
   }
   if (threadIdx.x == 0) {
-    state[s] = SLOT_ITER;
+    state[s] = next_state;
     it[s] = 0;
     dres[s] = 0ull;
   }
 }
 
 __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kappa0) {
+  if (e.mixed && blockIdx.x * blockDim.x + threadIdx.x < S) e.l_anchor[blockIdx.x * blockDim.x + threadIdx.x] = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < S) {
     e.state[s] = SLOT_RENEW;
@@ -316,7 +347,9 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
     e.counts[N_RENEW] = S;
     e.counts[N_FINISHED] = 0;
     e.counts[F_MAXITER] = 0;
+    e.counts[N_ANCHOR] = e.mixed ? S : 0;
     *e.rowiters = 0ull;
+    if (e.mixed) e.stats[0] = e.stats[1] = 0ull;
   }
 }
 
@@ -339,7 +372,7 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
   NNMPC_TRY(h->state.ensure(B));
   NNMPC_TRY(h->tcur.ensure(B));
   NNMPC_TRY(h->it.ensure(B));
-  NNMPC_TRY(h->lists.ensure(4 * B));
+  NNMPC_TRY(h->lists.ensure(5 * B));
   NNMPC_TRY(h->dres.ensure(B));
   NNMPC_TRY(h->kres.ensure(B));
   h->cap = B;
@@ -357,6 +390,11 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   const bool cont = resume && h->warm_B == B;
   h->warm_B = 0;
   const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = q->n, nxa = h->nxa_ld;
+  const int mixed = h->mixed;
+  if (mixed) {
+    if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
+    NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n));
+  }
   NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
@@ -365,8 +403,9 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   e.state = h->state.p; e.tcur = h->tcur.p; e.it = h->it.p; e.kappa = h->kappa.p; e.dtrig = h->dtrig.p;
   e.dres = h->dres.p; e.kres = h->kres.p;
   e.l_active = h->lists.p; e.l_cand = h->lists.p + B; e.l_done = h->lists.p + 2 * (long long)B;
-  e.l_renew = h->lists.p + 3 * (long long)B;
+  e.l_renew = h->lists.p + 3 * (long long)B; e.l_anchor = h->lists.p + 4 * (long long)B;
   e.counts = h->counts; e.rowiters = h->rowiters;
+  e.mixed = mixed; e.sc_in = h->lps.sc_in.p; e.sc_out = h->lps.sc_out.p; e.stats = h->stats; e.alpha = q->alpha;
   k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0);
   count_launch();
 
@@ -397,7 +436,8 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     count_launch(2);
     if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
     k_warm_shift<<<B, 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
-                                    h->dus.p, h->lb.p, h->ub.p, n, nu, cold);
+                                    h->dus.p, h->lb.p, h->ub.p, n, nu, cold, mixed ? SLOT_ANCHOR : SLOT_ITER,
+                                    mixed ? 0 : 1);
     count_launch();
     return 0;
   };
@@ -409,7 +449,24 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   long long loop = 0;
   for (; loop < max_loops && !finished; ++loop) {
     // 1. one Douglas-Rachford iteration for every live trajectory
-    {
+    if (mixed) {
+      // 1a. FP64 anchors for the rows that start a QP or failed an exact check: x = Top w - c with the
+      //     DMMA kernel, one full-precision step, first fp16 increment
+      int* cnt = e.counts + N_ANCHOR;
+      ProfSpan span64;
+      const bool prof64 = prof_begin(&span64, st);
+      NNMPC_TRY(lp_anchor_prep(e.l_anchor, cnt, B, h->V.p, q->W0.p, &h->lps, h->lb.p, h->ub.p, nu, st));
+      NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
+      NNMPC_TRY(lp_dr_first(e.l_anchor, cnt, B, &h->lps, h->V.p, q->W0.p, h->lb.p, h->ub.p, e.state, e.it, SLOT_ITER, nu,
+                            q->alpha, st));
+      if (prof64) prof_end(span64, st, 0.0, 1, 1);
+      // 1b. tensor-core pass (tcgen05, fp16 increments of the operand, state in FP64) over every live row
+      ProfSpan span;
+      const bool prof = prof_begin(&span, st);
+      NNMPC_TRY(lp_iterate(&q->lpop, &h->lps, B, h->V.p, h->lb.p, h->ub.p, e.state, SLOT_ITER, e.dres, nu, q->alpha,
+                           h->device, st));
+      if (prof) prof_end(span, st, 0.0, 1);
+    } else {
       GemmOperands gi{};
       gi.A = Wc; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = e.l_active;
       gi.m_count = e.counts + N_ACTIVE;
@@ -429,7 +486,10 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
       gv.A = h->Z.p; gv.lda = n; gv.Bt = q->P; gv.ldb = n; gv.M = B; gv.N = n; gv.K = n; gv.rows = e.l_cand;
       gv.m_count = e.counts + N_CAND;
       EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu};
+      ProfSpan span64;
+      const bool prof64 = mixed && prof_begin(&span64, st);
       NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
+      if (prof64) prof_end(span64, st, 0.0, 1, 1);
     }
     k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
     // 5. first move, dataset row, plant step for the done rows
@@ -461,8 +521,10 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   }
   // drain: the last loops may not have been polled yet
   unsigned long long* pin64 = reinterpret_cast<unsigned long long*>(h->pin + POLL_RING * N_COUNTERS);
+  pin64[1] = pin64[2] = 0ull;
   NNMPC_CUDA(cudaMemcpyAsync(h->pin, h->counts, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(pin64, h->rowiters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (mixed) NNMPC_CUDA(cudaMemcpyAsync(pin64 + 1, h->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(x_io, h->xcur.p, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(uprev_io, h->upcur.p, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));
@@ -471,7 +533,12 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], B);
   if (h->pin[F_MAXITER]) rc_warn = NNMPC_WARN_MAXITER;
   g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
-  prof_add_flops(2.0 * n * (double)n * (double)*pin64);
+  prof_add_flops(2.0 * n * (double)n * (double)*pin64);                               // iteration passes
+  prof_add_flops(2.0 * n * (double)n * (double)(pin64[1] + pin64[2]), 1);             // FP64 anchors + checks
+  h->tot_rowiters += (long long)pin64[0];
+  h->tot_anchors += (long long)pin64[1];
+  h->tot_verifies += (long long)pin64[2];
+  h->tot_qps += (long long)B * T;
   h->warm_B = B;
   return rc_warn;
 }
@@ -498,6 +565,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->kin_ld = (kin + 1) & ~1;
   h->cap = 0;
   h->warm_B = 0;
+  h->mixed = 0;
+  h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
@@ -512,7 +581,9 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   if (rc < 0) return rc;
   NNMPC_CUDA(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)));
   NNMPC_CUDA(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)));
-  NNMPC_CUDA(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 2 * sizeof(unsigned long long)));
+  NNMPC_CUDA(cudaMalloc((void**)&h->stats, 2 * sizeof(unsigned long long)));
+  NNMPC_CUDA(cudaMemset(h->stats, 0, 2 * sizeof(unsigned long long)));
+  NNMPC_CUDA(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 4 * sizeof(unsigned long long)));
   for (int i = 0; i < POLL_RING; ++i) NNMPC_CUDA(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming));
   *out = h;
   return 0;
@@ -524,7 +595,9 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   cudaFree(h->ABd);
   cudaFree(h->counts);
   cudaFree(h->rowiters);
+  cudaFree(h->stats);
   cudaFreeHost(h->pin);
+  h->lps.release();
   for (int i = 0; i < POLL_RING; ++i) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
   h->Z.release(); h->xin.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
@@ -533,6 +606,21 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   h->h_us.release(); h->h_u.release(); h->h_kkt.release(); h->h_xio.release(); h->h_upio.release();
   h->h_iters.release();
   delete h;
+  return 0;
+}
+
+int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_precision: null handle");
+  if (mode != NNMPC_PRECISION_F64 && mode != NNMPC_PRECISION_MIXED)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_precision: unknown mode %d", mode);
+  if (h->mixed != (mode == NNMPC_PRECISION_MIXED)) h->warm_B = 0;   // solver state is not shared between the modes
+  h->mixed = mode == NNMPC_PRECISION_MIXED;
+  return 0;
+}
+
+int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4) {
+  if (!h || !out4) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_stats: null argument");
+  out4[0] = h->tot_rowiters; out4[1] = h->tot_anchors; out4[2] = h->tot_verifies; out4[3] = h->tot_qps;
   return 0;
 }
 

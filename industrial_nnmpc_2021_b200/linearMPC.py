@@ -11,6 +11,7 @@ There is no CPU fallback: constructing a solver without the built library / a CU
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 import time
 
@@ -546,7 +547,10 @@ def load_training_data(filename):
 class ClosedLoopEngine:
     """Owns the nnmpc_sim handle for one (regulator, target selector, plant) triple."""
 
-    def __init__(self, regulator, target_selector, A, B, Bd):
+    def __init__(self, regulator, target_selector, A, B, Bd, precision=None):
+        """``precision``: "f64" (every iteration an FP64 tensor-core GEMM) or "mixed" (tcgen05 fp16
+        increments with FP64 anchors; every result still passes an FP64 KKT check).  Default: the
+        environment variable NNMPC_PRECISION, else "mixed"."""
         if regulator._dev != target_selector._dev:
             raise ValueError("regulator and target selector live on different devices")
         self.regulator, self.target_selector = regulator, target_selector
@@ -561,6 +565,20 @@ class ClosedLoopEngine:
                                 self.ny, _lib.hptr(ABd), self._dev)
         _lib.check(rc, "nnmpc_sim_create")
         self._handle = hnd
+        self.set_precision(precision or os.environ.get("NNMPC_PRECISION", "mixed"))
+
+    def set_precision(self, precision):
+        if precision not in _lib.PRECISION:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)}")
+        _lib.check(_lib.lib().nnmpc_sim_set_precision(self._handle, _lib.PRECISION[precision]),
+                   "nnmpc_sim_set_precision")
+        self.precision = precision
+
+    def stats(self):
+        """Cumulative solver work since construction: row-iterations, FP64 anchors, exact KKT checks, QPs."""
+        out = (C.c_longlong * 4)()
+        _lib.check(_lib.lib().nnmpc_sim_stats(self._handle, out), "nnmpc_sim_stats")
+        return dict(row_iterations=out[0], anchors=out[1], exact_checks=out[2], qps=out[3])
 
     def __del__(self):
         try:

@@ -219,9 +219,39 @@ def test_target_selector_matches_oracle(torch_cuda, which, cstrs_problem, cdu_sm
     assert oxs1.shape == (p.Nx, 1) and ous1.shape == (p.Nu, 1) and len(ts.xs) == 1
 
 
+# ------------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,n", [(128, 128), (1, 64), (300, 540), (1000, 40), (257, 4480), (2688, 1000)])
+def test_lp_split_gemm_matches_fp64(torch_cuda, M, n):
+    """The tcgen05 pass C = fp16(A) (T1 + T2)' / s (TMA-fed, TMEM-accumulated) against FP64 NumPy: the
+    two-term fp16 operator split carries ~22 bits, the fp32 accumulation ~2^-24 sqrt(K) of sum |a||t|."""
+    torch = torch_cuda
+    from industrial_nnmpc_2021_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(M * 7 + n)
+    A = rng.standard_normal((M, n)) * np.exp(rng.uniform(-6, 2, (M, 1)))
+    Bt = rng.standard_normal((n, n)) * np.exp(rng.uniform(-8, 0, (n, n)))
+    At, Btt = torch.tensor(A, device="cuda"), torch.tensor(Bt, device="cuda")
+    Cd = torch.full((M, n), np.nan, dtype=torch.float64, device="cuda")
+    rc = L.nnmpc_lp_gemm_test(M, n, n, _lib.dptr(At), _lib.dptr(Btt), float(np.abs(Bt).max()), _lib.dptr(Cd), None)
+    _lib.check(rc, "nnmpc_lp_gemm_test")
+    torch.cuda.synchronize()
+    A16 = A.astype(np.float16).astype(np.float64)
+    ref = A16 @ Bt.T
+    bound = 3e-6 * (np.abs(A16) @ np.abs(Bt).T) + 1e-10 * np.abs(A16).sum(axis=1, keepdims=True) * np.abs(Bt).max()
+    err = np.abs(Cd.cpu().numpy() - ref)
+    assert np.all(np.isfinite(err)) and np.all(err <= bound), float((err / bound).max())
+
+
 # ------------------------------------------------------------------------------------ closed loop
+@pytest.fixture(params=["f64", "mixed"])
+def precision(request, monkeypatch):
+    """Arithmetic of the closed-loop iteration: FP64 DMMA, or tcgen05 fp16 increments + FP64 anchors."""
+    monkeypatch.setenv("NNMPC_PRECISION", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("which", ["cstrs", "cdu_small"])
-def test_closed_loop_matches_oracle(torch_cuda, which, cstrs_problem, cdu_small_problem, cstr_case):
+def test_closed_loop_matches_oracle(torch_cuda, which, cstrs_problem, cdu_small_problem, cstr_case, precision):
     """OfflineSimulator data == oracle simulate_offline, sample by sample."""
     from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
     if which == "cstrs":
@@ -246,7 +276,7 @@ def test_closed_loop_matches_oracle(torch_cuda, which, cstrs_problem, cdu_small_
     assert res["iters"].min() >= 1
 
 
-def test_generate_data_files_and_sharding_invariance(torch_cuda, cdu_small_problem, tmp_path, monkeypatch):
+def test_generate_data_files_and_sharding_invariance(torch_cuda, cdu_small_problem, tmp_path, monkeypatch, precision):
     """generate_data writes {task}-{proc}-file per process with the reference's keys; results do not
     depend on how chunks are grouped into batches."""
     from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator, load_training_data
@@ -267,7 +297,7 @@ def test_generate_data_files_and_sharding_invariance(torch_cuda, cdu_small_probl
             assert np.array_equal(d[k], all4[k][2 + proc]), k     # bitwise: batching does not change results
 
 
-def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem):
+def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem, precision):
     """Many trajectories of different lengths-to-convergence in one continuously batched run: the
     batch crosses all three GEMM tile shapes (<=48, <=384, >384 rows) as trajectories finish, and
     every trajectory must come out bitwise identical to the same trajectory run in a small batch,
@@ -295,7 +325,7 @@ def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem):
             assert np.max(np.abs(big[k][c] - od[k])) / max(1.0, np.max(np.abs(od[k]))) <= 1e-6, (c, k)
 
 
-def test_closed_loop_resume_in_slabs(torch_cuda, cdu_small_problem):
+def test_closed_loop_resume_in_slabs(torch_cuda, cdu_small_problem, precision):
     """A trajectory advanced slab by slab (resume=True keeps the solver state) reproduces the
     single-call run within tolerance and needs no more iterations on the slab boundaries."""
     from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
