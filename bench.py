@@ -208,8 +208,10 @@ def _config(args, traj, slab):
     return {"workload": "CDU linear-MPC closed-loop offline data generation (BASELINE.json configs[2]): synthetic "
                         "CDU stand-in 252x32x90, reference tuning, PRBS scenarios",
             "Nx": 252, "Nu": 32, "Ny": 90, "horizon": args.horizon, "qp_vars": args.horizon * 32,
-            "trajectories_per_gpu": traj, "sim_steps_per_step": slab, "tol_kkt": KKT_TOL,
-            "l2": "no flush: operators (2 x 161 MB) + solver state exceed the 126 MB L2 every iteration",
+            "trajectories_per_gpu": traj, "concurrent_slots_per_gpu": min(traj, getattr(args, "slots", traj)),
+            "sim_steps_per_step": slab, "tol_kkt": KKT_TOL,
+            "precision": args.precision,
+            "l2": "no flush: operators (2 x 161 MB FP64 + 2 x 40 MB fp16) + solver state exceed the 126 MB L2 every iteration",
             "parallelism": f"trajectories sharded over {args.gpus} GPU(s), no collective on the solve path"}
 
 
@@ -246,7 +248,7 @@ def run_native(args):
     ts = LinearMPCController.setup_target_selector(p.A, p.B, p.C, p.H, p.Bd, p.Cd, p.usp, p.Qs, p.Rs, p.ulb, p.uub,
                                                    device=dev)
     reg = LinearMPCController.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub, device=dev)
-    eng = ClosedLoopEngine(reg, ts, p.A, p.B, p.Bd)
+    eng = ClosedLoopEngine(reg, ts, p.A, p.B, p.Bd, precision=args.precision, slots=args.slots)
     t_setup = time.perf_counter() - t_setup
     n, nx, nu, ny, nd = p.N * p.Nu, p.Nx, p.Nu, p.Ny, p.Nd
 
@@ -282,6 +284,7 @@ def run_native(args):
     barrier()
     _lib.prof_enable(True)
     _lib.prof_read(reset=True)
+    st0 = eng.stats()
     launches0 = L.nnmpc_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -298,8 +301,9 @@ def run_native(args):
         barrier()
     ms_dev = maxrank(ev0.elapsed_time(ev1))
     launches = L.nnmpc_launch_count() - launches0
-    gemm_ms, gemm_flops, gemm_launches = _lib.prof_read(reset=True)
+    (gemm_ms, gemm_flops, gemm_launches), (f64_ms, f64_flops, f64_launches) = _lib.prof_read2(reset=True)
     _lib.prof_enable(False)
+    st1 = eng.stats()
     kkt_max, it_sum, it_max = float(kkt_acc), int(it_sum), int(it_acc)
     clocks = clk.summary()
     value = world * B * Ts * K / (ms_dev * 1e-3)
@@ -368,14 +372,37 @@ def run_native(args):
         best = max(best, 2 * 6144 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12)
     del a, b
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAdmm> (regulator-QP iteration, FP64 DMMA)",
-                "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
-                "traffic": None, "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
-                "share_of_step": gemm_ms / (ms_dev if world == 1 else ev0.elapsed_time(ev1)),
-                "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (FP64 has no tcgen05 kind; "
-                               f"MEASURED_PEAKS.json carries bf16 {peaks.get('bf16_tflops')} TF/s and HBM "
-                               f"{peaks.get('hbm_gbs')} GB/s only, {peak_src})",
-                "flops_per_launch": "active samples x 2 n^2 (n = 4480: 40.14 MFLOP per sample-iteration)"}
+    step_ms_local = ms_dev if world == 1 else ev0.elapsed_time(ev1)
+    dgemm_src = ("cuBLAS DGEMM 6144^3 measured in this run (FP64 has no tcgen05 kind; "
+                 f"MEASURED_PEAKS.json carries bf16 {peaks.get('bf16_tflops')} TF/s and HBM "
+                 f"{peaks.get('hbm_gbs')} GB/s only, {peak_src})")
+    nvar = args.horizon * 32
+    per_unit = f"active samples x 2 n^2 (n = {nvar}: {2 * nvar * nvar / 1e6:.2f} MFLOP per sample-iteration)"
+    if args.precision == "f64":
+        roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAdmm> (regulator-QP iteration, FP64 DMMA)",
+                    "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+                    "traffic": None, "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+                    "share_of_step": gemm_ms / step_ms_local, "peak_source": dgemm_src, "flops_per_launch": per_unit}
+        roofline2 = None
+    else:
+        lp_peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0)
+        f64_ach = f64_flops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else 0.0
+        r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
+                                             "increments x two-term fp16 operator split, fp32 TMEM accumulators, FP64 state)",
+                "achieved": achieved, "executed_mma": 2.0 * achieved, "peak": lp_peak, "unit": "TFLOP/s",
+                "frac": achieved / lp_peak, "frac_executed": 2.0 * achieved / lp_peak, "traffic": None,
+                "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+                "share_of_step": gemm_ms / step_ms_local,
+                "peak_source": f"dense 16-bit tensor throughput, sustained figure of MEASURED_PEAKS.json ({peak_src}); "
+                               "kernel timed inside a long step",
+                "flops_per_launch": per_unit + "; the kernel executes 2x that in MMA work (T1 and T2 products)"}
+        r_64 = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAnchor|EpiVerifyMax> (FP64 anchors x = Top w - c and "
+                                             "exact KKT checks P z + q, DMMA, small row lists)",
+                "achieved": f64_ach, "peak": best, "unit": "TFLOP/s", "frac": f64_ach / best if best else None,
+                "traffic": None, "launches": f64_launches, "avg_launch_ms": f64_ms / max(f64_launches, 1),
+                "share_of_step": f64_ms / step_ms_local, "peak_source": dgemm_src,
+                "flops_per_launch": "listed samples x 2 n^2"}
+        roofline, roofline2 = (r_lp, r_64) if gemm_ms >= f64_ms else (r_64, r_lp)
 
     if rank == 0:
         cpu = None
@@ -389,7 +416,10 @@ def run_native(args):
             "dtype": "f64", "data": "synthetic", "config": _config(args, B, Ts),
             "qp_solves_per_s": {"regulator": value, "target_selector": value},
             "iterations": {"mean": it_sum / (B * Ts * K), "max": it_max, "kkt_max": kkt_max},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_second_kernel": roofline2, "cpu_baseline": cpu,
+            "precision": args.precision,
+            "solver_work_per_qp": {k: (st1[k] - st0[k]) / max(st1["qps"] - st0["qps"], 1)
+                                   for k in ("row_iterations", "anchors", "exact_checks")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K, "kkt_max": e2e_kkt},
             "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup, "gather": gather,
@@ -411,7 +441,12 @@ def main():
     ap.add_argument("--slab", type=int, default=32, help="simulation steps every trajectory advances per bench step")
     ap.add_argument("--horizon", type=int, default=140)
     ap.add_argument("--ref-steps", type=int, default=1, help="closed-loop steps per worker per reference step")
+    ap.add_argument("--slots", type=int, default=8192,
+                    help="trajectories advanced concurrently per GPU; with --traj above it the other chunks queue up and "
+                         "finished slots take the next one (continuous batching)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"],
+                    help="regulator-QP iteration arithmetic: tcgen05 fp16 increments + FP64 anchors, or all FP64 DMMA")
     ap.add_argument("--max-iter", type=int, default=3000, help="per-QP iteration cap (a hit rejects the number)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -117,6 +117,19 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h);
  *                          the drift whenever an exact check fails */
 enum { NNMPC_PRECISION_F64 = 0, NNMPC_PRECISION_MIXED = 1 };
 int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode);
+/* At most `slots` trajectories advance concurrently (default 8192).  A call with B > slots queues the
+ * remaining chunks: a slot that finishes its chunk immediately takes the next one (cold start from
+ * that chunk's x_io/uprev_io row), so the batch stays full until the queue is empty - the continuous
+ * batching that replaces the reference's one-OS-process-per-chunk fan-out (lib/linearMPC.py:817-825).
+ * With B > slots `resume` is ignored (every chunk starts cold). */
+int nnmpc_sim_set_slots(nnmpc_sim_t* h, int slots);
+/* Mixed mode only: the FP64 phases (anchors, exact checks, plant step, next targets) run every
+ * `cadence`-th engine loop over the rows that accumulated meanwhile (default 2; 1 = every loop). */
+int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence);
+/* Mixed mode only: once at most `rows` trajectories of a call are still running, the rest of the call
+ * iterates with skinny FP64 GEMMs over just those rows instead of full tensor-core passes
+ * (rows < 0: automatic, max(48, B/16); 0: never). */
+int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
 /* cumulative since create: out4 = {row-iterations, FP64 anchors, exact KKT checks, QPs solved} */
 int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
@@ -150,7 +163,8 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
  * nnmpc_lp_gemm_test: the tcgen05 split-operator GEMM, C[M x N] = fp16(A)[M x K] (T1 + T2)[N x K]^T / s with
  * (T1, T2, s) the two-term fp16 split of the square FP64 operator Bt (N == K, bt_max = max |Bt|);
  * A, Bt, C are dense row-major FP64 device matrices. */
-int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, void* stream);
+int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, int pair,
+                       void* stream);   /* pair != 0: the CTA-pair (cta_group::2) kernel, else the one-CTA kernel */
 /* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,
                   long long ldb, double* C, long long ldc, const int* rows, void* stream);

@@ -85,9 +85,15 @@ gemm_f64_kernel(GemmOperands g, typename Epi::Params ep) {
   const int Mact = min(Mraw, g.M);
   // linearised grid, column tiles fastest: CTAs resident together share A row panels and sweep Bt
   const int ntn = (g.N + T::BN - 1) / T::BN;
-  const int bn = blockIdx.x % ntn, bm = blockIdx.x / ntn;
-  const int m0 = bm * T::BM, n0 = bn * T::BN;
-  if (m0 >= Mact || Mraw <= g.m_lo || Mraw > g.m_hi) return;
+  const int bn = blockIdx.x % ntn;
+  const int n0 = bn * T::BN;
+  if (Mraw <= g.m_lo || Mraw > g.m_hi) return;
+  // Row tiles: one per CTA when the row count is known at launch; for a device-side count the grid is capped
+  // (see launch_gemm) and each CTA strides over the row tiles, so a short list costs few empty CTAs.
+  const int bm_stride = gridDim.x / ntn;
+  for (int bm = blockIdx.x / ntn; bm * T::BM < Mact; bm += bm_stride) {
+  const int m0 = bm * T::BM;
+  __syncthreads();   // the previous row tile's last fragments have been read before the ring is refilled
 
   double* As = smem;
   double* Bs = smem + T::STAGES * T::A_ELEMS;
@@ -189,6 +195,7 @@ gemm_f64_kernel(GemmOperands g, typename Epi::Params ep) {
     }
     epi.finish_row(pr, lr, slot, rok);   // all 32 lanes participate (warp shuffles inside)
   }
+  }  // row tiles of this CTA
 }
 
 template <class T, class Epi>
@@ -203,8 +210,13 @@ inline cudaError_t launch_gemm(const GemmOperands& g, const typename Epi::Params
     configured[dev & 63] = true;
   }
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  long long tiles = (long long)((g.N + T::BN - 1) / T::BN) * ((g.M + T::BM - 1) / T::BM);
-  gemm_f64_kernel<T, Epi><<<(unsigned)tiles, T::THREADS, T::SMEM_BYTES, st>>>(g, ep);
+  const long long ntn = (g.N + T::BN - 1) / T::BN;
+  long long ntm = (g.M + T::BM - 1) / T::BM;
+  if (g.m_count) {   // device-side row count: about eight waves of CTAs at most, the CTAs stride over the row tiles
+    const long long cap = (8 * 148 + ntn - 1) / ntn;
+    if (ntm > cap) ntm = cap;
+  }
+  gemm_f64_kernel<T, Epi><<<(unsigned)(ntn * ntm), T::THREADS, T::SMEM_BYTES, st>>>(g, ep);
   return cudaGetLastError();
 }
 

@@ -2,9 +2,22 @@
 // tensor maps, and the self-test entry point.
 #include "lp_iter.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace nnmpc {
+
+// which tcgen05 kernel serves the passes: the one-CTA kernel (128 x 128 tiles) unless
+// NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles; same speed today: both are epilogue-bound)
+static bool lp_use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNMPC_LP_KERNEL");
+    v = (e && strcmp(e, "pair") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
 
 int device_sm_count(int device) {
   static int cache[64] = {};
@@ -26,7 +39,7 @@ int lp_state_ensure(LpState* s, long long B, int n) {
   NNMPC_TRY(s->sc_in.ensure((size_t)cap));
   NNMPC_TRY(s->sc_out.ensure((size_t)cap));
   // rows and columns padded to whole TMA boxes (zeros), so no tile ever reaches outside the tensor
-  const long long cap_pad = (cap + lp::BM - 1) / lp::BM * lp::BM;
+  const long long cap_pad = (cap + 2 * lp::BM - 1) / (2 * lp::BM) * (2 * lp::BM);
   for (int b = 0; b < 2; ++b) {
     NNMPC_TRY(s->D[b].ensure((size_t)cap_pad * s->ldd));
     NNMPC_CUDA(cudaMemset(s->D[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half)));
@@ -56,24 +69,28 @@ int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double
 }
 
 int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
-                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, cudaStream_t st) {
+                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
+                cudaStream_t st) {
   if (max_rows <= 0) return 0;
   k_dr_first<<<max_rows, 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
-                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha);
+                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
 }
 
-int lp_iterate(const LpOperator* op, LpState* s, int B, double* V, const double* lb, const double* ub, const int* state,
-               int iter_state, unsigned long long* dres, int nu, double alpha, int device, cudaStream_t st) {
+int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
+               const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
+               double alpha, int device, cudaStream_t st) {
   if (B <= 0) return 0;
   EpiDelta::Params ep{};
   ep.X = s->X.p; ep.V = V; ep.E = s->E.p; ep.Dn = s->D[s->cur ^ 1].p; ep.ldd = s->ldd; ep.lb = lb; ep.ub = ub;
-  ep.state = state; ep.iter_state = iter_state; ep.sc_in = s->sc_in.p; ep.sc_out = s->sc_out.p; ep.dres = dres;
+  ep.state = state; ep.iter_state = iter_state; ep.list_r = list_r; ep.pos_w = pos_w; ep.sc_in = s->sc_in.p; ep.sc_out = s->sc_out.p; ep.dres = dres;
   ep.n = s->n; ep.nu = nu; ep.alpha = alpha; ep.inv_sT = 1.0 / op->scale;
-  lp::LpShape g{B, s->n, s->n};
-  cudaError_t e = lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
+  lp::LpShape g{B, s->n, s->n, len_r};
+  cudaError_t e = lp_use_pair()
+                      ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
+                      : lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
   count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));
   s->cur ^= 1;
@@ -88,7 +105,7 @@ int lp_split_operator(const double* T_dev, int n, double tmax, LpOperator* op, c
   int ex = 0;
   frexp(tmax > 0.0 ? tmax : 1.0, &ex);
   op->scale = ldexp(1.0, 10 - ex);
-  const long long rows_pad = ((long long)n + LpTileN128::BN - 1) / LpTileN128::BN * LpTileN128::BN;
+  const long long rows_pad = ((long long)n + lp::BN2 - 1) / lp::BN2 * lp::BN2;
   NNMPC_TRY(op->T1.ensure((size_t)rows_pad * op->ldh));
   NNMPC_TRY(op->T2.ensure((size_t)rows_pad * op->ldh));
   NNMPC_CUDA(cudaMemsetAsync(op->T1.p, 0, (size_t)rows_pad * op->ldh * sizeof(__half), st));
@@ -121,7 +138,8 @@ extern "C" {
 
 // Self test of the tcgen05 path:  C[M x N] = fp16(A)[M x K] * (T1 + T2)[N x K]^T / s  with (T1, T2, s) the
 // two-term fp16 split of Bt.  A, Bt, C are FP64 device matrices (row-major, dense).
-int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, void* stream) {
+int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, int pair,
+                       void* stream) {
   if (!A || !Bt || !C || M <= 0 || N <= 0 || K <= 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_lp_gemm_test: bad argument");
   if (N != K) return set_error(NNMPC_ERR_BADARG, "nnmpc_lp_gemm_test: the operator must be square (N == K)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -130,7 +148,7 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
   LpOperator op;
   int rc = lp_split_operator(Bt, N, bt_max, &op, st);
   DevBuf<__half> Ah;
-  const long long m_pad = ((long long)M + lp::BM - 1) / lp::BM * lp::BM;
+  const long long m_pad = ((long long)M + 2 * lp::BM - 1) / (2 * lp::BM) * (2 * lp::BM);
   if (rc == 0) rc = Ah.ensure((size_t)m_pad * op.ldh);
   if (rc == 0) {
     cudaMemsetAsync(Ah.p, 0, (size_t)m_pad * op.ldh * sizeof(__half), st);
@@ -140,9 +158,10 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
     if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
       rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
-      lp::LpShape g{M, N, K};
-      cudaError_t e = lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, EpiLpStore::Params{C, N, 1.0 / op.scale},
-                                                                 device_sm_count(dev), st);
+      lp::LpShape g{M, N, K, nullptr};
+      const EpiLpStore::Params ep{C, N, 1.0 / op.scale};
+      cudaError_t e = pair ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
+                           : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);
       count_launch();
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));

@@ -44,10 +44,15 @@ int lp_anchor_prep(const int* rows, const int* count, int max_rows, const double
 int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double* W, const double* Top, const double* C,
                    LpState* s, cudaStream_t st);
 // listed rows: one FP64 Douglas-Rachford step from the exact x, first fp16 increment, state := iter_state
+// pos_r: sample row -> row of the operand buffer the next pass reads (null = identity)
 int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
-                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, cudaStream_t st);
-// one tensor-core pass over rows [0, B) whose state == iter_state; flips s->cur
-int lp_iterate(const LpOperator* op, LpState* s, int B, double* V, const double* lb, const double* ub, const int* state,
-               int iter_state, unsigned long long* dres, int nu, double alpha, int device, cudaStream_t st);
+                const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
+                cudaStream_t st);
+// One tensor-core pass over the operand rows [0, *len_r) (at most B); flips s->cur.  Operand row p belongs to
+// sample list_r[p]; it takes part iff state[sample] == iter_state, and its next increment is written to
+// operand row pos_w[sample] of the other buffer (so the layout is re-compacted one pass behind the live list).
+int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
+               const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
+               double alpha, int device, cudaStream_t st);
 
 }  // namespace nnmpc

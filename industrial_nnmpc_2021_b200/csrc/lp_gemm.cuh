@@ -20,9 +20,11 @@
 //   warp 1     TMEM allocation + single-thread tcgen05.mma issue (M = 128, N = BN, K = 16 per
 //              instruction; the B1 and B2 products accumulate into the same TMEM tile),
 //              tcgen05.commit releases ring slots and publishes finished accumulators
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> FP64 update on
-//              registers -> global; TMEM accumulators are double buffered so the epilogue of tile
-//              i overlaps the MMAs of tile i+1
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 16 columns per warp and step; two warps share a
+//              lane quarter and split the columns) -> FP64 update on registers -> global; TMEM
+//              accumulators are double buffered so the epilogue of tile i overlaps the MMAs of
+//              tile i+1.  The epilogue moves 42 B of FP64 state per element through HBM, so it
+//              needs as many loads in flight as the MMA issue needs none.
 #pragma once
 #include <cuda.h>   // CUtensorMap and its enums (types only: the encoder is fetched through cudart)
 #include <cuda_fp16.h>
@@ -35,7 +37,8 @@ namespace lp {
 constexpr int BM = 128;          // rows (samples) per tile = TMEM lanes
 constexpr int BK = 64;           // fp16 elements per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: each owns 16 of every 32 accumulator columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;
 
 template <int BN_, int STAGES_>
@@ -127,6 +130,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major operand tile written by TMA with 128-byte swizzle:
@@ -147,18 +160,19 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 
 // ------------------------------------------------------------------------------------ the kernel
 struct LpShape {
-  int M;   // rows of A / of the output (samples)
-  int N;   // rows of B1/B2 = output columns
-  int K;   // contraction length (TMA zero-fills beyond it)
+  int M;              // rows of A / of the output (samples); upper bound when m_dev is given
+  int N;              // rows of B1/B2 = output columns
+  int K;              // contraction length (TMA zero-fills beyond it)
+  const int* m_dev;   // optional: the row count lives in device memory (0 = nothing to do)
 };
 
 // Epilogue concept:
 //   struct Epi { struct Params {...};
 //     __device__ Epi(const Params&);
-//     // one thread owns output row `row` (may be >= M: then ok == false) and 32 consecutive columns
-//     __device__ void begin_row(int row, bool in_range);
-//     __device__ void chunk(int row, int col0, const uint32_t (&acc)[32] /*fp32 bit patterns*/, int N);
-//     __device__ void end_row(int row);
+//     // one thread owns output row `pos` (in_range == false beyond M) and 16 consecutive columns at a time
+//     __device__ void begin_row(int pos, bool in_range);
+//     __device__ void chunk(int col0, const uint32_t (&acc)[16] /*fp32 bit patterns*/, int N);
+//     __device__ void end_row();
 //   };
 template <class T, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -175,8 +189,9 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
   const int ntn = (g.N + T::BN - 1) / T::BN;
-  const int ntm = (g.M + BM - 1) / BM;
+  const int ntm = (M + BM - 1) / BM;
   const int tiles = ntn * ntm;
   const int KB = (g.K + BK - 1) / BK;
 
@@ -190,7 +205,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, 4);   // one arrival per epilogue warp
+      mbar_init(acc_empty + s, EPI_WARPS);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -250,8 +265,9 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     Epi epi(ep);
     int i = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
@@ -259,18 +275,18 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
       const int row = bm * BM + q * 32 + lane;
-      epi.begin_row(row, row < g.M);
+      epi.begin_row(row, row < M);
       mbar_wait(acc_full + as, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * T::BN);
 #pragma unroll 1
       for (int cc = 0; cc < T::BN / 32; ++cc) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tacc + (uint32_t)(cc * 32), acc);
+        uint32_t acc[16];
+        tmem_ld_32x16(tacc + (uint32_t)(cc * 32 + hsel * 16), acc);
         tmem_ld_wait();
-        epi.chunk(row, bn * T::BN + cc * 32, acc, g.N);
+        epi.chunk(bn * T::BN + cc * 32 + hsel * 16, acc, g.N);
       }
-      epi.end_row(row);
+      epi.end_row();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);
@@ -282,6 +298,199 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, T::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ CTA-pair kernel
+// Same contraction with cta_group::2: a cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  Each CTA
+// loads its own 128 rows of A and HALF of the B1/B2 tiles (128 of the 256 operator rows); one thread of the
+// leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes each
+// CTA's 128 accumulator rows into its own TMEM.  Per output element this halves the operand bytes pulled
+// from L2, which is what bounds the single-CTA kernel (6.3 kB/clk chip-wide TMA throughput).
+constexpr int BN2 = 256;          // output columns per pair tile (128 operator rows staged per CTA)
+constexpr int STAGES2 = 4;
+constexpr int STAGE2_BYTES = BM * BK * 2 + 2 * (BN2 / 2) * BK * 2;   // A + B1 half + B2 half = 48 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int TMEM2_COLS = ACC_STAGES * BN2;                          // 512: all of TMEM
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; the bytes are credited to the LEADER CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once the pair MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmB2, LpShape g, typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES2 * STAGE2_BYTES);
+  uint64_t* full = bars;                          // [STAGES2]  leader's copy is used: both CTAs' TMA bytes + 2 arrivals
+  uint64_t* empty = bars + STAGES2;               // [STAGES2]  per CTA, released by the leader's multicast commit
+  uint64_t* acc_full = bars + 2 * STAGES2;        // [ACC_STAGES] per CTA, multicast commit
+  uint64_t* acc_empty = acc_full + ACC_STAGES;    // [ACC_STAGES] leader's copy is used: both CTAs' epilogue warps arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
+  const int ntn = (g.N + BN2 - 1) / BN2;
+  const int ntm = (M + 2 * BM - 1) / (2 * BM);
+  const int tiles = ntn * ntm;
+  const int KB = (g.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmB2);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full + s, 2);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM2_COLS);
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers and TMEM allocations exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane in EACH CTA: own A rows, own half of the operator tile) =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < tiles; t += nclusters) {
+        const int bn = t % ntn, bm = t / ntn;
+        const int arow = bm * 2 * BM + (int)rank * BM;
+        const int brow = bn * BN2 + (int)rank * (BN2 / 2);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          uint8_t* st = ring + s * STAGE2_BYTES;
+          tma_load_2d_pair(st, &tmA, full + s, kb * BK, arow);
+          tma_load_2d_pair(st + BM * BK * 2, &tmB1, full + s, kb * BK, brow);
+          tma_load_2d_pair(st + BM * BK * 2 + (BN2 / 2) * BK * 2, &tmB2, full + s, kb * BK, brow);
+          if (leader) mbar_expect_tx(full + s, 2 * STAGE2_BYTES);
+          else mbar_arrive_remote(full + s, 0);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one lane of the leader CTA =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN2);
+      int s = 0;
+      uint32_t ph = 0;
+      int i = 0;
+      for (int t = cluster_id; t < tiles; t += nclusters, ++i) {
+        const int as = i & 1;
+        const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(acc_empty + as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN2);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + s * STAGE2_BYTES);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db1 = make_sw128_kmajor_desc(sa + BM * BK * 2);
+          const uint64_t db2 = make_sw128_kmajor_desc(sa + BM * BK * 2 + (BN2 / 2) * BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_pair(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_pair(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+          umma_commit_pair(empty + s);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(acc_full + as);
+      }
+    }
+  } else {
+    // ===== epilogue warps of both CTAs: own 128 accumulator rows =====
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    Epi epi(ep);
+    int i = 0;
+    for (int t = cluster_id; t < tiles; t += nclusters, ++i) {
+      const int bn = t % ntn, bm = t / ntn;
+      const int as = i & 1;
+      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+      const int row = bm * 2 * BM + (int)rank * BM + q * 32 + lane;
+      epi.begin_row(row, row < M);
+      mbar_wait(acc_full + as, aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2);
+#pragma unroll 1
+      for (int cc = 0; cc < BN2 / 32; ++cc) {
+        uint32_t acc[16];
+        tmem_ld_32x16(tacc + (uint32_t)(cc * 32 + hsel * 16), acc);
+        tmem_ld_wait();
+        epi.chunk(bn * BN2 + cc * 32 + hsel * 16, acc, g.N);
+      }
+      epi.end_row();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(acc_empty + as);
+        else mbar_arrive_remote(acc_empty + as, 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM2_COLS);
   }
 }
 
@@ -334,6 +543,25 @@ inline cudaError_t launch_lp_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB
   const long long tiles = (long long)((g.N + T::BN - 1) / T::BN) * ((g.M + BM - 1) / BM);
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
   lp_gemm_kernel<T, Epi><<<grid, THREADS, T::SMEM_BYTES, st>>>(tmA, tmB1, tmB2, g, ep);
+  return cudaGetLastError();
+}
+
+template <class Epi>
+inline cudaError_t launch_lp_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
+                                       const LpShape& g, const typename Epi::Params& ep, int num_sms, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(lp_gemm_pair_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = true;
+  }
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
+  const long long tiles = (long long)((g.N + BN2 - 1) / BN2) * ((g.M + 2 * BM - 1) / (2 * BM));
+  long long clusters = num_sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  lp_gemm_pair_kernel<Epi><<<(unsigned)(2 * clusters), THREADS, SMEM2_BYTES, st>>>(tmA, tmB1, tmB2, g, ep);
   return cudaGetLastError();
 }
 

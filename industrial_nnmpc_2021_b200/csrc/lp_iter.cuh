@@ -50,6 +50,8 @@ struct EpiDelta {
     const double* ub;    // B x nu
     const int* state;    // row takes part iff state[row] == iter_state
     int iter_state;
+    const int* list_r;   // position (row of the operand the TMA reads) -> sample row; null = identity
+    const int* pos_w;    // sample row -> position in the operand written now; null = identity
     const double* sc_in;   // scale the current operand row was quantised with
     const double* sc_out;  // scale for the operand written now
     unsigned long long* dres;  // per row: max |d| (bit pattern of a non-negative double)
@@ -59,14 +61,18 @@ struct EpiDelta {
   };
   Params p;
   bool ok;
+  int row;
+  long long pw;
   double inv_in, s_out, inv_out, dmax;
   const double* lbr;
   const double* ubr;
-  __device__ explicit EpiDelta(const Params& p_) : p(p_), ok(false), inv_in(0), s_out(0), inv_out(0), dmax(0), lbr(nullptr), ubr(nullptr) {}
-  __device__ void begin_row(int row, bool in_range) {
+  __device__ explicit EpiDelta(const Params& p_) : p(p_), ok(false), row(0), pw(0), inv_in(0), s_out(0), inv_out(0), dmax(0), lbr(nullptr), ubr(nullptr) {}
+  __device__ void begin_row(int pos, bool in_range) {
+    row = in_range ? (p.list_r ? p.list_r[pos] : pos) : 0;
     ok = in_range && p.state[row] == p.iter_state;
     dmax = 0.0;
     if (ok) {
+      pw = p.pos_w ? p.pos_w[row] : row;
       inv_in = p.inv_sT / p.sc_in[row];
       s_out = p.sc_out[row];
       inv_out = 1.0 / s_out;
@@ -74,18 +80,73 @@ struct EpiDelta {
       ubr = p.ub + (long long)row * p.nu;
     }
   }
-  __device__ void chunk(int row, int col0, const uint32_t (&acc)[32], int N) {
-    if (!ok) return;
+  // 16 consecutive columns of this thread's row.  Fast path (stage width a multiple of 16, full chunk): every
+  // state load of the chunk is issued before the first use and results are stored at the end, so each
+  // epilogue thread keeps 24 x 16 B of HBM traffic in flight.
+  __device__ void chunk(int col0, const uint32_t (&acc)[16], int N) {
+    if (!ok || col0 >= N) return;
     const long long base = (long long)row * p.n + col0;
-    __half* dn = p.Dn + (long long)row * p.ldd + col0;
-    int k = col0 % p.nu;
+    __half* dn = p.Dn + pw * p.ldd + col0;
+    const int k0 = col0 % p.nu;
+    if ((p.nu & 15) == 0 && col0 + 16 <= N) {
+      double2 x[8], v[8];
+      float2 e[8];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+      for (int i = 0; i < 8; ++i) {
+        x[i] = *reinterpret_cast<const double2*>(p.X + base + 2 * i);
+        v[i] = *reinterpret_cast<const double2*>(p.V + base + 2 * i);
+        e[i] = *reinterpret_cast<const float2*>(p.E + base + 2 * i);
+      }
+      __half2 q[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        // the stage bounds of these 8 columns: L1/L2 hits (every column tile re-reads the same 2 x 256 B per row),
+        // loaded half a chunk at a time to stay inside the 168 registers ten warps leave per thread
+        double2 lbc[4], ubc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          lbc[i] = *reinterpret_cast<const double2*>(lbr + k0 + 8 * hh + 2 * i);
+          ubc[i] = *reinterpret_cast<const double2*>(ubr + k0 + 8 * hh + 2 * i);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = 4 * hh + ii;
+          x[i].x += (double)__uint_as_float(acc[2 * i]) * inv_in;
+          x[i].y += (double)__uint_as_float(acc[2 * i + 1]) * inv_in;
+          const double wl0 = (2.0 * clipd(v[i].x, lbc[ii].x, ubc[ii].x) - v[i].x) - (double)e[i].x;
+          const double wl1 = (2.0 * clipd(v[i].y, lbc[ii].y, ubc[ii].y) - v[i].y) - (double)e[i].y;
+          double dw0, dw1, a0, a1;
+          dr_delta_one(x[i].x, v[i].x, wl0, lbc[ii].x, ubc[ii].x, p.alpha, dw0, a0);
+          dr_delta_one(x[i].y, v[i].y, wl1, lbc[ii].y, ubc[ii].y, p.alpha, dw1, a1);
+          const __half q0 = quantise_dw(dw0, s_out, inv_out, e[i].x);
+          const __half q1 = quantise_dw(dw1, s_out, inv_out, e[i].y);
+          q[i] = __halves2half2(q0, q1);
+          const double a = (a0 <= a1) ? a1 : a0;       // NaN propagates
+          dmax = (a <= dmax) ? dmax : a;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<double2*>(p.X + base + 2 * i) = x[i];
+        *reinterpret_cast<double2*>(p.V + base + 2 * i) = v[i];
+        *reinterpret_cast<float2*>(p.E + base + 2 * i) = e[i];
+      }
+      uint4* d4 = reinterpret_cast<uint4*>(dn);
+      d4[0] = make_uint4(*reinterpret_cast<uint32_t*>(&q[0]), *reinterpret_cast<uint32_t*>(&q[1]),
+                         *reinterpret_cast<uint32_t*>(&q[2]), *reinterpret_cast<uint32_t*>(&q[3]));
+      d4[1] = make_uint4(*reinterpret_cast<uint32_t*>(&q[4]), *reinterpret_cast<uint32_t*>(&q[5]),
+                         *reinterpret_cast<uint32_t*>(&q[6]), *reinterpret_cast<uint32_t*>(&q[7]));
+      return;
+    }
+    // general path (any stage width, ragged last chunk): element pairs, n is even
+    int k = k0;
+#pragma unroll 1
+    for (int j = 0; j < 16; j += 2) {
       const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
-      if (col0 + j < N) {          // n is even: col0 + j + 1 < N as well
+      if (col0 + j < N) {
         double2 x = *reinterpret_cast<const double2*>(p.X + base + j);
         double2 v = *reinterpret_cast<const double2*>(p.V + base + j);
-        const float2 e = *reinterpret_cast<const float2*>(p.E + base + j);
+        float2 e = *reinterpret_cast<const float2*>(p.E + base + j);
         const double l0 = lbr[k], u0 = ubr[k], l1 = lbr[k1], u1 = ubr[k1];
         x.x += (double)__uint_as_float(acc[j]) * inv_in;
         x.y += (double)__uint_as_float(acc[j + 1]) * inv_in;
@@ -94,20 +155,19 @@ struct EpiDelta {
         double dw0, dw1, a0, a1;
         dr_delta_one(x.x, v.x, wl0, l0, u0, p.alpha, dw0, a0);
         dr_delta_one(x.y, v.y, wl1, l1, u1, p.alpha, dw1, a1);
-        float2 en;
-        const __half q0 = quantise_dw(dw0, s_out, inv_out, en.x);
-        const __half q1 = quantise_dw(dw1, s_out, inv_out, en.y);
+        const __half q0 = quantise_dw(dw0, s_out, inv_out, e.x);
+        const __half q1 = quantise_dw(dw1, s_out, inv_out, e.y);
         *reinterpret_cast<double2*>(p.X + base + j) = x;
         *reinterpret_cast<double2*>(p.V + base + j) = v;
-        *reinterpret_cast<float2*>(p.E + base + j) = en;
+        *reinterpret_cast<float2*>(p.E + base + j) = e;
         *reinterpret_cast<__half2*>(dn + j) = __halves2half2(q0, q1);
-        const double a = (a0 <= a1) ? a1 : a0;       // NaN propagates
+        const double a = (a0 <= a1) ? a1 : a0;
         dmax = (a <= dmax) ? dmax : a;
       }
       k = (k1 + 1 == p.nu) ? 0 : k1 + 1;
     }
   }
-  __device__ void end_row(int row) {
+  __device__ void end_row() {
     if (!ok) return;
     double m = dmax;
     if (!(m <= 1.7e308)) m = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
@@ -124,15 +184,16 @@ struct EpiLpStore {
   };
   Params p;
   bool ok;
-  __device__ explicit EpiLpStore(const Params& p_) : p(p_), ok(false) {}
-  __device__ void begin_row(int, bool in_range) { ok = in_range; }
-  __device__ void chunk(int row, int col0, const uint32_t (&acc)[32], int N) {
+  int row;
+  __device__ explicit EpiLpStore(const Params& p_) : p(p_), ok(false), row(0) {}
+  __device__ void begin_row(int pos, bool in_range) { ok = in_range; row = pos; }
+  __device__ void chunk(int col0, const uint32_t (&acc)[16], int N) {
     if (!ok) return;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < 16; ++j)
       if (col0 + j < N) p.C[(long long)row * p.ldc + col0 + j] = (double)__uint_as_float(acc[j]) * p.scale;
   }
-  __device__ void end_row(int) {}
+  __device__ void end_row() {}
 };
 
 // ---- FP64 anchor: x = Top w - c on the accumulators of the DMMA GEMM ---------------------------
@@ -195,7 +256,7 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
            double* __restrict__ W, float* __restrict__ E, __half* __restrict__ D, long long ldd,
            const double* __restrict__ lb, const double* __restrict__ ub, double* __restrict__ sc_in,
            double* __restrict__ sc_out, int* __restrict__ state, int* __restrict__ it, int iter_state, int n, int nu,
-           double alpha) {
+           double alpha, const int* __restrict__ pos_r) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   __shared__ double red[2][8];
@@ -229,9 +290,10 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
     wmax = (red[1][w] <= wmax) ? wmax : red[1][w];
   }
   const double sq = pow2_scale(wmax), inv = 1.0 / sq;
+  const long long dpos = pos_r ? pos_r[s] : s;      // row of the operand buffer the next pass reads for this sample
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     float e;
-    D[s * ldd + j] = quantise_dw(W[s * n + j], sq, inv, e);
+    D[dpos * ldd + j] = quantise_dw(W[s * n + j], sq, inv, e);
     E[s * n + j] = e;
   }
   if (threadIdx.x == 0) {

@@ -29,7 +29,11 @@ namespace nnmpc {
 int qp_ensure_scratch(nnmpc_qp* h, long long B);
 
 enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4, SLOT_ANCHOR = 5 };
-enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_ANCHOR = 6, N_COUNTERS = 8 };
+enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_ANCHOR = 6,
+               // mixed mode: effective row counts of this loop's launches (0 switches a launch off on the device)
+               E_ANCHOR = 7, E_LP = 8, E_TAIL = 9, LP_LEN0 = 10, LP_LEN1 = 11,
+               // chunk queue: slots that finished a trajectory chunk this loop, cold (re)starts, next chunk to hand out
+               N_SWAP = 12, N_COLD = 13, NEXT_CHUNK = 14, N_COUNTERS = 16 };
 constexpr int POLL_RING = 4;
 }  // namespace nnmpc
 
@@ -44,10 +48,15 @@ struct nnmpc_sim {
   long long cap;
   long long warm_B;   // batch size whose solver state (V, us_prev, kappa) is valid for `resume`; 0 = none
   nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, V, Z, xin, xcur, upcur, kappa, dtrig;
-  nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 5 x cap (active, cand, done, renew, anchor)
+  nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 9 x cap (active, cand, done, renew, anchor, cold, swap, swap_old, swap_new)
+  nnmpc::DevBuf<int> chunk, cold;              // per slot: the trajectory chunk it works on; cold (re)start pending
+  int slot_cap;                                // most trajectories advanced concurrently (further chunks queue up)
+  int cadence;                                 // mixed mode: the FP64 phases run every cadence-th loop
   // mixed-precision iteration (tcgen05 fp16 increments + FP64 anchors), see lp_iter.cuh
   int mixed;
+  int tail_rows;                    // live rows at or below which the mixed mode finishes in FP64 (-1 = auto)
   nnmpc::LpState lps;
+  nnmpc::DevBuf<int> lp_layout;     // 2 x cap operand layouts (position -> row) + 2 x cap inverses (row -> position)
   unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
@@ -129,20 +138,29 @@ struct EngineArrays {
   double* kappa; double* dtrig;
   unsigned long long* dres; unsigned long long* kres;
   int* l_active; int* l_cand; int* l_done; int* l_renew; int* l_anchor;
+  int* l_cold; int* l_swap; int* swap_old; int* swap_new; int* chunk; int* cold; int n_chunks;
   int* counts; unsigned long long* rowiters;
   // mixed-precision mode
   int mixed; double* sc_in; double* sc_out; unsigned long long* stats; double alpha;
+  int* lp_list; int* lp_pos;   // [2][S] each
+  int tail_rows;
 };
 
 // after an iteration: bump iteration counters, pick the rows worth an exact KKT check
-__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter) {
+// (append: candidates of earlier passes are still waiting for their exact check - the FP64 phases of the mixed
+//  mode run every `cadence`-th loop - so the list grows instead of starting over)
+__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int append, int full) {
   const int na = e.counts[N_ACTIVE];
-  int base = 0;
+  int base = append ? e.counts[N_CAND] : 0;
+  int iterated = 0;
+  __syncthreads();
   for (int i0 = 0; i0 < na; i0 += 1024) {
     const int i = i0 + threadIdx.x;
     bool cand = false;
     int s = 0;
-    if (i < na) {
+    const bool live = i < na && e.state[e.l_active[i]] == SLOT_ITER;   // rows waiting for an FP64 phase did not iterate
+    iterated += __syncthreads_count(live);
+    if (live) {
       s = e.l_active[i];
       const int it = e.it[s] + 1;
       e.it[s] = it;
@@ -163,11 +181,8 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
   }
   if (threadIdx.x == 0) {
     e.counts[N_CAND] = base;
-    *e.rowiters += (unsigned long long)na;
-    if (e.mixed) {
-      e.stats[0] += (unsigned long long)e.counts[N_ANCHOR];   // anchors served at the top of this loop
-      e.stats[1] += (unsigned long long)base;
-    }
+    *e.rowiters += (unsigned long long)iterated;
+    if (e.mixed && full) e.stats[0] += (unsigned long long)e.counts[E_ANCHOR];   // anchors served at the top of this loop
   }
 }
 
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
       }
       if (done) {
         e.state[s] = SLOT_DONE;
-        const long long o = (long long)s * T + e.tcur[s];
+        const long long o = (long long)e.chunk[s] * T + e.tcur[s];
         if (out_iters) out_iters[o] = it;
         if (out_kkt) out_kkt[o] = r;
         if (!(r <= tol)) e.counts[F_MAXITER] = 1;
@@ -225,18 +240,19 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
   if (threadIdx.x == 0) {
     e.counts[N_DONE] = base;
     e.counts[N_ANCHOR] = nfail;   // k_step appends the renewed rows
+    if (e.mixed) e.stats[1] += (unsigned long long)nc;
   }
 }
 
 // first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows
 __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
-                          int T, const double* __restrict__ Z, const double* __restrict__ us,
+                          const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
                           const double* __restrict__ xcur, const double* __restrict__ dist,
                           double* __restrict__ row_u, double* __restrict__ upcur, double* __restrict__ xin, int n,
                           int nx, int nu, int nd, int kin_ld) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
-  const long long o = s * T + tcur[s];
+  const long long o = (long long)chunk[s] * T + tcur[s];
   for (int c = threadIdx.x; c < kin_ld; c += blockDim.x) {
     double v;
     if (c < nx) {
@@ -256,41 +272,129 @@ __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ 
 }
 
 // done rows move to their next time step; finished trajectories leave; rebuild renew + active lists
-__global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
+__global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int wbuf) {
   const int nd = e.counts[N_DONE];
   int base = 0, fin = 0;
   const int na0 = e.mixed ? e.counts[N_ANCHOR] : 0;
   int nanch = na0;
   __syncthreads();
+  int nsw = 0, ncold = 0;
   for (int i0 = 0; i0 < nd; i0 += 1024) {
     const int i = i0 + threadIdx.x;
-    bool renew = false;
+    bool renew = false, swap = false;
     int s = 0;
     if (i < nd) {
       s = e.l_done[i];
       const int t = e.tcur[s] + 1;
       e.tcur[s] = t;
       renew = t < T;
+      swap = !renew;
       e.state[s] = renew ? SLOT_RENEW : SLOT_IDLE;
     }
-    fin += __syncthreads_count(i < nd && !renew);
     base = block_append(renew, s, e.l_renew, base);
     if (e.mixed) nanch = block_append(renew, s, e.l_anchor, nanch);
+    nsw = block_append(swap, s, e.l_swap, nsw);
+  }
+  fin = nsw;
+  // slots that finished their chunk take the next queued chunk (cold start at its t = 0), if any is left
+  const int next0 = e.counts[NEXT_CHUNK];
+  const int left = e.n_chunks - next0;
+  const int ntake = nsw < left ? nsw : (left > 0 ? left : 0);
+  __syncthreads();
+  for (int i0 = 0; i0 < nsw; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool take = i < ntake;
+    int s = 0;
+    if (i < nsw) {
+      s = e.l_swap[i];
+      e.swap_old[i] = e.chunk[s];
+      e.swap_new[i] = take ? next0 + i : -1;
+      if (take) {
+        e.chunk[s] = next0 + i;
+        e.tcur[s] = 0;
+        e.cold[s] = 1;
+        e.state[s] = SLOT_RENEW;
+      }
+    }
+    base = block_append(take, s, e.l_renew, base);
+    if (e.mixed) nanch = block_append(take, s, e.l_anchor, nanch);
+    ncold = block_append(take, s, e.l_cold, ncold);
   }
   int na = 0;
-  if (nd > 0) {   // only a finished trajectory changes the active list, but rebuilding is cheap
+  if (nd > 0) {   // only a finished chunk changes the live list, but rebuilding is cheap
     for (int i0 = 0; i0 < S; i0 += 1024) {
       const int s = i0 + threadIdx.x;
       const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW || e.state[s] == SLOT_ANCHOR);
       na = block_append(live, s, e.l_active, na);
     }
   }
+  if (nd == 0) na = e.counts[N_ACTIVE];
+  if (e.mixed) {
+    // Operand layout for the pass after next = the live list of the next loop (the tensor-core operand is
+    // rewritten every pass, so it is re-compacted for free, one pass behind the live list).
+    int* L = e.lp_list + (long long)wbuf * S;
+    int* Pp = e.lp_pos + (long long)wbuf * S;
+    for (int i = threadIdx.x; i < S; i += 1024) Pp[i] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < na; i += 1024) {
+      const int s = e.l_active[i];
+      L[i] = s;
+      Pp[s] = i;
+    }
+  }
   if (threadIdx.x == 0) {
     e.counts[N_RENEW] = base;
-    if (e.mixed) e.counts[N_ANCHOR] = nanch;
     e.counts[N_FINISHED] += fin;
-    if (nd > 0) e.counts[N_ACTIVE] = na;
+    e.counts[N_ACTIVE] = na;
+    e.counts[N_SWAP] = nsw;
+    e.counts[N_COLD] = ncold;
+    e.counts[NEXT_CHUNK] = next0 + ntake;
+    if (e.mixed) {
+      e.counts[N_ANCHOR] = nanch;
+      e.counts[LP_LEN0 + wbuf] = na;
+      const bool tail = na <= e.tail_rows;     // few live rows: skinny FP64 GEMMs beat a tensor-core pass
+      e.counts[E_ANCHOR] = tail ? 0 : nanch;
+      e.counts[E_LP] = tail ? 0 : e.counts[LP_LEN0 + (wbuf ^ 1)];
+      e.counts[E_TAIL] = tail ? na : 0;
+    }
   }
+}
+
+// mixed mode, tail: the live rows iterate in FP64; the operand is rebuilt from v every loop
+__global__ void k_tail_prep(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
+                            const double* __restrict__ V, double* __restrict__ W, const double* __restrict__ lb,
+                            const double* __restrict__ ub, int n, int nu) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int k = j % nu;
+    const double v = V[s * n + j];
+    W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
+  }
+  if (threadIdx.x == 0 && state[s] == SLOT_ANCHOR) state[s] = SLOT_ITER;
+}
+
+// slots that finished a chunk: hand its final state back, load the initial state of the chunk taken next
+__global__ void k_chunk_swap(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ c_old,
+                             const int* __restrict__ c_new, double* __restrict__ xcur, double* __restrict__ upcur,
+                             double* __restrict__ x_io, double* __restrict__ uprev_io, double* __restrict__ us_prev,
+                             double* __restrict__ kappa, double kappa0, int nx, int nu) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  const long long co = c_old[blockIdx.x], cn = c_new[blockIdx.x];
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+    x_io[co * nx + j] = xcur[s * nx + j];
+    if (cn >= 0) xcur[s * nx + j] = x_io[cn * nx + j];
+  }
+  for (int j = threadIdx.x; j < nu; j += blockDim.x) {
+    uprev_io[co * nu + j] = upcur[s * nu + j];
+    if (cn >= 0) {
+      upcur[s * nu + j] = uprev_io[cn * nu + j];
+      us_prev[s * nu + j] = 0.0;
+    }
+  }
+  // a new chunk starts like a fresh trajectory: results do not depend on which slot serves it
+  if (threadIdx.x == 0 && cn >= 0) kappa[s] = kappa0;
 }
 
 // renew rows: v <- shifted previous solution re-centred on the new target (or the cold-start law
@@ -298,10 +402,11 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S) {
 __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
                              int* __restrict__ it, unsigned long long* __restrict__ dres, double* __restrict__ V,
                              double* __restrict__ Zs, double* __restrict__ W, const double* __restrict__ dus,
-                             const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu, int cold,
-                             int next_state, int write_w) {
+                             const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu,
+                             int* __restrict__ cold_flag, int next_state, int write_w) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
+  const int cold = cold_flag[s];   // cold start: V already holds the unconstrained law of this QP
   double* v = V + s * n;
   double* z = Zs + s * n;
   double* w = W + s * n;
@@ -319,15 +424,28 @@ __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict
     if (!cold) v[j] = vn;
     if (write_w) w[j] = 2.0 * clipd(vn, lb[s * nu + k], ub[s * nu + k]) - vn;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    cold_flag[s] = 0;
     state[s] = next_state;
     it[s] = 0;
     dres[s] = 0ull;
   }
 }
 
-__global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kappa0) {
-  if (e.mixed && blockIdx.x * blockDim.x + threadIdx.x < S) e.l_anchor[blockIdx.x * blockDim.x + threadIdx.x] = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kappa0, int cold_all) {
+  if (blockIdx.x * blockDim.x + threadIdx.x < S) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    e.chunk[i] = i;
+    e.cold[i] = cold_all;
+    e.l_cold[i] = i;
+  }
+  if (e.mixed && blockIdx.x * blockDim.x + threadIdx.x < S) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    e.l_anchor[i] = i;
+    e.lp_list[i] = e.lp_list[S + i] = i;
+    e.lp_pos[i] = e.lp_pos[S + i] = i;
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < S) {
     e.state[s] = SLOT_RENEW;
@@ -348,6 +466,14 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
     e.counts[N_FINISHED] = 0;
     e.counts[F_MAXITER] = 0;
     e.counts[N_ANCHOR] = e.mixed ? S : 0;
+    e.counts[N_SWAP] = 0;
+    e.counts[N_COLD] = cold_all ? S : 0;
+    e.counts[NEXT_CHUNK] = S;
+    const bool tail = S <= e.tail_rows;
+    e.counts[LP_LEN0] = e.counts[LP_LEN1] = S;
+    e.counts[E_ANCHOR] = (e.mixed && !tail) ? S : 0;
+    e.counts[E_LP] = (e.mixed && !tail) ? S : 0;
+    e.counts[E_TAIL] = (e.mixed && tail) ? S : 0;
     *e.rowiters = 0ull;
     if (e.mixed) e.stats[0] = e.stats[1] = 0ull;
   }
@@ -372,22 +498,28 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
   NNMPC_TRY(h->state.ensure(B));
   NNMPC_TRY(h->tcur.ensure(B));
   NNMPC_TRY(h->it.ensure(B));
-  NNMPC_TRY(h->lists.ensure(5 * B));
+  NNMPC_TRY(h->lists.ensure(9 * B));
+  NNMPC_TRY(h->chunk.ensure(B));
+  NNMPC_TRY(h->cold.ensure(B));
+  NNMPC_TRY(h->lp_layout.ensure(4 * B));
   NNMPC_TRY(h->dres.ensure(B));
   NNMPC_TRY(h->kres.ensure(B));
   h->cap = B;
   return 0;
 }
 
-static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* uprev_io, const double* sp,
+static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* uprev_io, const double* sp,
                           const double* dist, double* ox, double* ouprev, double* oxs, double* ous, double* ou,
                           int* oiters, double* okkt, double tol, int max_iter, int resume, cudaStream_t st) {
-  if (B <= 0 || T <= 0) return 0;
+  if (Btot <= 0 || T <= 0) return 0;
   if (max_iter < 1) max_iter = 1;
+  // B trajectory slots advance concurrently; with more chunks than slots the rest queue up and a slot that
+  // finishes its chunk takes the next one (cold start), so the batch stays full until the queue is empty
+  const int B = Btot < h->slot_cap ? Btot : h->slot_cap;
   NNMPC_TRY(sim_ensure(h, B));
   nnmpc_qp* q = h->qp;
   NNMPC_TRY(qp_ensure_scratch(q, B));
-  const bool cont = resume && h->warm_B == B;
+  const bool cont = resume && h->warm_B == Btot && Btot == B;   // solver state is kept per slot
   h->warm_B = 0;
   const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = q->n, nxa = h->nxa_ld;
   const int mixed = h->mixed;
@@ -405,8 +537,13 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   e.l_active = h->lists.p; e.l_cand = h->lists.p + B; e.l_done = h->lists.p + 2 * (long long)B;
   e.l_renew = h->lists.p + 3 * (long long)B; e.l_anchor = h->lists.p + 4 * (long long)B;
   e.counts = h->counts; e.rowiters = h->rowiters;
+  e.l_cold = h->lists.p + 5 * (long long)B; e.l_swap = h->lists.p + 6 * (long long)B;
+  e.swap_old = h->lists.p + 7 * (long long)B; e.swap_new = h->lists.p + 8 * (long long)B;
+  e.chunk = h->chunk.p; e.cold = h->cold.p; e.n_chunks = Btot;
+  e.lp_list = h->lp_layout.p; e.lp_pos = h->lp_layout.p + 2 * (long long)B;
+  e.tail_rows = h->tail_rows >= 0 ? h->tail_rows : (B / 16 > 48 ? B / 16 : 48);
   e.mixed = mixed; e.sc_in = h->lps.sc_in.p; e.sc_out = h->lps.sc_out.p; e.stats = h->stats; e.alpha = q->alpha;
-  k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0);
+  k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0, cont ? 0 : 1);
   count_launch();
 
   double* Wc = q->W0.p;   // operand the next iteration reads
@@ -418,7 +555,7 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     F.x = h->xcur.p; F.uprev = h->upcur.p; F.x0 = h->x0.p; F.nxa_ld = nxa; F.lb = h->lb.p; F.ub = h->ub.p;
     F.us_prev = h->us_prev.p; F.dus = h->dus.p;
     F.row_x = ox; F.row_uprev = ouprev; F.row_stride_x = nx; F.row_stride_u = nu;
-    TsIndex ix{e.l_renew, e.counts + N_RENEW, e.tcur, T};
+    TsIndex ix{e.l_renew, e.counts + N_RENEW, e.tcur, T, e.chunk};
     NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, st));
     GemmOperands g{};
     g.A = h->x0.p; g.lda = nxa; g.ldb = nxa; g.M = B; g.N = n; g.K = nxa; g.rows = e.l_renew;
@@ -427,45 +564,68 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     cudaError_t ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{q->C.p, n, nullptr, 0}, st);
     g.Bt = q->tq;
     if (ce == cudaSuccess) ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{q->Ql.p, n, nullptr, 0}, st);
-    const int cold = first && !cont;
-    if (cold && ce == cudaSuccess) {   // cold start: the unconstrained (LQR) law v0 = Kunc x0
-      g.Bt = q->Kunc;
+    if (ce == cudaSuccess && (first ? !cont : Btot > B)) {   // cold starts: the unconstrained (LQR) law v0 = Kunc x0
+      g.Bt = q->Kunc; g.rows = e.l_cold; g.m_count = e.counts + N_COLD;
       ce = launch_gemm<TileMid, EpiStore>(g, EpiStore::Params{h->V.p, n, nullptr, 0}, st);
       count_launch();
     }
     count_launch(2);
     if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
     k_warm_shift<<<B, 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
-                                    h->dus.p, h->lb.p, h->ub.p, n, nu, cold, mixed ? SLOT_ANCHOR : SLOT_ITER,
+                                    h->dus.p, h->lb.p, h->ub.p, n, nu, e.cold, mixed ? SLOT_ANCHOR : SLOT_ITER,
                                     mixed ? 0 : 1);
     count_launch();
     return 0;
   };
   NNMPC_TRY(renew(1));
 
-  const long long max_loops = (long long)T * ((long long)max_iter + 2) + 8;
+  // mixed mode: the FP64 phases (anchors, exact checks, plant step, next targets) run every cad-th loop over the
+  // rows that accumulated meanwhile - those rows sit out at most cad-1 tensor-core passes, and the FP64 GEMMs
+  // and the small kernels around them see cad times longer row lists
+  const int cad = mixed ? (h->cadence > 1 ? h->cadence : 1) : 1;
+  int lay = 0;            // operand layout buffer the next tensor-core pass reads
+  long long polls = 0;
+  const long long max_loops = ((long long)T * ((long long)max_iter + 2) * ((Btot + B - 1) / B) + 8) * cad;
   int rc_warn = 0;
   bool finished = false;
   long long loop = 0;
   for (; loop < max_loops && !finished; ++loop) {
     // 1. one Douglas-Rachford iteration for every live trajectory
+    const bool full = (loop % cad) == 0;
     if (mixed) {
       // 1a. FP64 anchors for the rows that start a QP or failed an exact check: x = Top w - c with the
       //     DMMA kernel, one full-precision step, first fp16 increment
-      int* cnt = e.counts + N_ANCHOR;
+      int* cnt = e.counts + E_ANCHOR;
+      const int rbuf = lay;
+      const int* list_r = e.lp_list + (long long)rbuf * B;
+      const int* pos_r = e.lp_pos + (long long)rbuf * B;
+      // a full loop ends with k_step, which publishes the next live list: write the operand in that layout
+      const int* pos_w = e.lp_pos + (long long)(full ? rbuf ^ 1 : rbuf) * B;
       ProfSpan span64;
-      const bool prof64 = prof_begin(&span64, st);
-      NNMPC_TRY(lp_anchor_prep(e.l_anchor, cnt, B, h->V.p, q->W0.p, &h->lps, h->lb.p, h->ub.p, nu, st));
-      NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
-      NNMPC_TRY(lp_dr_first(e.l_anchor, cnt, B, &h->lps, h->V.p, q->W0.p, h->lb.p, h->ub.p, e.state, e.it, SLOT_ITER, nu,
-                            q->alpha, st));
-      if (prof64) prof_end(span64, st, 0.0, 1, 1);
+      if (full) {
+        const bool prof64 = prof_begin(&span64, st);
+        NNMPC_TRY(lp_anchor_prep(e.l_anchor, cnt, B, h->V.p, q->W0.p, &h->lps, h->lb.p, h->ub.p, nu, st));
+        NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
+        NNMPC_TRY(lp_dr_first(e.l_anchor, cnt, B, &h->lps, h->V.p, q->W0.p, h->lb.p, h->ub.p, e.state, e.it, SLOT_ITER,
+                              nu, q->alpha, pos_r, st));
+        if (prof64) prof_end(span64, st, 0.0, 1, 1);
+      }
       // 1b. tensor-core pass (tcgen05, fp16 increments of the operand, state in FP64) over every live row
       ProfSpan span;
       const bool prof = prof_begin(&span, st);
-      NNMPC_TRY(lp_iterate(&q->lpop, &h->lps, B, h->V.p, h->lb.p, h->ub.p, e.state, SLOT_ITER, e.dres, nu, q->alpha,
-                           h->device, st));
+      NNMPC_TRY(lp_iterate(&q->lpop, &h->lps, B, list_r, e.counts + E_LP, pos_w, h->V.p, h->lb.p, h->ub.p, e.state,
+                           SLOT_ITER, e.dres, nu, q->alpha, h->device, st));
       if (prof) prof_end(span, st, 0.0, 1);
+      // 1c. tail: with few live rows left the same update runs as skinny FP64 GEMMs (counts[E_TAIL] rows, else 0)
+      k_tail_prep<<<B, 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
+      count_launch();
+      GemmOperands gi{};
+      gi.A = q->W0.p; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
+      gi.N = n; gi.K = n; gi.rows = e.l_active; gi.m_count = e.counts + E_TAIL;
+      EpiAdmm::Params ept{h->V.p, q->C.p, q->W1.p, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres};
+      const bool prof64b = prof_begin(&span64, st);
+      NNMPC_TRY(gemm_by_count<EpiAdmm>(gi, ept, st));
+      if (prof64b) prof_end(span64, st, 0.0, 1, 1);
     } else {
       GemmOperands gi{};
       gi.A = Wc; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = e.l_active;
@@ -478,7 +638,11 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
       double* t = Wc; Wc = Wn; Wn = t;
     }
     // 2-4. candidates -> exact KKT check -> done list
-    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter);
+    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter, (cad > 1 && (loop % cad) != 1 % cad) ? 1 : 0, full ? 1 : 0);
+    if (!full) {
+      count_launch();
+      continue;
+    }
     k_make_z<<<B, 256, 0, st>>>(e.l_cand, e.counts + N_CAND, h->V.p, h->Z.p, h->lb.p, h->ub.p, n, nu);
     count_launch(2);
     {
@@ -493,7 +657,7 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
     }
     k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
     // 5. first move, dataset row, plant step for the done rows
-    k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, T, h->Z.p, ous, h->xcur.p, dist, ou,
+    k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
                                  h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld);
     count_launch(2);
     {
@@ -505,18 +669,22 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
       if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
     }
     // 6-7. next time step for the done rows
-    k_step<<<1, 1024, 0, st>>>(e, T, B);
-    count_launch();
+    k_step<<<1, 1024, 0, st>>>(e, T, B, lay);
+    lay ^= 1;
+    k_chunk_swap<<<B, 128, 0, st>>>(e.l_swap, e.counts + N_SWAP, e.swap_old, e.swap_new, h->xcur.p, h->upcur.p, x_io,
+                                    uprev_io, h->us_prev.p, h->kappa.p, h->kappa0, nx, nu);
+    count_launch(2);
     NNMPC_TRY(renew(0));
     // poll the finished counter with a two-loop lag (the GPU never waits for the host)
-    const int slot = (int)(loop % POLL_RING);
+    const int slot = (int)(polls % POLL_RING);
     NNMPC_CUDA(cudaMemcpyAsync(h->pin + slot * N_COUNTERS, h->counts, N_COUNTERS * sizeof(int),
                                cudaMemcpyDeviceToHost, st));
     NNMPC_CUDA(cudaEventRecord(h->poll_ev[slot], st));
-    if (loop >= 2) {
-      const int k = (int)((loop - 2) % POLL_RING);
+    ++polls;
+    if (polls >= 3) {
+      const int k = (int)((polls - 3) % POLL_RING);
       NNMPC_CUDA(cudaEventSynchronize(h->poll_ev[k]));
-      if (h->pin[k * N_COUNTERS + N_FINISHED] >= B) finished = true;
+      if (h->pin[k * N_COUNTERS + N_FINISHED] >= Btot) finished = true;
     }
   }
   // drain: the last loops may not have been polled yet
@@ -525,12 +693,10 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   NNMPC_CUDA(cudaMemcpyAsync(h->pin, h->counts, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(pin64, h->rowiters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (mixed) NNMPC_CUDA(cudaMemcpyAsync(pin64 + 1, h->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  NNMPC_CUDA(cudaMemcpyAsync(x_io, h->xcur.p, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
-  NNMPC_CUDA(cudaMemcpyAsync(uprev_io, h->upcur.p, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
-  NNMPC_CUDA(cudaStreamSynchronize(st));
+  NNMPC_CUDA(cudaStreamSynchronize(st));   // final states were handed back chunk by chunk (k_chunk_swap)
   NNMPC_CUDA(cudaGetLastError());
-  if (h->pin[N_FINISHED] < B)
-    return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], B);
+  if (h->pin[N_FINISHED] < Btot)
+    return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], Btot);
   if (h->pin[F_MAXITER]) rc_warn = NNMPC_WARN_MAXITER;
   g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
   prof_add_flops(2.0 * n * (double)n * (double)*pin64);                               // iteration passes
@@ -538,8 +704,8 @@ static int sim_run_device(nnmpc_sim* h, int B, int T, double* x_io, double* upre
   h->tot_rowiters += (long long)pin64[0];
   h->tot_anchors += (long long)pin64[1];
   h->tot_verifies += (long long)pin64[2];
-  h->tot_qps += (long long)B * T;
-  h->warm_B = B;
+  h->tot_qps += (long long)Btot * T;
+  h->warm_B = Btot == B ? Btot : 0;
   return rc_warn;
 }
 
@@ -566,6 +732,9 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cap = 0;
   h->warm_B = 0;
   h->mixed = 0;
+  h->tail_rows = -1;
+  h->slot_cap = 8192;
+  h->cadence = 2;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
@@ -598,9 +767,11 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   cudaFree(h->stats);
   cudaFreeHost(h->pin);
   h->lps.release();
+  h->lp_layout.release();
   for (int i = 0; i < POLL_RING; ++i) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
   h->Z.release(); h->xin.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
+  h->chunk.release(); h->cold.release();
   h->state.release(); h->tcur.release(); h->it.release(); h->lists.release(); h->dres.release(); h->kres.release();
   h->h_sp.release(); h->h_dist.release(); h->h_x.release(); h->h_uprev.release(); h->h_xs.release();
   h->h_us.release(); h->h_u.release(); h->h_kkt.release(); h->h_xio.release(); h->h_upio.release();
@@ -615,6 +786,27 @@ int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode) {
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_precision: unknown mode %d", mode);
   if (h->mixed != (mode == NNMPC_PRECISION_MIXED)) h->warm_B = 0;   // solver state is not shared between the modes
   h->mixed = mode == NNMPC_PRECISION_MIXED;
+  return 0;
+}
+
+int nnmpc_sim_set_slots(nnmpc_sim_t* h, int slots) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_slots: null handle");
+  if (slots < 1) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_slots: need at least one slot");
+  h->slot_cap = slots;
+  h->warm_B = 0;
+  return 0;
+}
+
+int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_cadence: null handle");
+  if (cadence < 1 || cadence > 8) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_cadence: cadence must be in 1..8");
+  h->cadence = cadence;
+  return 0;
+}
+
+int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_tail_rows: null handle");
+  h->tail_rows = rows < 0 ? -1 : rows;
   return 0;
 }
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
   for (int lb_ = blockIdx.x * TS_WARPS + warp; lb_ < Bn; lb_ += gridDim.x * TS_WARPS) {
     // s: per-slot buffers; b: position in the strided sample arrays
     const long long s = p.indexed ? (long long)p.ix.rows[lb_] : (long long)lb_;
-    const long long b = p.indexed ? s * p.ix.T + p.ix.tcur[s] : s;
+    const long long b = p.indexed ? (p.ix.chunk ? (long long)p.ix.chunk[s] : s) * p.ix.T + p.ix.tcur[s] : s;
     const double* ysp = p.ysp + b * p.ysp_stride;
     const double* dd = p.d + b * p.d_stride;
     // Set-points and disturbances are piecewise constant (sample_prbs_like holds each level for

@@ -31,13 +31,14 @@ struct TsFused {
 
 // Optional indirection for the closed-loop engine: logical sample b is trajectory slot rows[b]
 // (b < *count), at its own time index tcur[slot]; the strided arrays (ysp, d, xs, us, iters and the
-// dataset rows of TsFused) are then indexed by slot*T + tcur[slot], the per-slot buffers of TsFused
+// dataset rows of TsFused) are then indexed by chunk[slot]*T + tcur[slot], the per-slot buffers of TsFused
 // (x, uprev, x0, lb, ub, us_prev, dus) by slot.
 struct TsIndex {
   const int* rows;
   const int* count;
   const int* tcur;
   int T;
+  const int* chunk = nullptr;   // optional: slot -> trajectory chunk it currently works on (default: the slot itself)
 };
 
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,

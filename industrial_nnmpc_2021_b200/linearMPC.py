@@ -547,7 +547,7 @@ def load_training_data(filename):
 class ClosedLoopEngine:
     """Owns the nnmpc_sim handle for one (regulator, target selector, plant) triple."""
 
-    def __init__(self, regulator, target_selector, A, B, Bd, precision=None):
+    def __init__(self, regulator, target_selector, A, B, Bd, precision=None, tail_rows=None, slots=None):
         """``precision``: "f64" (every iteration an FP64 tensor-core GEMM) or "mixed" (tcgen05 fp16
         increments with FP64 anchors; every result still passes an FP64 KKT check).  Default: the
         environment variable NNMPC_PRECISION, else "mixed"."""
@@ -566,6 +566,19 @@ class ClosedLoopEngine:
         _lib.check(rc, "nnmpc_sim_create")
         self._handle = hnd
         self.set_precision(precision or os.environ.get("NNMPC_PRECISION", "mixed"))
+        slots = os.environ.get("NNMPC_SLOTS") if slots is None else slots
+        if slots is not None:
+            self.set_slots(slots)
+        if os.environ.get("NNMPC_CADENCE"):
+            _lib.check(L.nnmpc_sim_set_cadence(self._handle, int(os.environ["NNMPC_CADENCE"])), "nnmpc_sim_set_cadence")
+        tail_rows = os.environ.get("NNMPC_TAIL_ROWS") if tail_rows is None else tail_rows
+        if tail_rows is not None:     # mixed mode: live rows at or below which a call finishes in FP64 (-1 = automatic)
+            _lib.check(L.nnmpc_sim_set_tail_rows(self._handle, int(tail_rows)), "nnmpc_sim_set_tail_rows")
+
+    def set_slots(self, slots):
+        """Most trajectories advanced concurrently; a run with more chunks queues the rest (continuous batching)."""
+        _lib.check(_lib.lib().nnmpc_sim_set_slots(self._handle, int(slots)), "nnmpc_sim_set_slots")
+        self.slots = int(slots)
 
     def set_precision(self, precision):
         if precision not in _lib.PRECISION:

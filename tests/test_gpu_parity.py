@@ -220,8 +220,9 @@ def test_target_selector_matches_oracle(torch_cuda, which, cstrs_problem, cdu_sm
 
 
 # ------------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("M,n", [(128, 128), (1, 64), (300, 540), (1000, 40), (257, 4480), (2688, 1000)])
-def test_lp_split_gemm_matches_fp64(torch_cuda, M, n):
+def test_lp_split_gemm_matches_fp64(torch_cuda, M, n, pair):
     """The tcgen05 pass C = fp16(A) (T1 + T2)' / s (TMA-fed, TMEM-accumulated) against FP64 NumPy: the
     two-term fp16 operator split carries ~22 bits, the fp32 accumulation ~2^-24 sqrt(K) of sum |a||t|."""
     torch = torch_cuda
@@ -232,7 +233,7 @@ def test_lp_split_gemm_matches_fp64(torch_cuda, M, n):
     Bt = rng.standard_normal((n, n)) * np.exp(rng.uniform(-8, 0, (n, n)))
     At, Btt = torch.tensor(A, device="cuda"), torch.tensor(Bt, device="cuda")
     Cd = torch.full((M, n), np.nan, dtype=torch.float64, device="cuda")
-    rc = L.nnmpc_lp_gemm_test(M, n, n, _lib.dptr(At), _lib.dptr(Btt), float(np.abs(Bt).max()), _lib.dptr(Cd), None)
+    rc = L.nnmpc_lp_gemm_test(M, n, n, _lib.dptr(At), _lib.dptr(Btt), float(np.abs(Bt).max()), _lib.dptr(Cd), pair, None)
     _lib.check(rc, "nnmpc_lp_gemm_test")
     torch.cuda.synchronize()
     A16 = A.astype(np.float16).astype(np.float64)
@@ -243,10 +244,15 @@ def test_lp_split_gemm_matches_fp64(torch_cuda, M, n):
 
 
 # ------------------------------------------------------------------------------------ closed loop
-@pytest.fixture(params=["f64", "mixed"])
+@pytest.fixture(params=["f64", "mixed", "mixed-notail"])
 def precision(request, monkeypatch):
-    """Arithmetic of the closed-loop iteration: FP64 DMMA, or tcgen05 fp16 increments + FP64 anchors."""
-    monkeypatch.setenv("NNMPC_PRECISION", request.param)
+    """Arithmetic of the closed-loop iteration: FP64 DMMA, or tcgen05 fp16 increments + FP64 anchors (with
+    the automatic switch to skinny FP64 GEMMs for the last few live rows, or tensor-core passes to the end)."""
+    monkeypatch.setenv("NNMPC_PRECISION", request.param.split("-")[0])
+    if request.param == "mixed-notail":
+        monkeypatch.setenv("NNMPC_TAIL_ROWS", "0")
+    else:
+        monkeypatch.delenv("NNMPC_TAIL_ROWS", raising=False)
     return request.param
 
 
@@ -314,7 +320,13 @@ def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem, pr
     for sel in (slice(0, 40), slice(100, 230), slice(449, 450)):
         sub = sim.engine.run(p.xprior, p.uprev, spc[sel], dsc[sel])
         for k in ("x", "uprev", "xs", "us", "u", "iters"):
-            assert np.array_equal(sub[k], big[k][sel]), (sel, k)
+            if precision == "mixed":
+                # the automatic FP64 tail makes the arithmetic path (not the optimum) depend on how many
+                # trajectories are still live, so batches agree to the solver tolerance, not bitwise
+                if k != "iters":
+                    assert np.max(np.abs(sub[k] - big[k][sel])) <= 1e-7 * max(1.0, np.max(np.abs(big[k][sel]))), (sel, k)
+            else:
+                assert np.array_equal(sub[k], big[k][sel]), (sel, k)
     oreg = om.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub)
     ots = om.TargetSelectorOracle(A=p.A, B=p.B, C=p.C, H=p.H, Bd=p.Bd, Cd=p.Cd, usp=p.usp, Rs=p.Rs, Qs=p.Qs,
                                   ulb=p.ulb, uub=p.uub)
@@ -323,6 +335,32 @@ def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem, pr
                                  uub=p.uub, target_selector=ots, setpoints=spc[c], disturbances=dsc[c])
         for k in ("x", "xs", "us", "u"):
             assert np.max(np.abs(big[k][c] - od[k])) / max(1.0, np.max(np.abs(od[k]))) <= 1e-6, (c, k)
+
+
+def test_closed_loop_chunk_queue(torch_cuda, cdu_small_problem, precision):
+    """More trajectory chunks than slots: finished slots take the next queued chunk (continuous batching).
+    Every chunk must come out as when all chunks run side by side."""
+    from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
+    p = cdu_small_problem
+    Bn, T = 300, 6
+    sim = OfflineSimulator(**p.controller_kwargs(), xprior=p.xprior, setpoints=p.setpoints[:Bn * T],
+                           disturbances=p.disturbances[:Bn * T], num_data_gen_task=1, num_process_per_task=Bn)
+    wide = sim.generate_batch()
+    spc = np.stack(sim.setpoints[0]); dsc = np.stack(sim.disturbances[0])
+    rng = np.random.default_rng(3)
+    x0 = np.tile(p.xprior.T, (Bn, 1)) + 0.01 * rng.standard_normal((Bn, p.Nx))     # per-chunk initial states
+    wide2 = sim.engine.run(x0, p.uprev, spc, dsc)
+    for slots in (64, 7):
+        sim.engine.set_slots(slots)
+        for ref, x_init in ((wide, p.xprior), (wide2, x0)):
+            q = sim.engine.run(x_init, p.uprev, spc, dsc)
+            assert not q["maxiter_hit"] and float(q["kkt"].max()) <= KKT_TOL
+            for k in ("x", "uprev", "xs", "us", "u", "x_final", "uprev_final"):
+                if precision == "mixed":
+                    assert np.max(np.abs(q[k] - ref[k])) <= 1e-7 * max(1.0, np.max(np.abs(ref[k]))), (slots, k)
+                else:
+                    assert np.array_equal(q[k], ref[k]), (slots, k)
+    sim.engine.set_slots(8192)
 
 
 def test_closed_loop_resume_in_slabs(torch_cuda, cdu_small_problem, precision):
