@@ -87,7 +87,12 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   ep.X = s->X.p; ep.V = V; ep.E = s->E.p; ep.Dn = s->D[s->cur ^ 1].p; ep.ldd = s->ldd; ep.lb = lb; ep.ub = ub;
   ep.state = state; ep.iter_state = iter_state; ep.list_r = list_r; ep.pos_w = pos_w; ep.sc_in = s->sc_in.p; ep.sc_out = s->sc_out.p; ep.dres = dres;
   ep.n = s->n; ep.nu = nu; ep.alpha = alpha; ep.inv_sT = 1.0 / op->scale;
-  lp::LpShape g{B, s->n, s->n, len_r};
+  // column-tile groups of at most ~24 MB of operator (both fp16 terms) per group
+  const int bn_tile = lp_use_pair() ? lp::BN2 : LpTileN128::BN;
+  const double tile_mb = 2.0 * bn_tile * (double)op->ldh * 2.0 / 1048576.0;
+  int group_cols = (int)(24.0 / tile_mb);
+  if (group_cols < 1) group_cols = 1;
+  lp::LpShape g{B, s->n, s->n, len_r, group_cols};
   cudaError_t e = lp_use_pair()
                       ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
                       : lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
@@ -158,7 +163,7 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
     if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
       rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
-      lp::LpShape g{M, N, K, nullptr};
+      lp::LpShape g{M, N, K, nullptr, 2};
       const EpiLpStore::Params ep{C, N, 1.0 / op.scale};
       cudaError_t e = pair ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
                            : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);

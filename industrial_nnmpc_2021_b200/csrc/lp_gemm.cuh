@@ -37,16 +37,39 @@ namespace lp {
 constexpr int BM = 128;          // rows (samples) per tile = TMEM lanes
 constexpr int BK = 64;           // fp16 elements per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: each owns 16 of every 32 accumulator columns
+#ifndef NNMPC_EPI_WARPS
+#define NNMPC_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = NNMPC_EPI_WARPS;   // EPI_WARPS / 4 warps per TMEM lane quarter, each owns CW of every 32 accumulator columns
+constexpr int CW = 128 / EPI_WARPS;          // accumulator columns per warp and step (16 or 8)
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;
+
+// Per-warp shared memory of the epilogue: the 32 x 16 accumulator block of one step, transposed through shared
+// memory so that the FP64 state is read and written in 64-byte runs per row (4 lanes x 16 B), and the per-row
+// scalars of the warp's 32 rows.
+struct EpiRowInfo {
+  int row;          // sample row (-1: not taking part)
+  int pw;           // operand row written for it
+  double inv_in, s_out, inv_out;
+};
+struct EpiWarpSmem {
+  float stg[CW * 33];
+  EpiRowInfo info[32];
+};
+constexpr int EPI_SMEM_BYTES = EPI_WARPS * (int)sizeof(EpiWarpSmem);
+
+// L2 eviction-priority policies for TMA loads (createpolicy encodings)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
 template <int BN_, int STAGES_>
 struct LpTile {
   static constexpr int BN = BN_, STAGES = STAGES_;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*1 KB alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*1 KB alignment slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
@@ -91,6 +114,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// same with an L2 eviction-priority hint (the shared operator is re-read by every row tile: keep it resident
+// while the per-sample state streams through)
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                                 uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 
@@ -140,6 +173,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld_32x8(taddr, r); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major operand tile written by TMA with 128-byte swizzle:
@@ -164,15 +206,37 @@ struct LpShape {
   int N;              // rows of B1/B2 = output columns
   int K;              // contraction length (TMA zero-fills beyond it)
   const int* m_dev;   // optional: the row count lives in device memory (0 = nothing to do)
+  int group_cols;     // column tiles per L2 group (see tile_coords); <= 0: all
 };
+
+// Tile order of the persistent CTAs.  The operator (2 x n x n fp16, 80 MB at n = 4480) does not fit the part of
+// the L2 one die can keep while the per-sample state streams through, so the column tiles are walked in groups
+// whose operator slice (group_cols x BN rows of T1 and T2) does: within a group the order is row tile major,
+// column tile minor, so the ~148 tiles in flight share the same few MB of operand rows and the group's operator
+// slice is read from HBM once per pass instead of once per wave of CTAs.
+__device__ __forceinline__ void tile_coords(int t, int ntm, int ntn, int group_cols, int& bm, int& bn) {
+  if (group_cols <= 0 || group_cols >= ntn) {
+    bm = t / ntn;
+    bn = t - bm * ntn;
+    return;
+  }
+  const int per_group = ntm * group_cols;
+  const int gi = t / per_group;
+  const int rem = t - gi * per_group;
+  const int c0 = gi * group_cols;
+  const int gc = (ntn - c0 < group_cols) ? ntn - c0 : group_cols;   // only the last group can be narrower
+  bm = rem / gc;
+  bn = c0 + (rem - bm * gc);
+}
 
 // Epilogue concept:
 //   struct Epi { struct Params {...};
 //     __device__ Epi(const Params&);
-//     // one thread owns output row `pos` (in_range == false beyond M) and 16 consecutive columns at a time
-//     __device__ void begin_row(int pos, bool in_range);
-//     __device__ void chunk(int col0, const uint32_t (&acc)[16] /*fp32 bit patterns*/, int N);
-//     __device__ void end_row();
+//     // warp-collective: the warp owns 32 consecutive output rows (lane l holds the accumulators of row pos0 + l)
+//     __device__ Epi(const Params&, EpiWarpSmem* warp_smem, int lane);
+//     __device__ void begin_tile(int pos0, int M);
+//     __device__ void chunk(int col0, const uint32_t (&acc)[CW] /*fp32 bit patterns*/, int N);   // CW columns
+//     __device__ void end_tile();
 //   };
 template <class T, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -187,6 +251,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 2 * T::STAGES;           // [ACC_STAGES]  MMA -> epilogue
   uint64_t* acc_empty = acc_full + ACC_STAGES;         // [ACC_STAGES]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  EpiWarpSmem* epi_smem = reinterpret_cast<EpiWarpSmem*>(ring + T::STAGES * T::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
@@ -221,14 +286,15 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int bn = t % ntn, bm = t / ntn;     // column tiles fastest: resident CTAs share A row panels
+        int bm, bn;
+        tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * T::STAGE_BYTES;
           mbar_expect_tx(full + s, T::STAGE_BYTES);
           tma_load_2d(st, &tmA, full + s, kb * BK, bm * BM);
-          tma_load_2d(st + T::A_BYTES, &tmB1, full + s, kb * BK, bn * T::BN);
-          tma_load_2d(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN);
+          tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
+          tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -268,25 +334,25 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    Epi epi(ep);
+    Epi epi(ep, epi_smem + (warp - 2), lane);
     int i = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-      const int bn = t % ntn, bm = t / ntn;
+      int bm, bn;
+      tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
       const int as = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      const int row = bm * BM + q * 32 + lane;
-      epi.begin_row(row, row < M);
+      epi.begin_tile(bm * BM + q * 32, M);
       mbar_wait(acc_full + as, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * T::BN);
 #pragma unroll 1
       for (int cc = 0; cc < T::BN / 32; ++cc) {
-        uint32_t acc[16];
-        tmem_ld_32x16(tacc + (uint32_t)(cc * 32 + hsel * 16), acc);
+        uint32_t acc[CW];
+        tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
         tmem_ld_wait();
-        epi.chunk(bn * T::BN + cc * 32 + hsel * 16, acc, g.N);
+        epi.chunk(bn * T::BN + cc * 32 + hsel * CW, acc, g.N);
       }
-      epi.end_row();
+      epi.end_tile();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);
@@ -310,7 +376,8 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int BN2 = 256;          // output columns per pair tile (128 operator rows staged per CTA)
 constexpr int STAGES2 = 4;
 constexpr int STAGE2_BYTES = BM * BK * 2 + 2 * (BN2 / 2) * BK * 2;   // A + B1 half + B2 half = 48 KB
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
+static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory");
 constexpr int TMEM2_COLS = ACC_STAGES * BN2;                          // 512: all of TMEM
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -336,6 +403,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                                      uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
@@ -372,6 +446,7 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* acc_full = bars + 2 * STAGES2;        // [ACC_STAGES] per CTA, multicast commit
   uint64_t* acc_empty = acc_full + ACC_STAGES;    // [ACC_STAGES] leader's copy is used: both CTAs' epilogue warps arrive
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  EpiWarpSmem* epi_smem = reinterpret_cast<EpiWarpSmem*>(ring + STAGES2 * STAGE2_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -409,15 +484,16 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int t = cluster_id; t < tiles; t += nclusters) {
-        const int bn = t % ntn, bm = t / ntn;
+        int bm, bn;
+      tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
         const int arow = bm * 2 * BM + (int)rank * BM;
         const int brow = bn * BN2 + (int)rank * (BN2 / 2);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * STAGE2_BYTES;
           tma_load_2d_pair(st, &tmA, full + s, kb * BK, arow);
-          tma_load_2d_pair(st + BM * BK * 2, &tmB1, full + s, kb * BK, brow);
-          tma_load_2d_pair(st + BM * BK * 2 + (BN2 / 2) * BK * 2, &tmB2, full + s, kb * BK, brow);
+          tma_load_2d_pair_hint(st + BM * BK * 2, &tmB1, full + s, kb * BK, brow, L2_EVICT_LAST);
+          tma_load_2d_pair_hint(st + BM * BK * 2 + (BN2 / 2) * BK * 2, &tmB2, full + s, kb * BK, brow, L2_EVICT_LAST);
           if (leader) mbar_expect_tx(full + s, 2 * STAGE2_BYTES);
           else mbar_arrive_remote(full + s, 0);
           if (++s == STAGES2) { s = 0; ph ^= 1; }
@@ -458,25 +534,25 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== epilogue warps of both CTAs: own 128 accumulator rows =====
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    Epi epi(ep);
+    Epi epi(ep, epi_smem + (warp - 2), lane);
     int i = 0;
     for (int t = cluster_id; t < tiles; t += nclusters, ++i) {
-      const int bn = t % ntn, bm = t / ntn;
+      int bm, bn;
+      tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
       const int as = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      const int row = bm * 2 * BM + (int)rank * BM + q * 32 + lane;
-      epi.begin_row(row, row < M);
+      epi.begin_tile(bm * 2 * BM + (int)rank * BM + q * 32, M);
       mbar_wait(acc_full + as, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2);
 #pragma unroll 1
       for (int cc = 0; cc < BN2 / 32; ++cc) {
-        uint32_t acc[16];
-        tmem_ld_32x16(tacc + (uint32_t)(cc * 32 + hsel * 16), acc);
+        uint32_t acc[CW];
+        tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
         tmem_ld_wait();
-        epi.chunk(bn * BN2 + cc * 32 + hsel * 16, acc, g.N);
+        epi.chunk(bn * BN2 + cc * 32 + hsel * CW, acc, g.N);
       }
-      epi.end_row();
+      epi.end_tile();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

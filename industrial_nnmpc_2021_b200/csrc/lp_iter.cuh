@@ -39,6 +39,10 @@ __device__ __forceinline__ __half quantise_dw(double dw, double s, double inv_s,
 }
 
 // ---- epilogue of the tensor-core pass: the whole iteration on the accumulator registers ----------
+// Warp-collective (see lp_gemm.cuh): the warp owns 32 rows; TMEM hands lane l the 16 accumulators of row l, the
+// block is transposed through shared memory, and lane (rg = l / 4, cp = l % 4) then updates rows rg, rg + 8,
+// rg + 16, rg + 24 at columns {2cp, 2cp + 1} (and {8 + 2cp, 9 + 2cp} with 16-column steps): every global access of the FP64 state is a
+// 64-byte run per row, whole 32-byte sectors, all loads of a step in flight before the first use.
 struct EpiDelta {
   struct Params {
     double* X;
@@ -60,118 +64,122 @@ struct EpiDelta {
     double inv_sT;       // 1 / operator scale
   };
   Params p;
-  bool ok;
-  int row;
-  long long pw;
-  double inv_in, s_out, inv_out, dmax;
-  const double* lbr;
-  const double* ubr;
-  __device__ explicit EpiDelta(const Params& p_) : p(p_), ok(false), row(0), pw(0), inv_in(0), s_out(0), inv_out(0), dmax(0), lbr(nullptr), ubr(nullptr) {}
-  __device__ void begin_row(int pos, bool in_range) {
-    row = in_range ? (p.list_r ? p.list_r[pos] : pos) : 0;
-    ok = in_range && p.state[row] == p.iter_state;
-    dmax = 0.0;
-    if (ok) {
-      pw = p.pos_w ? p.pos_w[row] : row;
-      inv_in = p.inv_sT / p.sc_in[row];
-      s_out = p.sc_out[row];
-      inv_out = 1.0 / s_out;
-      lbr = p.lb + (long long)row * p.nu;
-      ubr = p.ub + (long long)row * p.nu;
+  lp::EpiWarpSmem* sm;
+  int lane, rg, cp;
+  double dmax[4];
+  __device__ EpiDelta(const Params& p_, lp::EpiWarpSmem* sm_, int lane_)
+      : p(p_), sm(sm_), lane(lane_), rg(lane_ >> 2), cp(lane_ & 3) {}
+  __device__ void begin_tile(int pos0, int M) {
+    const int pos = pos0 + lane;
+    lp::EpiRowInfo ri;
+    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0;
+    if (pos < M) {
+      const int row = p.list_r ? p.list_r[pos] : pos;
+      if (p.state[row] == p.iter_state) {
+        ri.row = row;
+        ri.pw = p.pos_w ? p.pos_w[row] : row;
+        ri.inv_in = p.inv_sT / p.sc_in[row];
+        ri.s_out = p.sc_out[row];
+        ri.inv_out = 1.0 / ri.s_out;
+      }
     }
+    __syncwarp();            // the previous tile's last reads of info[] are done
+    sm->info[lane] = ri;
+    dmax[0] = dmax[1] = dmax[2] = dmax[3] = 0.0;
+    __syncwarp();
   }
-  // 16 consecutive columns of this thread's row.  Fast path (stage width a multiple of 16, full chunk): every
-  // state load of the chunk is issued before the first use and results are stored at the end, so each
-  // epilogue thread keeps 24 x 16 B of HBM traffic in flight.
-  __device__ void chunk(int col0, const uint32_t (&acc)[16], int N) {
-    if (!ok || col0 >= N) return;
-    const long long base = (long long)row * p.n + col0;
-    __half* dn = p.Dn + pw * p.ldd + col0;
-    const int k0 = col0 % p.nu;
-    if ((p.nu & 15) == 0 && col0 + 16 <= N) {
-      double2 x[8], v[8];
-      float2 e[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = *reinterpret_cast<const double2*>(p.X + base + 2 * i);
-        v[i] = *reinterpret_cast<const double2*>(p.V + base + 2 * i);
-        e[i] = *reinterpret_cast<const float2*>(p.E + base + 2 * i);
-      }
-      __half2 q[8];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        // the stage bounds of these 8 columns: L1/L2 hits (every column tile re-reads the same 2 x 256 B per row),
-        // loaded half a chunk at a time to stay inside the 168 registers ten warps leave per thread
-        double2 lbc[4], ubc[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          lbc[i] = *reinterpret_cast<const double2*>(lbr + k0 + 8 * hh + 2 * i);
-          ubc[i] = *reinterpret_cast<const double2*>(ubr + k0 + 8 * hh + 2 * i);
-        }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int i = 4 * hh + ii;
-          x[i].x += (double)__uint_as_float(acc[2 * i]) * inv_in;
-          x[i].y += (double)__uint_as_float(acc[2 * i + 1]) * inv_in;
-          const double wl0 = (2.0 * clipd(v[i].x, lbc[ii].x, ubc[ii].x) - v[i].x) - (double)e[i].x;
-          const double wl1 = (2.0 * clipd(v[i].y, lbc[ii].y, ubc[ii].y) - v[i].y) - (double)e[i].y;
-          double dw0, dw1, a0, a1;
-          dr_delta_one(x[i].x, v[i].x, wl0, lbc[ii].x, ubc[ii].x, p.alpha, dw0, a0);
-          dr_delta_one(x[i].y, v[i].y, wl1, lbc[ii].y, ubc[ii].y, p.alpha, dw1, a1);
-          const __half q0 = quantise_dw(dw0, s_out, inv_out, e[i].x);
-          const __half q1 = quantise_dw(dw1, s_out, inv_out, e[i].y);
-          q[i] = __halves2half2(q0, q1);
-          const double a = (a0 <= a1) ? a1 : a0;       // NaN propagates
-          dmax = (a <= dmax) ? dmax : a;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        *reinterpret_cast<double2*>(p.X + base + 2 * i) = x[i];
-        *reinterpret_cast<double2*>(p.V + base + 2 * i) = v[i];
-        *reinterpret_cast<float2*>(p.E + base + 2 * i) = e[i];
-      }
-      uint4* d4 = reinterpret_cast<uint4*>(dn);
-      d4[0] = make_uint4(*reinterpret_cast<uint32_t*>(&q[0]), *reinterpret_cast<uint32_t*>(&q[1]),
-                         *reinterpret_cast<uint32_t*>(&q[2]), *reinterpret_cast<uint32_t*>(&q[3]));
-      d4[1] = make_uint4(*reinterpret_cast<uint32_t*>(&q[4]), *reinterpret_cast<uint32_t*>(&q[5]),
-                         *reinterpret_cast<uint32_t*>(&q[6]), *reinterpret_cast<uint32_t*>(&q[7]));
-      return;
-    }
-    // general path (any stage width, ragged last chunk): element pairs, n is even
-    int k = k0;
-#pragma unroll 1
-    for (int j = 0; j < 16; j += 2) {
-      const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
-      if (col0 + j < N) {
-        double2 x = *reinterpret_cast<const double2*>(p.X + base + j);
-        double2 v = *reinterpret_cast<const double2*>(p.V + base + j);
-        float2 e = *reinterpret_cast<const float2*>(p.E + base + j);
-        const double l0 = lbr[k], u0 = ubr[k], l1 = lbr[k1], u1 = ubr[k1];
-        x.x += (double)__uint_as_float(acc[j]) * inv_in;
-        x.y += (double)__uint_as_float(acc[j + 1]) * inv_in;
-        const double wl0 = (2.0 * clipd(v.x, l0, u0) - v.x) - (double)e.x;
-        const double wl1 = (2.0 * clipd(v.y, l1, u1) - v.y) - (double)e.y;
-        double dw0, dw1, a0, a1;
-        dr_delta_one(x.x, v.x, wl0, l0, u0, p.alpha, dw0, a0);
-        dr_delta_one(x.y, v.y, wl1, l1, u1, p.alpha, dw1, a1);
-        const __half q0 = quantise_dw(dw0, s_out, inv_out, e.x);
-        const __half q1 = quantise_dw(dw1, s_out, inv_out, e.y);
-        *reinterpret_cast<double2*>(p.X + base + j) = x;
-        *reinterpret_cast<double2*>(p.V + base + j) = v;
-        *reinterpret_cast<float2*>(p.E + base + j) = e;
-        *reinterpret_cast<__half2*>(dn + j) = __halves2half2(q0, q1);
-        const double a = (a0 <= a1) ? a1 : a0;
-        dmax = (a <= dmax) ? dmax : a;
-      }
-      k = (k1 + 1 == p.nu) ? 0 : k1 + 1;
-    }
+  // one column pair of one row
+  __device__ __forceinline__ void pair(double2& x, double2& v, float2& e, float a0, float a1, double2 l, double2 u,
+                                       const lp::EpiRowInfo& ri, __half2& q, double& dm) {
+    x.x += (double)a0 * ri.inv_in;
+    x.y += (double)a1 * ri.inv_in;
+    const double wl0 = (2.0 * clipd(v.x, l.x, u.x) - v.x) - (double)e.x;
+    const double wl1 = (2.0 * clipd(v.y, l.y, u.y) - v.y) - (double)e.y;
+    double dw0, dw1, d0, d1;
+    dr_delta_one(x.x, v.x, wl0, l.x, u.x, p.alpha, dw0, d0);
+    dr_delta_one(x.y, v.y, wl1, l.y, u.y, p.alpha, dw1, d1);
+    const __half q0 = quantise_dw(dw0, ri.s_out, ri.inv_out, e.x);
+    const __half q1 = quantise_dw(dw1, ri.s_out, ri.inv_out, e.y);
+    q = __halves2half2(q0, q1);
+    const double a = (d0 <= d1) ? d1 : d0;       // NaN propagates
+    dm = (a <= dm) ? dm : a;
   }
-  __device__ void end_row() {
-    if (!ok) return;
-    double m = dmax;
-    if (!(m <= 1.7e308)) m = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
-    atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(m));
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
+    constexpr int NP = lp::CW / 8;     // column pairs per row and lane
+    // transpose: stg[c][r] (stride 33: conflict-free writes)
+#pragma unroll
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * 33 + lane] = __uint_as_float(acc[c]);
+    __syncwarp();
+    const bool fast = (p.nu & 7) == 0;                         // stage width a multiple of 8: no wrap inside a pair run
+    double2 x[4 * NP], v[4 * NP];
+    float2 e[4 * NP];
+    // all state loads of the step first (streaming: read once per pass)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = sm->info[rg + 8 * i].row;
+      if (row >= 0) {
+        const long long base = (long long)row * p.n;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const int c = col0 + 8 * j + 2 * cp;                 // n is even: the pair is inside when its first column is
+          if (c < N) {
+            x[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.X + base + c));
+            v[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.V + base + c));
+            e[NP * i + j] = __ldcs(reinterpret_cast<const float2*>(p.E + base + c));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg + 8 * i;
+      const lp::EpiRowInfo ri = sm->info[r];
+      if (ri.row < 0) continue;
+      const long long base = (long long)ri.row * p.n;
+      const double* lbr = p.lb + (long long)ri.row * p.nu;
+      const double* ubr = p.ub + (long long)ri.row * p.nu;
+      __half* dn = p.Dn + (long long)ri.pw * p.ldd;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int c = col0 + 8 * j + 2 * cp;
+        if (c < N) {
+          const int k = c % p.nu;
+          double2 l, u;
+          if (fast) {
+            l = *reinterpret_cast<const double2*>(lbr + k);
+            u = *reinterpret_cast<const double2*>(ubr + k);
+          } else {
+            const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
+            l = make_double2(lbr[k], lbr[k1]);
+            u = make_double2(ubr[k], ubr[k1]);
+          }
+          __half2 q;
+          pair(x[NP * i + j], v[NP * i + j], e[NP * i + j], sm->stg[(8 * j + 2 * cp) * 33 + r],
+               sm->stg[(8 * j + 2 * cp + 1) * 33 + r], l, u, ri, q, dmax[i]);
+          __stcs(reinterpret_cast<double2*>(p.X + base + c), x[NP * i + j]);
+          __stcs(reinterpret_cast<double2*>(p.V + base + c), v[NP * i + j]);
+          __stcs(reinterpret_cast<float2*>(p.E + base + c), e[NP * i + j]);
+          *reinterpret_cast<__half2*>(dn + c) = q;
+        }
+      }
+    }
+    __syncwarp();            // stg is rewritten by the next step
+  }
+  __device__ void end_tile() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double m = dmax[i];
+      // the 4 lanes of a row group hold disjoint columns of the same rows; NaN must survive the reduction
+      double o = __shfl_xor_sync(0xffffffffu, m, 1);
+      m = (o <= m) ? m : o;
+      o = __shfl_xor_sync(0xffffffffu, m, 2);
+      m = (o <= m) ? m : o;
+      const int row = sm->info[rg + 8 * i].row;
+      if (cp == 0 && row >= 0) {
+        if (!(m <= 1.7e308)) m = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
+        atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(m));
+      }
+    }
   }
 };
 
@@ -183,17 +191,20 @@ struct EpiLpStore {
     double scale;
   };
   Params p;
+  int lane, row;
   bool ok;
-  int row;
-  __device__ explicit EpiLpStore(const Params& p_) : p(p_), ok(false), row(0) {}
-  __device__ void begin_row(int pos, bool in_range) { ok = in_range; row = pos; }
-  __device__ void chunk(int col0, const uint32_t (&acc)[16], int N) {
+  __device__ EpiLpStore(const Params& p_, lp::EpiWarpSmem*, int lane_) : p(p_), lane(lane_), row(0), ok(false) {}
+  __device__ void begin_tile(int pos0, int M) {
+    row = pos0 + lane;
+    ok = row < M;
+  }
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
     if (!ok) return;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
+    for (int j = 0; j < lp::CW; ++j)
       if (col0 + j < N) p.C[(long long)row * p.ldc + col0 + j] = (double)__uint_as_float(acc[j]) * p.scale;
   }
-  __device__ void end_row() {}
+  __device__ void end_tile() {}
 };
 
 // ---- FP64 anchor: x = Top w - c on the accumulators of the DMMA GEMM ---------------------------
