@@ -436,12 +436,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--traj", type=int, default=2688,
-                    help="closed-loop trajectories per GPU (2688 = 21 row tiles x 35 column tiles = 4.97 waves of 148 SMs)")
-    ap.add_argument("--slab", type=int, default=32, help="simulation steps every trajectory advances per bench step")
+    ap.add_argument("--traj", type=int, default=32768,
+                    help="closed-loop trajectory chunks per GPU and bench step (the reference's per-process chunks, "
+                         "lib/linearMPC.py:786-801); with --slots below it they queue up (continuous batching)")
+    ap.add_argument("--slab", type=int, default=16, help="simulation steps every trajectory advances per bench step")
     ap.add_argument("--horizon", type=int, default=140)
     ap.add_argument("--ref-steps", type=int, default=1, help="closed-loop steps per worker per reference step")
-    ap.add_argument("--slots", type=int, default=8192,
+    ap.add_argument("--slots", type=int, default=16384,
                     help="trajectories advanced concurrently per GPU; with --traj above it the other chunks queue up and "
                          "finished slots take the next one (continuous batching)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

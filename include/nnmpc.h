@@ -61,6 +61,10 @@ int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset);
 int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N,
                     const double* P_host, const double* tq_host, const double* Top_host,
                     const double* Mtq_host, const double* Kunc_host, double alpha, int device);
+/* The ADMM penalty vector rho (host, n doubles, all > 0) behind Top = (P + diag(rho))^-1 diag(rho).  Needed by the
+ * mixed-precision closed loop (nnmpc_sim_set_precision), which re-anchors x = Top w - c from the exact gradient
+ * g = P z + q of its KKT checks:  w := z + g / rho  gives  x = z  exactly. */
+int nnmpc_qp_set_penalty(nnmpc_qp_t* h, const double* rho_host);
 int nnmpc_qp_destroy(nnmpc_qp_t* h);
 
 /* Batched solve; replaces one DenseQPRegulator.solve(x0) per sample (:495-512) with the bounds
@@ -124,7 +128,7 @@ int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode);
  * With B > slots `resume` is ignored (every chunk starts cold). */
 int nnmpc_sim_set_slots(nnmpc_sim_t* h, int slots);
 /* Mixed mode only: the FP64 phases (anchors, exact checks, plant step, next targets) run every
- * `cadence`-th engine loop over the rows that accumulated meanwhile (default 2; 1 = every loop). */
+ * `cadence`-th engine loop over the rows that accumulated meanwhile (default 4; 1 = every loop). */
 int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence);
 /* Mixed mode only: once at most `rows` trajectories of a call are still running, the rest of the call
  * iterates with skinny FP64 GEMMs over just those rows instead of full tensor-core passes

@@ -36,6 +36,7 @@ int lp_state_ensure(LpState* s, long long B, int n) {
   s->ldd = ((long long)n + 63) / 64 * 64;
   NNMPC_TRY(s->X.ensure((size_t)cap * n));
   NNMPC_TRY(s->E.ensure((size_t)cap * n));
+  NNMPC_TRY(s->Wl.ensure((size_t)cap * n));
   NNMPC_TRY(s->sc_in.ensure((size_t)cap));
   NNMPC_TRY(s->sc_out.ensure((size_t)cap));
   // rows and columns padded to whole TMA boxes (zeros), so no tile ever reaches outside the tensor
@@ -74,6 +75,26 @@ int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, dou
   if (max_rows <= 0) return 0;
   k_dr_first<<<max_rows, 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
                                        s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lp_reanchor(const int* rows, const int* count, int max_rows, const int* state, int emit_state, const double* Z,
+                const double* rinv, LpState* s, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  k_reanchor<<<max_rows, 256, 0, st>>>(rows, count, state, emit_state, Z, s->Wl.p, rinv, s->X.p, s->n);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emit_state, int iter_state, LpState* s,
+            const double* V, const double* lb, const double* ub, const double* dtrig, int nu, double alpha,
+            const int* pos_r, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  k_lp_emit<<<max_rows, 256, 0, st>>>(rows, count, state, emit_state, iter_state, V, s->Wl.p, s->E.p, s->D[s->cur].p,
+                                      s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;

@@ -13,11 +13,12 @@ struct LpState {
   int n = 0;
   long long ldd = 0;                 // leading dimension of the fp16 increment buffers
   DevBuf<double> X, sc_in, sc_out;
+  DevBuf<double> Wl;                 // exact gradient of the last check, then w_lp, then the staged first increment
   DevBuf<float> E;
   DevBuf<__half> D[2];               // double buffered: the TMA reads D[cur], the epilogue writes D[cur ^ 1]
   CUtensorMap tmD[2];
   int cur = 0;
-  void release() { X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release(); cap = 0; }
+  void release() { Wl.release(); X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release(); cap = 0; }
 };
 
 #ifdef __CUDACC__
@@ -48,6 +49,13 @@ int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double
 int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
                 const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
                 cudaStream_t st);
+// candidates that failed their exact check (state == emit_state; Wl holds g = P z + q): x := z, Wl := w_lp = z + g / rho
+int lp_reanchor(const int* rows, const int* count, int max_rows, const int* state, int emit_state, const double* Z,
+                const double* rinv, LpState* s, cudaStream_t st);
+// listed rows in emit_state: first fp16 increment from the exactly anchored (x, w_lp); state := iter_state
+int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emit_state, int iter_state, LpState* s,
+            const double* V, const double* lb, const double* ub, const double* dtrig, int nu, double alpha,
+            const int* pos_r, cudaStream_t st);
 // One tensor-core pass over the operand rows [0, *len_r) (at most B); flips s->cur.  Operand row p belongs to
 // sample list_r[p]; it takes part iff state[sample] == iter_state, and its next increment is written to
 // operand row pos_w[sample] of the other buffer (so the layout is re-compacted one pass behind the live list).

@@ -315,4 +315,71 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
   }
 }
 
+// ---- re-anchoring from a failed exact check (no FP64 anchor GEMM) -------------------------------
+// The check computes g = P z + q in FP64 for z = clip(v).  With w_lp := z + g / rho the tracked quantity
+// x = Top w_lp - c = (P + D)^-1 (D z + P z) = z holds EXACTLY, so the check itself re-anchors the fp16 path:
+// x := z, and what is left to deliver is w - w_lp = (z - v) - g / rho, which vanishes at the solution - the
+// operator-split and fp32-accumulation errors of delivering it are relative to a vanishing quantity.
+__global__ void k_reanchor(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ state,
+                           int emit_state, const double* __restrict__ Z, double* __restrict__ GW,
+                           const double* __restrict__ rinv, double* __restrict__ X, int n) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  if (state[s] != emit_state) return;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double z = Z[s * n + j];
+    GW[s * n + j] = z + GW[s * n + j] * rinv[j];          // g -> w_lp
+    X[s * n + j] = z;
+  }
+}
+
+// Rows in `emit_state` (one CTA per row): first fp16 increment from the exactly anchored (x, w_lp):
+//   dw = (2 clip(v) - v) - w_lp  -> operand row of the next tensor-core pass, quantisation residual into E.
+// The scale of the operand the next pass WRITES is a guess from the ||d|| that triggered the check plus the
+// increment itself (k_select takes over from the measured ||d|| after that pass; a guess that is too small only
+// saturates the increment, whose remainder E carries forward).
+__global__ void __launch_bounds__(256)
+k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state, int emit_state,
+          int iter_state, const double* __restrict__ V, double* __restrict__ WL, float* __restrict__ E,
+          __half* __restrict__ D, long long ldd, const double* __restrict__ lb, const double* __restrict__ ub,
+          double* __restrict__ sc_in, double* __restrict__ sc_out, const double* __restrict__ dtrig, int n, int nu,
+          double alpha, const int* __restrict__ pos_r) {
+  if ((int)blockIdx.x >= *count) return;
+  const long long s = rows[blockIdx.x];
+  if (state[s] != emit_state) return;
+  __shared__ double red[8];
+  double wmax = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int k = j % nu;
+    const double v = V[s * n + j];
+    const double z = clipd(v, lb[s * nu + k], ub[s * nu + k]);
+    const double dw = (2.0 * z - v) - WL[s * n + j];
+    WL[s * n + j] = dw;                   // staged for the second pass
+    const double b = fabs(dw);
+    wmax = (b <= wmax) ? wmax : b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double b = __shfl_xor_sync(0xffffffffu, wmax, o);
+    wmax = (b <= wmax) ? wmax : b;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wmax;
+  __syncthreads();
+  wmax = red[0];
+  for (int w = 1; w < 8; ++w) wmax = (red[w] <= wmax) ? wmax : red[w];
+  const double sq = pow2_scale(wmax), inv = 1.0 / sq;
+  const long long dpos = pos_r ? pos_r[s] : s;      // row of the operand buffer the next pass reads for this sample
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float e;
+    const __half q = quantise_dw(WL[s * n + j], sq, inv, e);
+    if (dpos >= 0) D[dpos * ldd + j] = q;
+    E[s * n + j] = e;
+  }
+  if (threadIdx.x == 0) {
+    sc_in[s] = sq;
+    sc_out[s] = pow2_scale(3.0 * alpha * (dtrig[s] + wmax));
+    state[s] = iter_state;
+  }
+}
+
 }  // namespace nnmpc

@@ -317,9 +317,34 @@ int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N, const doubl
   return 0;
 }
 
+int nnmpc_qp_set_penalty(nnmpc_qp_t* h, const double* rho_host) {
+  if (!h || !rho_host) return set_error(NNMPC_ERR_BADARG, "nnmpc_qp_set_penalty: null argument");
+  DeviceGuard dg(h->device);
+  double* tmp = new (std::nothrow) double[(size_t)h->n];
+  if (!tmp) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+  for (int i = 0; i < h->n; ++i) {
+    if (!(rho_host[i] > 0.0) || !(rho_host[i] <= 1.7e308)) {
+      delete[] tmp;
+      return set_error(NNMPC_ERR_BADARG, "nnmpc_qp_set_penalty: rho[%d] must be positive and finite", i);
+    }
+    tmp[i] = 1.0 / rho_host[i];
+  }
+  int rc = 0;
+  if (!h->rinv && cudaMalloc((void**)&h->rinv, (size_t)h->n * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    h->rinv = nullptr;
+    rc = set_error(NNMPC_ERR_NOMEM, "cudaMalloc failed for the penalty vector");
+  }
+  if (rc == 0 && cudaMemcpy(h->rinv, tmp, (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = set_error(NNMPC_ERR_CUDA, "nnmpc_qp_set_penalty: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  delete[] tmp;
+  return rc;
+}
+
 int nnmpc_qp_destroy(nnmpc_qp_t* h) {
   if (!h) return 0;
   DeviceGuard dg(h->device);
+  if (h->rinv) cudaFree(h->rinv);
   cudaFree(h->P); cudaFree(h->Top); cudaFree(h->tq); cudaFree(h->Mtq); cudaFree(h->Kunc);
   cudaFree(h->counts); cudaFree(h->iter_sum); cudaFreeHost(h->h_pinned);
   h->V.release(); h->W0.release(); h->W1.release(); h->C.release(); h->Ql.release();

@@ -242,6 +242,7 @@ struct nnmpc_qp {
   double p_norm_inf;                  // ||P||_inf (max absolute row sum), scale of the convergence trigger
   double *P, *Top, *tq, *Mtq, *Kunc;  // device operators
   double top_max;                     // max |Top|
+  double* rinv = nullptr;             // device n: 1 / rho (nnmpc_qp_set_penalty), null until set
   nnmpc::LpOperator lpop;             // fp16 split of Top, built on first use by the mixed-precision iteration
   // scratch, sized for `cap` samples
   long long cap;

@@ -28,7 +28,8 @@
 namespace nnmpc {
 int qp_ensure_scratch(nnmpc_qp* h, long long B);
 
-enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4, SLOT_ANCHOR = 5 };
+// SLOT_EMIT (mixed mode): x and w_lp are exact (re-anchored by an exact check), the first fp16 increment is pending
+enum SlotState { SLOT_IDLE = 0, SLOT_ITER = 1, SLOT_CAND = 2, SLOT_DONE = 3, SLOT_RENEW = 4, SLOT_ANCHOR = 5, SLOT_EMIT = 6 };
 enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4, F_MAXITER = 5, N_ANCHOR = 6,
                // mixed mode: effective row counts of this loop's launches (0 switches a launch off on the device)
                E_ANCHOR = 7, E_LP = 8, E_TAIL = 9, LP_LEN0 = 10, LP_LEN1 = 11,
@@ -80,6 +81,7 @@ struct EpiVerifyMax {
     const double* ub;
     unsigned long long* kres;
     int n, nu;
+    double* G;   // nullable: the exact gradient g = P z + q per element (mixed mode re-anchors x from it)
   };
   Params p;
   double rmax;
@@ -89,6 +91,7 @@ struct EpiVerifyMax {
     const long long off = (long long)pr * p.n + col;
     const int k = col % p.nu;
     const double z = p.Z[off], g = a + p.Ql[off];
+    if (p.G) p.G[off] = g;
     double r = fabs(z - clipd(z - g, p.lb[(long long)pr * p.nu + k], p.ub[(long long)pr * p.nu + k]));
     if (!(r <= 1.7e308)) r = __longlong_as_double(0x7ff0000000000000ll);
     rmax = fmax(rmax, r);
@@ -204,10 +207,10 @@ __global__ void k_make_z(const int* __restrict__ rows, const int* __restrict__ c
 __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int max_iter, int T, int* out_iters,
                                                  double* out_kkt, double kappa_max) {
   const int nc = e.counts[N_CAND];
-  int base = 0, nfail = 0;
+  int base = 0;
   for (int i0 = 0; i0 < nc; i0 += 1024) {
     const int i = i0 + threadIdx.x;
-    bool done = false, fail = false;
+    bool done = false;
     int s = 0;
     if (i < nc) {
       s = e.l_cand[i];
@@ -230,17 +233,17 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
         if (out_kkt) out_kkt[o] = r;
         if (!(r <= tol)) e.counts[F_MAXITER] = 1;
       } else {
-        fail = true;
-        e.state[s] = e.mixed ? SLOT_ANCHOR : SLOT_ITER;
+        // mixed mode: the exact check re-anchors x (k_reanchor), the row goes on once k_lp_emit has issued
+        // its first increment - no FP64 anchor GEMM
+        e.state[s] = e.mixed ? SLOT_EMIT : SLOT_ITER;
       }
     }
     base = block_append(done, s, e.l_done, base);
-    if (e.mixed) nfail = block_append(fail, s, e.l_anchor, nfail);
   }
   if (threadIdx.x == 0) {
     e.counts[N_DONE] = base;
-    e.counts[N_ANCHOR] = nfail;   // k_step appends the renewed rows
-    if (e.mixed) e.stats[1] += (unsigned long long)nc;
+    e.counts[N_ANCHOR] = 0;   // k_step appends the rows that start a QP
+    if (e.mixed) e.stats[1] += (unsigned long long)nc;   // failed checks = checks - QPs
   }
 }
 
@@ -324,7 +327,8 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int
   if (nd > 0) {   // only a finished chunk changes the live list, but rebuilding is cheap
     for (int i0 = 0; i0 < S; i0 += 1024) {
       const int s = i0 + threadIdx.x;
-      const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW || e.state[s] == SLOT_ANCHOR);
+      const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW || e.state[s] == SLOT_ANCHOR ||
+                                  e.state[s] == SLOT_EMIT);
       na = block_append(live, s, e.l_active, na);
     }
   }
@@ -524,6 +528,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny, n = q->n, nxa = h->nxa_ld;
   const int mixed = h->mixed;
   if (mixed) {
+    if (!q->rinv)
+      return set_error(NNMPC_ERR_BADARG, "mixed precision needs the ADMM penalty vector: call nnmpc_qp_set_penalty first");
     if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
     NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n));
   }
@@ -548,6 +554,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
 
   double* Wc = q->W0.p;   // operand the next iteration reads
   double* Wn = q->W1.p;
+  int lay = 0;            // mixed mode: operand layout buffer the next tensor-core pass reads
 
   // target selector + regulator inputs + solver (re)start for the rows of the renew list
   auto renew = [&](int first) -> int {
@@ -571,19 +578,24 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     }
     count_launch(2);
     if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
+    // mixed mode: a QP starts from an FP64 anchor GEMM at the top of the next full loop.  (Measured on B200:
+    // starting it instead from the x the previous QP's last check anchored, with the change of the operand as
+    // the first fp16 increment, makes nearly every first check fail - the stage shift is an O(1e-2) increment
+    // whose fp32-accumulation error is far above the 1e-10 the trigger needs - and costs 2 checks + 53
+    // iterations per QP instead of 1.1 + 30.)
     k_warm_shift<<<B, 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
                                     h->dus.p, h->lb.p, h->ub.p, n, nu, e.cold, mixed ? SLOT_ANCHOR : SLOT_ITER,
                                     mixed ? 0 : 1);
     count_launch();
     return 0;
   };
+
   NNMPC_TRY(renew(1));
 
-  // mixed mode: the FP64 phases (anchors, exact checks, plant step, next targets) run every cad-th loop over the
-  // rows that accumulated meanwhile - those rows sit out at most cad-1 tensor-core passes, and the FP64 GEMMs
-  // and the small kernels around them see cad times longer row lists
+  // mixed mode: the FP64 phases (exact checks, plant step, next targets, cold-start anchors) run every cad-th loop
+  // over the rows that accumulated meanwhile - those rows sit out at most cad-1 tensor-core passes, and the FP64
+  // GEMMs and the small kernels around them see cad times longer row lists
   const int cad = mixed ? (h->cadence > 1 ? h->cadence : 1) : 1;
-  int lay = 0;            // operand layout buffer the next tensor-core pass reads
   long long polls = 0;
   const long long max_loops = ((long long)T * ((long long)max_iter + 2) * ((Btot + B - 1) / B) + 8) * cad;
   int rc_warn = 0;
@@ -649,13 +661,20 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       GemmOperands gv{};
       gv.A = h->Z.p; gv.lda = n; gv.Bt = q->P; gv.ldb = n; gv.M = B; gv.N = n; gv.K = n; gv.rows = e.l_cand;
       gv.m_count = e.counts + N_CAND;
-      EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu};
+      EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu, mixed ? h->lps.Wl.p : nullptr};
       ProfSpan span64;
       const bool prof64 = mixed && prof_begin(&span64, st);
       NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
       if (prof64) prof_end(span64, st, 0.0, 1, 1);
     }
     k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
+    if (mixed) {
+      // a failed exact check re-anchors the fp16 path from its own gradient (no FP64 anchor GEMM): x := z exactly
+      // for w_lp = z + g / rho; the row goes on with the first increment of what is left to deliver
+      NNMPC_TRY(lp_reanchor(e.l_cand, e.counts + N_CAND, B, e.state, SLOT_EMIT, h->Z.p, q->rinv, &h->lps, st));
+      NNMPC_TRY(lp_emit(e.l_cand, e.counts + N_CAND, B, e.state, SLOT_EMIT, SLOT_ITER, &h->lps, h->V.p, h->lb.p,
+                        h->ub.p, e.dtrig, nu, q->alpha, e.lp_pos + (long long)(lay ^ 1) * B, st));
+    }
     // 5. first move, dataset row, plant step for the done rows
     k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
                                  h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld);
@@ -734,7 +753,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->mixed = 0;
   h->tail_rows = -1;
   h->slot_cap = 8192;
-  h->cadence = 2;
+  h->cadence = 4;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;

@@ -312,6 +312,8 @@ class DenseQPRegulator:
                                float(self.alpha), self._dev)
         _lib.check(rc, "nnmpc_qp_create")
         self._handle = hnd
+        rho = _lib.host(self.rho_vec)
+        _lib.check(L.nnmpc_qp_set_penalty(hnd, _lib.hptr(rho)), "nnmpc_qp_set_penalty")
 
     def __del__(self):
         try:
