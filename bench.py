@@ -396,12 +396,31 @@ def run_native(args):
                 "peak_source": f"dense 16-bit tensor throughput, sustained figure of MEASURED_PEAKS.json ({peak_src}); "
                                "kernel timed inside a long step",
                 "flops_per_launch": per_unit + "; the kernel executes 2x that in MMA work (T1 and T2 products)"}
-        r_64 = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAnchor|EpiVerifyMax> (FP64 anchors x = Top w - c and "
-                                             "exact KKT checks P z + q, DMMA, small row lists)",
-                "achieved": f64_ach, "peak": best, "unit": "TFLOP/s", "frac": f64_ach / best if best else None,
-                "traffic": None, "launches": f64_launches, "avg_launch_ms": f64_ms / max(f64_launches, 1),
-                "share_of_step": f64_ms / step_ms_local, "peak_source": dgemm_src,
-                "flops_per_launch": "listed samples x 2 n^2"}
+        if os.environ.get("NNMPC_EXACT_GEMM", "int8") == "dmma":
+            r_64 = {"bound": "tensor", "kernel": "gemm_f64_kernel<EpiAnchor|EpiVerifyMax> (FP64 anchors x = Top w - c and "
+                                                 "exact KKT checks P z + q, DMMA, small row lists)",
+                    "achieved": f64_ach, "peak": best, "unit": "TFLOP/s", "frac": f64_ach / best if best else None,
+                    "traffic": None, "launches": f64_launches, "avg_launch_ms": f64_ms / max(f64_launches, 1),
+                    "share_of_step": f64_ms / step_ms_local, "peak_source": dgemm_src,
+                    "flops_per_launch": "listed samples x 2 n^2"}
+        else:
+            # INT8-sliced exact applies: 28 (anchors, 7 levels) / 36 (checks, 8 levels) INT8 products of 2 n^2 ops per row
+            n_anch, n_chk = st1["anchors"] - st0["anchors"], st1["exact_checks"] - st0["exact_checks"]
+            int8_ops = 2.0 * nvar * nvar * (28.0 * n_anch + 36.0 * n_chk)
+            int8_ach = int8_ops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else 0.0
+            int8_peak = 2.0 * lp_peak
+            r_64 = {"bound": "tensor", "kernel": "oz_gemm2_kernel<.,.,128,OzEpiAnchor|OzEpiVerify> + k_oz_slice (FP64-accurate "
+                                                 "anchors x = Top w - c and exact KKT checks P z + q on tcgen05 kind::i8: "
+                                                 "error-free base-128 digit planes, exact INT32 accumulation)",
+                    "achieved": int8_ach, "fp64_equivalent": f64_ach, "peak": int8_peak, "unit": "TOP/s",
+                    "frac": int8_ach / int8_peak, "fp64_equivalent_vs_cublas_dgemm": f64_ach / best if best else None,
+                    "cublas_dgemm_tflops": best,
+                    "traffic": None, "launches": f64_launches, "avg_launch_ms": f64_ms / max(f64_launches, 1),
+                    "share_of_step": f64_ms / step_ms_local,
+                    "peak_source": "2 x the sustained 16-bit dense figure of MEASURED_PEAKS.json (INT8 dense is nominally twice "
+                                   "the 16-bit rate; the file carries no measured INT8 entry)",
+                    "flops_per_launch": "listed samples x 2 n^2 FP64-equivalent = x 28 (anchor) or 36 (check) INT8 products; "
+                                        "span includes the digit-plane slicing kernel"}
         roofline, roofline2 = (r_lp, r_64) if gemm_ms >= f64_ms else (r_64, r_lp)
 
     if rank == 0:

@@ -134,6 +134,9 @@ int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence);
  * iterates with skinny FP64 GEMMs over just those rows instead of full tensor-core passes
  * (rows < 0: automatic, max(48, B/16); 0: never). */
 int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
+/* Mixed mode only: which tensor pipe evaluates the FP64-exact operator applies (anchors x = Top w - c, KKT checks
+ * g = P z + q): 1 (default) = INT8 tcgen05 with error-free slicing (FP64-accurate, see oz_gemm.cuh), 0 = FP64 DMMA. */
+int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
 /* cumulative since create: out4 = {row-iterations, FP64 anchors, exact KKT checks, QPs solved} */
 int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
@@ -169,6 +172,10 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
  * A, Bt, C are dense row-major FP64 device matrices. */
 int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, int pair,
                        void* stream);   /* pair != 0: the CTA-pair (cta_group::2) kernel, else the one-CTA kernel */
+/* nnmpc_oz_gemm_test: the FP64-accurate GEMM on the INT8 tcgen05 tensor cores (error-free base-128 slicing of both
+ * operands, exact INT32 accumulation, 36 INT8 products), C[M x N] = A[M x K] Bt[N x K]^T; dense row-major FP64
+ * device matrices, K <= 32768. */
+int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, double* C, void* stream);
 /* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,
                   long long ldb, double* C, long long ldc, const int* rows, void* stream);

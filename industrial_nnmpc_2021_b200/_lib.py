@@ -44,6 +44,7 @@ SIGNATURES = {
     "nnmpc_sim_set_slots": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_set_cadence": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_set_tail_rows": (C.c_int, [vp, C.c_int]),
+    "nnmpc_sim_set_exact_gemm": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
                                 C.c_int, C.c_int, vp]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     "nnmpc_mlp_forward": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_mlp_forward_host": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_lp_gemm_test": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, vp, C.c_int, vp]),
+    "nnmpc_oz_gemm_test": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "nnmpc_gemm_tn": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp, C.c_longlong,
                                 vp, vp]),
 }

@@ -1,0 +1,243 @@
+// Host-side glue and fused epilogues of the INT8-sliced FP64-accurate GEMM (oz_gemm.cuh): the exact anchors
+// x = Top w - c and the exact KKT checks g = P z + q of the mixed-precision closed-loop engine, and the
+// self-test entry point.
+#include "oz_gemm.cuh"
+#include "oz.cuh"
+#include "lp.cuh"     // device_sm_count
+#include <cstdlib>
+#include <cstring>
+
+namespace nnmpc {
+
+constexpr int OZ_LMAX = 7;     // levels 0..7: 36 INT8 products, truncation (LMAX+1) K 2^(-7 (LMAX+1) - 2) ~ 1.2e-13 at K = 4480
+constexpr int OZ_NS = OZ_LMAX + 1;
+constexpr int OZ_LMAX_ANCHOR = 6;   // anchors (|Top| <= 1, result only steers the iteration; the check certifies): 28 products
+
+// kernel variant: 2 (default) = 128-column tiles, two level windows; 1 = 64-column tiles, one launch, just-in-time
+// operator slices; 0 = first-generation kernel (64 columns, double-buffered slice sets)
+static int oz_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNMPC_OZ_VARIANT");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
+  }
+  return v;
+}
+
+// ---- epilogues (one lane = one output row, CH consecutive columns per call) ---------------------
+struct OzEpiStore {
+  struct Params {
+    double* C;
+    long long ldc;
+  };
+  Params p;
+  long long pos;
+  __device__ explicit OzEpiStore(const Params& p_) : p(p_), pos(0) {}
+  __device__ void begin_row(int pos_, bool) { pos = pos_; }
+  __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+#pragma unroll
+    for (int k = 0; k < oz::CH; ++k)
+      if (col0 + k < N) p.C[pos * p.ldc + col0 + k] = v[k];
+  }
+  __device__ void end_row() {}
+};
+
+struct OzEpiAnchor {
+  struct Params {
+    double* X;
+    const double* C;
+    const int* rows;
+    int n;
+  };
+  Params p;
+  long long base;
+  __device__ explicit OzEpiAnchor(const Params& p_) : p(p_), base(0) {}
+  __device__ void begin_row(int pos, bool ok) { base = ok ? (long long)(p.rows ? p.rows[pos] : pos) * p.n : 0; }
+  __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+#pragma unroll
+    for (int k = 0; k < oz::CH; k += 2) {
+      const int col = col0 + k;
+      if (col + 1 < N) {
+        const double2 c = *reinterpret_cast<const double2*>(p.C + base + col);
+        *reinterpret_cast<double2*>(p.X + base + col) = make_double2(v[k] - c.x, v[k + 1] - c.y);
+      } else if (col < N) {
+        p.X[base + col] = v[k] - p.C[base + col];
+      }
+    }
+  }
+  __device__ void end_row() {}
+};
+
+struct OzEpiVerify {
+  struct Params {
+    const double* Z;
+    const double* Ql;
+    const double* lb;
+    const double* ub;
+    unsigned long long* kres;
+    double* G;        // nullable
+    const int* rows;
+    int n, nu;
+  };
+  Params p;
+  long long pr;
+  bool ok;
+  double rmax;
+  __device__ explicit OzEpiVerify(const Params& p_) : p(p_), pr(0), ok(false), rmax(0.0) {}
+  __device__ void begin_row(int pos, bool ok_) {
+    ok = ok_;
+    pr = ok ? (long long)(p.rows ? p.rows[pos] : pos) : 0;
+    rmax = 0.0;
+  }
+  __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+    const long long base = pr * p.n;
+    const double* lbr = p.lb + pr * p.nu;
+    const double* ubr = p.ub + pr * p.nu;
+#pragma unroll
+    for (int k = 0; k < oz::CH; ++k) {
+      const int col = col0 + k;
+      if (col < N) {
+        const int s = col % p.nu;
+        const double z = p.Z[base + col], g = v[k] + p.Ql[base + col];
+        if (p.G) p.G[base + col] = g;
+        double r = fabs(z - fmin(fmax(z - g, lbr[s]), ubr[s]));
+        if (!(r <= 1.7e308)) r = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
+        rmax = fmax(rmax, r);
+      }
+    }
+  }
+  __device__ void end_row() {
+    if (ok) atomicMax(p.kres + pr, (unsigned long long)__double_as_longlong(rmax));
+  }
+};
+
+// ---- host side ---------------------------------------------------------------------------------
+int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st) {
+  if (ncols > 32768) return set_error(NNMPC_ERR_BADARG, "oz_slice_operator: contraction length %d above 32768 (int32 accumulators)", ncols);
+  op->nrows = nrows; op->ncols = ncols;
+  op->ldb = ((long long)ncols + oz::BKB - 1) / oz::BKB * oz::BKB;
+  op->rows_pad = ((long long)nrows + 127) / 128 * 128;
+  const size_t bytes = (size_t)OZ_NS * op->rows_pad * op->ldb;
+  NNMPC_TRY(op->S.ensure(bytes));
+  NNMPC_TRY(op->escale.ensure((size_t)op->rows_pad));
+  NNMPC_CUDA(cudaMemsetAsync(op->S.p, 0, bytes, st));
+  NNMPC_CUDA(cudaMemsetAsync(op->escale.p, 0, (size_t)op->rows_pad * sizeof(double), st));
+  oz::k_oz_slice<OZ_NS><<<nrows, 256, 0, st>>>(nullptr, nullptr, T_dev, ncols, ncols, op->S.p, op->rows_pad, op->ldb,
+                                               op->escale.p);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  if (!oz::make_tmap_u8(&op->tm, op->S.p, OZ_NS * op->rows_pad, op->ldb, op->ldb, oz::BN))
+    return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the operator digit planes");
+  if (!oz::make_tmap_u8(&op->tm128, op->S.p, OZ_NS * op->rows_pad, op->ldb, op->ldb, 128))
+    return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the operator digit planes");
+  op->ready = true;
+  return 0;
+}
+
+int oz_rows_ensure(OzRows* r, long long cap, int ncols) {
+  const long long ldb = ((long long)ncols + oz::BKB - 1) / oz::BKB * oz::BKB;
+  const long long cap_pad = (cap + oz::BM - 1) / oz::BM * oz::BM;
+  if (cap_pad <= r->cap_pad && ldb == r->ldb && ncols == r->ncols) return 0;
+  const long long cp = cap_pad > r->cap_pad ? cap_pad : r->cap_pad;
+  const size_t bytes = (size_t)OZ_NS * cp * ldb;
+  NNMPC_TRY(r->S.ensure(bytes));
+  NNMPC_TRY(r->fscale.ensure((size_t)cp));
+  NNMPC_CUDA(cudaMemset(r->S.p, 0, bytes));      // the k-padding stays zero: the slicing kernel writes ncols bytes per row
+  NNMPC_CUDA(cudaMemset(r->fscale.p, 0, (size_t)cp * sizeof(double)));
+  if (!oz::make_tmap_u8(&r->tm, r->S.p, OZ_NS * cp, ldb, ldb, oz::BM))
+    return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the sample digit planes");
+  r->cap_pad = cp; r->ldb = ldb; r->ncols = ncols;
+  return 0;
+}
+
+static int oz_slice_rows(OzRows* r, const int* rows, const int* count, int max_rows, const double* src, long long ld_src,
+                         cudaStream_t st) {
+  oz::k_oz_slice<OZ_NS><<<max_rows, 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
+                                                  r->fscale.p);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static oz::OzShape oz_shape(const OzOperator* op, const OzRows* r, int max_rows, const int* count) {
+  oz::OzShape g{};
+  g.M = max_rows; g.N = op->nrows; g.KB = (int)(op->ldb / oz::BKB); g.m_dev = count;
+  g.a_rows_pad = r->cap_pad; g.b_rows_pad = op->rows_pad; g.fscale = r->fscale.p; g.escale = op->escale.p;
+  g.group_rows = 8;
+  return g;
+}
+
+// one FP64-accurate apply over the sliced rows: levels 0..LMAX through the selected kernel variant
+template <int LMAX, class Epi>
+static int oz_apply(const OzOperator* op, OzRows* r, int max_rows, const int* count, const typename Epi::Params& ep,
+                    int device, cudaStream_t st) {
+  const int sms = device_sm_count(device);
+  const oz::OzShape g = oz_shape(op, r, max_rows, count);
+  cudaError_t e;
+  const int var = oz_variant();
+  if (var == 0) {
+    e = oz::launch_oz_gemm<LMAX, Epi>(r->tm, op->tm, g, ep, sms, st);
+    count_launch();
+  } else if (var == 1) {
+    e = oz::launch_oz_gemm2<0, LMAX, 64, Epi>(r->tm, op->tm, oz::OzShape2{g, nullptr, 0, 0}, ep, sms, st);
+    count_launch();
+  } else {
+    NNMPC_TRY(r->partial.ensure((size_t)r->cap_pad * op->nrows));
+    e = oz::launch_oz_gemm2<4, LMAX, 128, OzEpiStore>(r->tm, op->tm128, oz::OzShape2{g, nullptr, 0, 1},
+                                                      OzEpiStore::Params{r->partial.p, op->nrows}, sms, st);
+    if (e == cudaSuccess)
+      e = oz::launch_oz_gemm2<0, 3, 128, Epi>(r->tm, op->tm128, oz::OzShape2{g, r->partial.p, op->nrows, 0}, ep, sms, st);
+    count_launch(2);
+  }
+  if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oz_anchor(const OzOperator* top, OzRows* r, const int* rows, const int* count, int max_rows, const double* W,
+              const double* C, double* X, int n, int device, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  if (!top->ready || top->ncols != n || r->ncols != n || max_rows > r->cap_pad)
+    return set_error(NNMPC_ERR_BADARG, "oz_anchor: operator / row planes not prepared for n = %d, %d rows", n, max_rows);
+  NNMPC_TRY(oz_slice_rows(r, rows, count, max_rows, W, n, st));
+  return oz_apply<OZ_LMAX_ANCHOR, OzEpiAnchor>(top, r, max_rows, count, OzEpiAnchor::Params{X, C, rows, n}, device, st);
+}
+
+int oz_verify(const OzOperator* P, OzRows* r, const int* rows, const int* count, int max_rows, const double* Z,
+              const double* Ql, const double* lb, const double* ub, unsigned long long* kres, double* G, int n, int nu,
+              int device, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  if (!P->ready || P->ncols != n || r->ncols != n || max_rows > r->cap_pad)
+    return set_error(NNMPC_ERR_BADARG, "oz_verify: operator / row planes not prepared for n = %d, %d rows", n, max_rows);
+  NNMPC_TRY(oz_slice_rows(r, rows, count, max_rows, Z, n, st));
+  return oz_apply<OZ_LMAX, OzEpiVerify>(P, r, max_rows, count, OzEpiVerify::Params{Z, Ql, lb, ub, kres, G, rows, n, nu},
+                                        device, st);
+}
+
+}  // namespace nnmpc
+
+using namespace nnmpc;
+
+extern "C" {
+
+// Self test of the INT8-sliced path:  C[M x N] = A[M x K] * Bt[N x K]^T, all FP64 device matrices (row-major, dense).
+int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, double* C, void* stream) {
+  if (!A || !Bt || !C || M <= 0 || N <= 0 || K <= 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_oz_gemm_test: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  NNMPC_CUDA(cudaGetDevice(&dev));
+  OzOperator op;
+  OzRows rows;
+  int rc = oz_slice_operator(Bt, N, K, &op, st);
+  if (rc == 0) rc = oz_rows_ensure(&rows, M, K);
+  if (rc == 0) rc = oz_slice_rows(&rows, nullptr, nullptr, M, A, K, st);
+  if (rc == 0) rc = oz_apply<OZ_LMAX, OzEpiStore>(&op, &rows, M, nullptr, OzEpiStore::Params{C, N}, dev, st);
+  if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess)
+    rc = set_error(NNMPC_ERR_CUDA, "oz_gemm failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaStreamSynchronize(st);
+  op.release();
+  rows.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// Host-visible interface of the INT8-sliced FP64-accurate GEMM (oz_gemm.cuh); compiled in oz.cu.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+#include "nnmpc_common.cuh"
+
+namespace nnmpc {
+
+// a shared FP64 operator (rows = output columns of the GEMM) cut into signed base-128 digit planes
+struct OzOperator {
+  int nrows = 0, ncols = 0;
+  long long ldb = 0;        // bytes per row of a plane (multiple of 128, zero padded)
+  long long rows_pad = 0;   // rows per plane (multiple of 128, zero padded)
+  DevBuf<int8_t> S;         // NS planes stacked: [(s * rows_pad + row) * ldb + k]
+  DevBuf<double> escale;    // per row: 2^e, max |row| <= 2^(e-1)
+  CUtensorMap tm;           // boxes of 64 operator rows
+  CUtensorMap tm128;        // boxes of 128 operator rows
+  bool ready = false;
+  void release() { S.release(); escale.release(); ready = false; }
+};
+
+// digit planes of up to cap sample rows (rewritten before every GEMM)
+struct OzRows {
+  long long cap_pad = 0;    // rows per plane (multiple of 128)
+  long long ldb = 0;
+  int ncols = 0;
+  DevBuf<int8_t> S;
+  DevBuf<double> fscale;    // per position: 2^f
+  DevBuf<double> partial;   // cap_pad x ncols: partial level sums between the two launches of the 128-column kernel
+  CUtensorMap tm;
+  void release() { S.release(); fscale.release(); partial.release(); cap_pad = 0; }
+};
+
+int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st);
+int oz_rows_ensure(OzRows* r, long long cap, int ncols);
+// x = Top w - c for the listed rows (W, C, X are B x n with the sample row as physical row)
+int oz_anchor(const OzOperator* top, OzRows* r, const int* rows, const int* count, int max_rows, const double* W,
+              const double* C, double* X, int n, int device, cudaStream_t st);
+// g = P z + q for the listed rows; per row ||z - clip(z - g)||_inf folded into kres (atomicMax of the bit pattern),
+// g itself into G when non-null
+int oz_verify(const OzOperator* P, OzRows* r, const int* rows, const int* count, int max_rows, const double* Z,
+              const double* Ql, const double* lb, const double* ub, unsigned long long* kres, double* G, int n, int nu,
+              int device, cudaStream_t st);
+
+}  // namespace nnmpc

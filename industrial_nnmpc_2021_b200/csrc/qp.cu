@@ -352,6 +352,8 @@ int nnmpc_qp_destroy(nnmpc_qp_t* h) {
   h->hx0.release(); h->hlb.release(); h->hub.release(); h->hu.release(); h->hcost.release(); h->hkkt.release();
   h->hiters.release();
   h->lpop.release();
+  h->ozP.release();
+  h->ozTop.release();
   delete h;
   return 0;
 }

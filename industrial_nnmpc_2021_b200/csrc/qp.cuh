@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include "nnmpc_common.cuh"
 #include "gemm_f64.cuh"
+#include "oz.cuh"
 
 namespace nnmpc {
 
@@ -244,6 +245,7 @@ struct nnmpc_qp {
   double top_max;                     // max |Top|
   double* rinv = nullptr;             // device n: 1 / rho (nnmpc_qp_set_penalty), null until set
   nnmpc::LpOperator lpop;             // fp16 split of Top, built on first use by the mixed-precision iteration
+  nnmpc::OzOperator ozP, ozTop;       // INT8 digit planes of P and Top (FP64-accurate tensor-core applies), built on first use
   // scratch, sized for `cap` samples
   long long cap;
   int nslots_cap;

@@ -57,6 +57,8 @@ struct nnmpc_sim {
   int mixed;
   int tail_rows;                    // live rows at or below which the mixed mode finishes in FP64 (-1 = auto)
   nnmpc::LpState lps;
+  int exact_oz;                     // mixed mode: anchors and exact checks on the INT8 tensor cores (oz_gemm.cuh) instead of DMMA
+  nnmpc::OzRows ozr;
   nnmpc::DevBuf<int> lp_layout;     // 2 x cap operand layouts (position -> row) + 2 x cap inverses (row -> position)
   unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps;   // since create (host)
@@ -532,7 +534,13 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       return set_error(NNMPC_ERR_BADARG, "mixed precision needs the ADMM penalty vector: call nnmpc_qp_set_penalty first");
     if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
     NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n));
+    if (h->exact_oz) {
+      if (!q->ozP.ready) NNMPC_TRY(oz_slice_operator(q->P, n, n, &q->ozP, st));
+      if (!q->ozTop.ready) NNMPC_TRY(oz_slice_operator(q->Top, n, n, &q->ozTop, st));
+      NNMPC_TRY(oz_rows_ensure(&h->ozr, h->cap, n));
+    }
   }
+  const bool oz = mixed && h->exact_oz;
   NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
@@ -617,7 +625,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       if (full) {
         const bool prof64 = prof_begin(&span64, st);
         NNMPC_TRY(lp_anchor_prep(e.l_anchor, cnt, B, h->V.p, q->W0.p, &h->lps, h->lb.p, h->ub.p, nu, st));
-        NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
+        if (oz) NNMPC_TRY(oz_anchor(&q->ozTop, &h->ozr, e.l_anchor, cnt, B, q->W0.p, q->C.p, h->lps.X.p, n, h->device, st));
+        else NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
         NNMPC_TRY(lp_dr_first(e.l_anchor, cnt, B, &h->lps, h->V.p, q->W0.p, h->lb.p, h->ub.p, e.state, e.it, SLOT_ITER,
                               nu, q->alpha, pos_r, st));
         if (prof64) prof_end(span64, st, 0.0, 1, 1);
@@ -664,7 +673,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu, mixed ? h->lps.Wl.p : nullptr};
       ProfSpan span64;
       const bool prof64 = mixed && prof_begin(&span64, st);
-      NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
+      if (oz) NNMPC_TRY(oz_verify(&q->ozP, &h->ozr, e.l_cand, e.counts + N_CAND, B, h->Z.p, q->Ql.p, h->lb.p, h->ub.p,
+                                  e.kres, h->lps.Wl.p, n, nu, h->device, st));
+      else NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
       if (prof64) prof_end(span64, st, 0.0, 1, 1);
     }
     k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
@@ -754,6 +765,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->tail_rows = -1;
   h->slot_cap = 8192;
   h->cadence = 4;
+  h->exact_oz = 1;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
@@ -786,6 +798,7 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   cudaFree(h->stats);
   cudaFreeHost(h->pin);
   h->lps.release();
+  h->ozr.release();
   h->lp_layout.release();
   for (int i = 0; i < POLL_RING; ++i) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
@@ -826,6 +839,13 @@ int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence) {
 int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_tail_rows: null handle");
   h->tail_rows = rows < 0 ? -1 : rows;
+  return 0;
+}
+
+int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_exact_gemm: null handle");
+  if (mode != 0 && mode != 1) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_exact_gemm: mode must be 0 (DMMA) or 1 (INT8 slices)");
+  h->exact_oz = mode;
   return 0;
 }
 

@@ -573,6 +573,9 @@ class ClosedLoopEngine:
             self.set_slots(slots)
         if os.environ.get("NNMPC_CADENCE"):
             _lib.check(L.nnmpc_sim_set_cadence(self._handle, int(os.environ["NNMPC_CADENCE"])), "nnmpc_sim_set_cadence")
+        if os.environ.get("NNMPC_EXACT_GEMM"):      # "dmma" = FP64 tensor cores, "int8" (default) = sliced INT8 tcgen05
+            mode = {"dmma": 0, "int8": 1}[os.environ["NNMPC_EXACT_GEMM"]]
+            _lib.check(L.nnmpc_sim_set_exact_gemm(self._handle, mode), "nnmpc_sim_set_exact_gemm")
         tail_rows = os.environ.get("NNMPC_TAIL_ROWS") if tail_rows is None else tail_rows
         if tail_rows is not None:     # mixed mode: live rows at or below which a call finishes in FP64 (-1 = automatic)
             _lib.check(L.nnmpc_sim_set_tail_rows(self._handle, int(tail_rows)), "nnmpc_sim_set_tail_rows")

@@ -243,6 +243,30 @@ def test_lp_split_gemm_matches_fp64(torch_cuda, M, n, pair):
     assert np.all(np.isfinite(err)) and np.all(err <= bound), float((err / bound).max())
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 128), (1, 8, 4), (37, 100, 540), (300, 540, 540), (257, 4480, 4480),
+                                   (2200, 1000, 1000)])
+def test_oz_int8_gemm_is_fp64_accurate(torch_cuda, M, N, K):
+    """C = A Bt' on the INT8 tensor cores (error-free base-128 slicing, exact INT32 accumulation) against FP64
+    NumPy.  Worst-case bound per element, with 2^f, 2^e the row scales (2^(f+e) < 16 max|a_row| max|b_row|):
+    truncation 8 K 2^-58 2^(f+e) plus the FP64 fold of the levels K 2^-55 2^(f+e) - i.e. K 2^-50 max|a| max|b|,
+    the worst-case rounding level of an FP64 dot product of that length."""
+    torch = torch_cuda
+    from industrial_nnmpc_2021_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(M * 7 + N + K)
+    A = rng.standard_normal((M, K)) * np.exp(rng.uniform(-6, 2, (M, 1)))
+    Bt = rng.standard_normal((N, K)) * np.exp(rng.uniform(-8, 0, (N, K))) * np.exp(rng.uniform(-3, 3, (N, 1)))
+    At, Btt = torch.tensor(A, device="cuda"), torch.tensor(Bt, device="cuda")
+    Cd = torch.full((M, N), np.nan, dtype=torch.float64, device="cuda")
+    _lib.check(L.nnmpc_oz_gemm_test(M, N, K, _lib.dptr(At), _lib.dptr(Btt), _lib.dptr(Cd), None), "nnmpc_oz_gemm_test")
+    torch.cuda.synchronize()
+    ref = A @ Bt.T
+    scale = np.abs(A).max(axis=1, keepdims=True) * np.abs(Bt).max(axis=1)[None, :]
+    bound = K * 2.0 ** -50 * scale + 4 * K * 2.0 ** -53 * (np.abs(A) @ np.abs(Bt).T)
+    err = np.abs(Cd.cpu().numpy() - ref)
+    assert np.all(np.isfinite(err)) and np.all(err <= bound), float((err / bound).max())
+
+
 # ------------------------------------------------------------------------------------ closed loop
 @pytest.fixture(params=["f64", "mixed", "mixed-notail"])
 def precision(request, monkeypatch):
