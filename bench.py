@@ -247,7 +247,12 @@ def run_native(args):
     t_setup = time.perf_counter()
     ts = LinearMPCController.setup_target_selector(p.A, p.B, p.C, p.H, p.Bd, p.Cd, p.usp, p.Qs, p.Rs, p.ulb, p.uub,
                                                    device=dev)
-    reg = LinearMPCController.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub, device=dev)
+    solver_kw = {}
+    if args.alpha is not None:
+        solver_kw["alpha"] = args.alpha
+    if args.rho_scale is not None:
+        solver_kw["rho_scale"] = args.rho_scale
+    reg = LinearMPCController.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub, device=dev, **solver_kw)
     eng = ClosedLoopEngine(reg, ts, p.A, p.B, p.Bd, precision=args.precision, slots=args.slots)
     t_setup = time.perf_counter() - t_setup
     n, nx, nu, ny, nd = p.N * p.Nu, p.Nx, p.Nu, p.Ny, p.Nd
@@ -467,6 +472,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"],
                     help="regulator-QP iteration arithmetic: tcgen05 fp16 increments + FP64 anchors, or all FP64 DMMA")
+    ap.add_argument("--alpha", type=float, default=None, help="Douglas-Rachford relaxation (solver default 1.8)")
+    ap.add_argument("--rho-scale", type=float, default=None, help="multiplier of the default ADMM penalty (solver default 1)")
     ap.add_argument("--max-iter", type=int, default=3000, help="per-QP iteration cap (a hit rejects the number)")
     args = ap.parse_args()
     if args.impl == "reference":

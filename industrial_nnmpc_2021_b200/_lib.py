@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnnmpc.so")
+if os.environ.get("NNMPC_LIB_PATH"):      # experimental build variants (build.py --out ...)
+    LIB_PATH = os.environ["NNMPC_LIB_PATH"]
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -33,17 +33,22 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Default: csrc/libnnmpc.so.  `out` + `defines` build an experimental variant next to it (e.g.
+    defines=("NNMPC_EPI_WARPS=16",), out="libnnmpc_e16.so"), loaded when NNMPC_LIB_PATH points at it."""
+    variant = out is not None
+    lib = os.path.join(CSRC, out) if variant else LIB
+    if not variant and not force and not _stale():
         return LIB
     nvcc = find_nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + [f"-D{d}" for d in defines]
     if verbose:
         flags += ["-Xptxas", "-v"]
     objs = []
     procs = []
+    tag = ("." + os.path.splitext(out)[0]) if variant else ""
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        o = os.path.join(CSRC, s.replace(".cu", tag + ".o"))
         objs.append(o)
         cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -54,10 +59,14 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    kw = {}
+    if "--out" in sys.argv:
+        kw["out"] = sys.argv[sys.argv.index("--out") + 1]
+        kw["defines"] = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, **kw))

@@ -38,6 +38,29 @@ __device__ __forceinline__ __half quantise_dw(double dw, double s, double inv_s,
   return q;
 }
 
+// The tensor-core epilogue is bound by instruction issue (8 warps, ~100 instructions per element before this
+// form): fmin/fmax on doubles expand into DSETP + four selects + NaN fix-ups each, so the epilogue clips with
+// compare/select (a NaN stays a NaN and is caught by the residual check) and clamps the quantised value in fp32.
+__device__ __forceinline__ double clip_sel(double v, double l, double u) {
+  const double r = v < l ? l : v;
+  return r > u ? u : r;
+}
+__device__ __forceinline__ void dr_delta_fast(double& x, double& v, double z0, double wl, double l, double u, double alpha,
+                                              double& dw, double& dabs) {
+  const double d = x - z0;
+  v += alpha * d;
+  const double z1 = clip_sel(v, l, u);
+  dw = (2.0 * z1 - v) - wl;
+  dabs = fabs(d);
+}
+__device__ __forceinline__ __half quantise_dw_fast(double dw, double s, double inv_s, float& e) {
+  float tf = (float)(dw * s);
+  tf = fminf(fmaxf(tf, -60000.f), 60000.f);      // saturate: the residual e carries what did not fit
+  const __half q = __float2half_rn(tf);          // any rounding will do: e is formed from the q actually sent
+  e = (float)(dw - (double)__half2float(q) * inv_s);
+  return q;
+}
+
 // ---- epilogue of the tensor-core pass: the whole iteration on the accumulator registers ----------
 // Warp-collective (see lp_gemm.cuh): the warp owns 32 rows; TMEM hands lane l the 16 accumulators of row l, the
 // block is transposed through shared memory, and lane (rg = l / 4, cp = l % 4) then updates rows rg, rg + 8,
@@ -93,13 +116,14 @@ struct EpiDelta {
                                        const lp::EpiRowInfo& ri, __half2& q, double& dm) {
     x.x += (double)a0 * ri.inv_in;
     x.y += (double)a1 * ri.inv_in;
-    const double wl0 = (2.0 * clipd(v.x, l.x, u.x) - v.x) - (double)e.x;
-    const double wl1 = (2.0 * clipd(v.y, l.y, u.y) - v.y) - (double)e.y;
+    const double z00 = clip_sel(v.x, l.x, u.x), z01 = clip_sel(v.y, l.y, u.y);
+    const double wl0 = (2.0 * z00 - v.x) - (double)e.x;
+    const double wl1 = (2.0 * z01 - v.y) - (double)e.y;
     double dw0, dw1, d0, d1;
-    dr_delta_one(x.x, v.x, wl0, l.x, u.x, p.alpha, dw0, d0);
-    dr_delta_one(x.y, v.y, wl1, l.y, u.y, p.alpha, dw1, d1);
-    const __half q0 = quantise_dw(dw0, ri.s_out, ri.inv_out, e.x);
-    const __half q1 = quantise_dw(dw1, ri.s_out, ri.inv_out, e.y);
+    dr_delta_fast(x.x, v.x, z00, wl0, l.x, u.x, p.alpha, dw0, d0);
+    dr_delta_fast(x.y, v.y, z01, wl1, l.y, u.y, p.alpha, dw1, d1);
+    const __half q0 = quantise_dw_fast(dw0, ri.s_out, ri.inv_out, e.x);
+    const __half q1 = quantise_dw_fast(dw1, ri.s_out, ri.inv_out, e.y);
     q = __halves2half2(q0, q1);
     const double a = (d0 <= d1) ? d1 : d0;       // NaN propagates
     dm = (a <= dm) ? dm : a;
@@ -110,7 +134,11 @@ struct EpiDelta {
 #pragma unroll
     for (int c = 0; c < lp::CW; ++c) sm->stg[c * 33 + lane] = __uint_as_float(acc[c]);
     __syncwarp();
-    const bool fast = (p.nu & 7) == 0;                         // stage width a multiple of 8: no wrap inside a pair run
+    // stage width a multiple of the chunk width: the chunk (col0 is a multiple of CW) lies inside one stage, so the
+    // bound index of the lane's first pair is taken once and the others are constant offsets
+    const bool fast = (p.nu % lp::CW) == 0;
+    const int cbase = col0 + 2 * cp;                           // this lane's first column; n is even: a pair is inside when its first column is
+    const int kbase = cbase % p.nu;
     double2 x[4 * NP], v[4 * NP];
     float2 e[4 * NP];
     // all state loads of the step first (streaming: read once per pass)
@@ -118,14 +146,13 @@ struct EpiDelta {
     for (int i = 0; i < 4; ++i) {
       const int row = sm->info[rg + 8 * i].row;
       if (row >= 0) {
-        const long long base = (long long)row * p.n;
+        const long long base = (long long)row * p.n + cbase;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          const int c = col0 + 8 * j + 2 * cp;                 // n is even: the pair is inside when its first column is
-          if (c < N) {
-            x[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.X + base + c));
-            v[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.V + base + c));
-            e[NP * i + j] = __ldcs(reinterpret_cast<const float2*>(p.E + base + c));
+          if (cbase + 8 * j < N) {
+            x[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.X + base + 8 * j));
+            v[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.V + base + 8 * j));
+            e[NP * i + j] = __ldcs(reinterpret_cast<const float2*>(p.E + base + 8 * j));
           }
         }
       }
@@ -134,32 +161,32 @@ struct EpiDelta {
     for (int i = 0; i < 4; ++i) {
       const int r = rg + 8 * i;
       const lp::EpiRowInfo ri = sm->info[r];
-      if (ri.row < 0) continue;
-      const long long base = (long long)ri.row * p.n;
-      const double* lbr = p.lb + (long long)ri.row * p.nu;
-      const double* ubr = p.ub + (long long)ri.row * p.nu;
-      __half* dn = p.Dn + (long long)ri.pw * p.ldd;
+      if (ri.row >= 0) {
+        const long long base = (long long)ri.row * p.n + cbase;
+        const double* lbr = p.lb + (long long)ri.row * p.nu;
+        const double* ubr = p.ub + (long long)ri.row * p.nu;
+        __half* dn = p.Dn + (long long)ri.pw * p.ldd + cbase;
 #pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const int c = col0 + 8 * j + 2 * cp;
-        if (c < N) {
-          const int k = c % p.nu;
-          double2 l, u;
-          if (fast) {
-            l = *reinterpret_cast<const double2*>(lbr + k);
-            u = *reinterpret_cast<const double2*>(ubr + k);
-          } else {
-            const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
-            l = make_double2(lbr[k], lbr[k1]);
-            u = make_double2(ubr[k], ubr[k1]);
+        for (int j = 0; j < NP; ++j) {
+          if (cbase + 8 * j < N) {
+            double2 l, u;
+            if (fast) {
+              l = *reinterpret_cast<const double2*>(lbr + kbase + 8 * j);
+              u = *reinterpret_cast<const double2*>(ubr + kbase + 8 * j);
+            } else {
+              const int k = (cbase + 8 * j) % p.nu;
+              const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
+              l = make_double2(lbr[k], lbr[k1]);
+              u = make_double2(ubr[k], ubr[k1]);
+            }
+            __half2 q;
+            pair(x[NP * i + j], v[NP * i + j], e[NP * i + j], sm->stg[(8 * j + 2 * cp) * 33 + r],
+                 sm->stg[(8 * j + 2 * cp + 1) * 33 + r], l, u, ri, q, dmax[i]);
+            __stcs(reinterpret_cast<double2*>(p.X + base + 8 * j), x[NP * i + j]);
+            __stcs(reinterpret_cast<double2*>(p.V + base + 8 * j), v[NP * i + j]);
+            __stcs(reinterpret_cast<float2*>(p.E + base + 8 * j), e[NP * i + j]);
+            *reinterpret_cast<__half2*>(dn + 8 * j) = q;
           }
-          __half2 q;
-          pair(x[NP * i + j], v[NP * i + j], e[NP * i + j], sm->stg[(8 * j + 2 * cp) * 33 + r],
-               sm->stg[(8 * j + 2 * cp + 1) * 33 + r], l, u, ri, q, dmax[i]);
-          __stcs(reinterpret_cast<double2*>(p.X + base + c), x[NP * i + j]);
-          __stcs(reinterpret_cast<double2*>(p.V + base + c), v[NP * i + j]);
-          __stcs(reinterpret_cast<float2*>(p.E + base + c), e[NP * i + j]);
-          *reinterpret_cast<__half2*>(dn + c) = q;
         }
       }
     }

@@ -240,4 +240,43 @@ int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
   return rc;
 }
 
+// Probe (tools/probes/oz_rates.py, not on the product path): time `reps` applies over already sliced operands.
+// ms[0] = sample slicing kernel, ms[1] = GEMM launches (the variant NNMPC_OZ_VARIANT selects), both per apply.
+int nnmpc_oz_gemm_bench(int M, int N, int K, const double* A, const double* Bt, double* C, int reps, float* ms) {
+  if (!A || !Bt || !C || !ms || M <= 0 || N <= 0 || K <= 0 || reps <= 0)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_oz_gemm_bench: bad argument");
+  cudaStream_t st = 0;
+  int dev = 0;
+  NNMPC_CUDA(cudaGetDevice(&dev));
+  OzOperator op;
+  OzRows rows;
+  int rc = oz_slice_operator(Bt, N, K, &op, st);
+  if (rc == 0) rc = oz_rows_ensure(&rows, M, K);
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int w = 0; w < 2 && rc == 0; ++w) {
+    rc = oz_slice_rows(&rows, nullptr, nullptr, M, A, K, st);
+    if (rc == 0) rc = oz_apply<OZ_LMAX, OzEpiStore>(&op, &rows, M, nullptr, OzEpiStore::Params{C, N}, dev, st);
+  }
+  if (rc == 0) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && rc == 0; ++i) rc = oz_slice_rows(&rows, nullptr, nullptr, M, A, K, st);
+    cudaEventRecord(e1, st);
+    for (int i = 0; i < reps && rc == 0; ++i)
+      rc = oz_apply<OZ_LMAX, OzEpiStore>(&op, &rows, M, nullptr, OzEpiStore::Params{C, N}, dev, st);
+    cudaEventRecord(e2, st);
+    if (cudaEventSynchronize(e2) != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "oz bench failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == 0) {
+      cudaEventElapsedTime(&ms[0], e0, e1);
+      cudaEventElapsedTime(&ms[1], e1, e2);
+      ms[0] /= reps; ms[1] /= reps;
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaStreamSynchronize(st);
+  op.release();
+  rows.release();
+  return rc;
+}
+
 }  // extern "C"

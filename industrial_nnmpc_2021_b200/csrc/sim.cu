@@ -151,42 +151,94 @@ struct EngineArrays {
   int tail_rows;
 };
 
+// exclusive prefix of a per-thread count over one 1024-thread block; total to every thread
+__device__ int block_excl_scan(int c, int& total_out) {
+  __shared__ int warp_tot[32];
+  __shared__ int total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_tot[lane] = w;   // inclusive over warps
+    if (lane == 31) total = w;
+  }
+  __syncthreads();
+  const int excl = v - c + (warp ? warp_tot[warp - 1] : 0);
+  total_out = total;
+  __syncthreads();
+  return excl;
+}
+
 // after an iteration: bump iteration counters, pick the rows worth an exact KKT check
 // (append: candidates of earlier passes are still waiting for their exact check - the FP64 phases of the mixed
-//  mode run every `cadence`-th loop - so the list grows instead of starting over)
+//  mode run every `cadence`-th loop - so the list grows instead of starting over).
+// Four consecutive list entries per thread and round: the dependent loads of a row (list -> state -> residual)
+// overlap across the four, and the candidate list keeps the order of the live list.
 __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int append, int full) {
+  constexpr int RPT = 4;
   const int na = e.counts[N_ACTIVE];
   int base = append ? e.counts[N_CAND] : 0;
   int iterated = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < na; i0 += 1024) {
-    const int i = i0 + threadIdx.x;
-    bool cand = false;
-    int s = 0;
-    const bool live = i < na && e.state[e.l_active[i]] == SLOT_ITER;   // rows waiting for an FP64 phase did not iterate
-    iterated += __syncthreads_count(live);
-    if (live) {
-      s = e.l_active[i];
-      const int it = e.it[s] + 1;
-      e.it[s] = it;
-      const double d = __longlong_as_double((long long)e.dres[s]);
-      e.dres[s] = 0ull;
-      if (e.mixed) {   // the operand written by this pass was quantised with sc_out; pick the next scale from ||d||
-        e.sc_in[s] = e.sc_out[s];
-        e.sc_out[s] = pow2_scale(3.0 * e.alpha * d);
-      }
-      cand = (e.kappa[s] * d <= tol) || it >= max_iter;
-      if (cand) {
-        e.state[s] = SLOT_CAND;
-        e.dtrig[s] = d;
-        e.kres[s] = 0ull;
+  for (int i0 = 0; i0 < na; i0 += 1024 * RPT) {
+    int s[RPT];
+    bool live[RPT], cand[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int i = i0 + threadIdx.x * RPT + r;
+      s[r] = i < na ? e.l_active[i] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) live[r] = s[r] >= 0 && e.state[s[r]] == SLOT_ITER;   // rows waiting for an exact phase did not iterate
+    int nc = 0;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      cand[r] = false;
+      if (live[r]) {
+        const int row = s[r];
+        ++iterated;
+        const int it = e.it[row] + 1;
+        e.it[row] = it;
+        const double d = __longlong_as_double((long long)e.dres[row]);
+        e.dres[row] = 0ull;
+        if (e.mixed) {   // the operand written by this pass was quantised with sc_out; pick the next scale from ||d||
+          e.sc_in[row] = e.sc_out[row];
+          e.sc_out[row] = pow2_scale(3.0 * e.alpha * d);
+        }
+        cand[r] = (e.kappa[row] * d <= tol) || it >= max_iter;
+        if (cand[r]) {
+          e.state[row] = SLOT_CAND;
+          e.dtrig[row] = d;
+          e.kres[row] = 0ull;
+          ++nc;
+        }
       }
     }
-    base = block_append(cand, s, e.l_cand, base);
+    int total;
+    int off = base + block_excl_scan(nc, total);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+      if (cand[r]) e.l_cand[off++] = s[r];
+    base += total;
   }
+  // block-wide count of the rows that iterated
+  int tot_it;
+  block_excl_scan(iterated, tot_it);
   if (threadIdx.x == 0) {
     e.counts[N_CAND] = base;
-    *e.rowiters += (unsigned long long)iterated;
+    *e.rowiters += (unsigned long long)tot_it;
     if (e.mixed && full) e.stats[0] += (unsigned long long)e.counts[E_ANCHOR];   // anchors served at the top of this loop
   }
 }
