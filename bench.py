@@ -306,7 +306,9 @@ def run_native(args):
         barrier()
     ms_dev = maxrank(ev0.elapsed_time(ev1))
     launches = L.nnmpc_launch_count() - launches0
-    (gemm_ms, gemm_flops, gemm_launches), (f64_ms, f64_flops, f64_launches) = _lib.prof_read2(reset=True)
+    chans = _lib.prof_readn(4, reset=True)
+    (gemm_ms, gemm_flops, gemm_launches), (f64_ms, f64_flops, f64_launches) = chans[0], chans[1]
+    tail_ms, rest_ms = chans[2][0], chans[3][0]
     _lib.prof_enable(False)
     st1 = eng.stats()
     kkt_max, it_sum, it_max = float(kkt_acc), int(it_sum), int(it_acc)
@@ -446,6 +448,11 @@ def run_native(args):
                                    for k in ("row_iterations", "anchors", "exact_checks")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K, "kkt_max": e2e_kkt},
+            "time_breakdown": {"unit": "share of the timed region (CUDA events on the launching stream, rank 0)",
+                               "iteration_passes": gemm_ms / step_ms_local, "exact_anchors_and_checks": f64_ms / step_ms_local,
+                               "fp64_tail_iterations": tail_ms / step_ms_local,
+                               "plant_target_qbuild_lists": rest_ms / step_ms_local,
+                               "other": 1.0 - (gemm_ms + f64_ms + tail_ms + rest_ms) / step_ms_local},
             "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup, "gather": gather,
         }
         print(json.dumps(line), flush=True)

@@ -50,6 +50,8 @@ int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset);
 /* Same with two channels (arrays of 2): [0] the iteration passes (FP64 DMMA GEMM, or the tcgen05 pass
  * of the mixed-precision mode), [1] the FP64 anchor / exact-check GEMMs of the mixed-precision mode. */
 int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset);
+/* up to 4 channels: 0 iteration passes, 1 exact anchors / KKT checks, 2 FP64 tail iterations, 3 rest of a full engine loop */
+int nnmpc_prof_readn(int nchan, double* ms, double* flops, long long* launches, int reset);
 
 /* ---- regulator QP:  DenseQPRegulator (lib/linearMPC.py:321-517) -------------------------------
  *   min_u 1/2 u'Pu + (tq x0)'u   s.t.  lb <= u_k <= ub  for every stage k     (box path, :481)

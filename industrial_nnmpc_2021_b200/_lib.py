@@ -29,6 +29,7 @@ SIGNATURES = {
     "nnmpc_prof_enable": (C.c_int, [C.c_int]),
     "nnmpc_prof_read": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "nnmpc_prof_read2": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
+    "nnmpc_prof_readn": (C.c_int, [C.c_int, c_double_p, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "nnmpc_qp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                   C.c_double, C.c_int]),
     "nnmpc_qp_set_penalty": (C.c_int, [vp, vp]),
@@ -134,6 +135,14 @@ def prof_read2(reset=True):
     ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
     check(lib().nnmpc_prof_read2(ms, fl, n, int(bool(reset))), "nnmpc_prof_read2")
     return [(ms[i], fl[i], n[i]) for i in range(2)]
+
+
+def prof_readn(nchan=4, reset=True):
+    """[(ms, flops, launches)] per channel: 0 iteration passes, 1 exact anchors / KKT checks, 2 FP64 tail
+    iterations, 3 the rest of a full engine loop."""
+    ms, fl, n = (C.c_double * nchan)(), (C.c_double * nchan)(), (C.c_longlong * nchan)()
+    check(lib().nnmpc_prof_readn(nchan, ms, fl, n, int(bool(reset))), "nnmpc_prof_readn")
+    return [(ms[i], fl[i], n[i]) for i in range(nchan)]
 
 
 PRECISION = {"f64": 0, "mixed": 1}

@@ -30,11 +30,12 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof_spans;   // recorded since the last reset
 static std::vector<ProfSpan> g_prof_pool;    // events to reuse
-static double g_prof_extra_flops[2] = {0.0, 0.0};
+constexpr int NNMPC_PROF_CHANNELS = 4;
+static double g_prof_extra_flops[NNMPC_PROF_CHANNELS] = {};
 
 void prof_add_flops(double flops, int chan) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (g_prof_on) g_prof_extra_flops[chan & 1] += flops;
+  if (g_prof_on) g_prof_extra_flops[chan & (NNMPC_PROF_CHANNELS - 1)] += flops;
 }
 
 bool prof_begin(ProfSpan* sp, cudaStream_t st) {
@@ -240,20 +241,25 @@ int nnmpc_prof_enable(int on) {
   return 0;
 }
 
-// ms/flops/launches: arrays of 2 (channel 0 = iteration passes, channel 1 = FP64 anchors and exact checks)
-int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset) {
+// ms/flops/launches: arrays of nchan <= 4.  channel 0 = iteration passes, 1 = exact anchors and KKT checks of the
+// mixed mode, 2 = FP64 tail iterations of the mixed mode (few live rows), 3 = the rest of a full engine loop
+// (plant step, target selector, q-build, list kernels)
+int nnmpc_prof_readn(int nchan, double* ms, double* flops, long long* launches, int reset) {
+  if (nchan < 1 || nchan > NNMPC_PROF_CHANNELS) return set_error(NNMPC_ERR_BADARG, "nnmpc_prof_readn: 1..4 channels");
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double t[2] = {0.0, 0.0}, f[2] = {g_prof_extra_flops[0], g_prof_extra_flops[1]};
-  long long l[2] = {0, 0};
+  double t[NNMPC_PROF_CHANNELS] = {}, f[NNMPC_PROF_CHANNELS] = {};
+  long long l[NNMPC_PROF_CHANNELS] = {};
+  for (int c = 0; c < NNMPC_PROF_CHANNELS; ++c) f[c] = g_prof_extra_flops[c];
   for (const ProfSpan& sp : g_prof_spans) {
     float e = 0.f;
     if (cudaEventSynchronize(sp.b) != cudaSuccess || cudaEventElapsedTime(&e, sp.a, sp.b) != cudaSuccess)
       return set_error(NNMPC_ERR_CUDA, "nnmpc_prof_read: %s", cudaGetErrorString(cudaGetLastError()));
-    t[sp.chan] += e;
-    f[sp.chan] += sp.flops;
-    l[sp.chan] += sp.launches;
+    const int c = sp.chan & (NNMPC_PROF_CHANNELS - 1);
+    t[c] += e;
+    f[c] += sp.flops;
+    l[c] += sp.launches;
   }
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < nchan; ++c) {
     if (ms) ms[c] = t[c];
     if (flops) flops[c] = f[c];
     if (launches) launches[c] = l[c];
@@ -261,9 +267,13 @@ int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset) 
   if (reset) {
     for (const ProfSpan& sp : g_prof_spans) g_prof_pool.push_back(sp);
     g_prof_spans.clear();
-    g_prof_extra_flops[0] = g_prof_extra_flops[1] = 0.0;
+    for (int c = 0; c < NNMPC_PROF_CHANNELS; ++c) g_prof_extra_flops[c] = 0.0;
   }
   return 0;
+}
+
+int nnmpc_prof_read2(double* ms, double* flops, long long* launches, int reset) {
+  return nnmpc_prof_readn(2, ms, flops, launches, reset);
 }
 
 int nnmpc_prof_read(double* ms, double* flops, long long* launches, int reset) {

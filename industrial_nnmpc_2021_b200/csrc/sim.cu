@@ -690,15 +690,15 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
                            SLOT_ITER, e.dres, nu, q->alpha, h->device, st));
       if (prof) prof_end(span, st, 0.0, 1);
       // 1c. tail: with few live rows left the same update runs as skinny FP64 GEMMs (counts[E_TAIL] rows, else 0)
+      const bool prof64b = prof_begin(&span64, st);
       k_tail_prep<<<B, 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
       count_launch();
       GemmOperands gi{};
       gi.A = q->W0.p; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
       gi.N = n; gi.K = n; gi.rows = e.l_active; gi.m_count = e.counts + E_TAIL;
       EpiAdmm::Params ept{h->V.p, q->C.p, q->W1.p, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres};
-      const bool prof64b = prof_begin(&span64, st);
       NNMPC_TRY(gemm_by_count<EpiAdmm>(gi, ept, st));
-      if (prof64b) prof_end(span64, st, 0.0, 1, 1);
+      if (prof64b) prof_end(span64, st, 0.0, 1, 2);
     } else {
       GemmOperands gi{};
       gi.A = Wc; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = e.l_active;
@@ -730,6 +730,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       else NNMPC_TRY(gemm_by_count<EpiVerifyMax>(gv, ev, st));
       if (prof64) prof_end(span64, st, 0.0, 1, 1);
     }
+    ProfSpan span_rest;
+    const bool prof_rest = mixed && prof_begin(&span_rest, st);
     k_retire<<<1, 1024, 0, st>>>(e, tol, max_iter, T, oiters, okkt, h->kappa_max);
     if (mixed) {
       // a failed exact check re-anchors the fp16 path from its own gradient (no FP64 anchor GEMM): x := z exactly
@@ -757,6 +759,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
                                     uprev_io, h->us_prev.p, h->kappa.p, h->kappa0, nx, nu);
     count_launch(2);
     NNMPC_TRY(renew(0));
+    if (prof_rest) prof_end(span_rest, st, 0.0, 1, 3);
     // poll the finished counter with a two-loop lag (the GPU never waits for the host)
     const int slot = (int)(polls % POLL_RING);
     NNMPC_CUDA(cudaMemcpyAsync(h->pin + slot * N_COUNTERS, h->counts, N_COUNTERS * sizeof(int),

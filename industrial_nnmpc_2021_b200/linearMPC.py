@@ -226,7 +226,7 @@ class DenseQPRegulator:
     CDU size.  ``solve(x0)`` has the reference signature; ``solve_batch`` is the data-parallel form.
 
     Solver parameters (additive): ``rho_scale`` multiplies the default ADMM penalty
-    ``0.4 sqrt(lambda_min lambda_max)`` which is spread over the variables proportionally to
+    ``0.5 sqrt(lambda_min lambda_max)`` which is spread over the variables proportionally to
     ``diag(P)``; ``alpha`` is the over-relaxation.
     """
 
@@ -292,7 +292,7 @@ class DenseQPRegulator:
         lmin, lmax = condense.extreme_eigs(P, cho)
         self.eig_range = (lmin, lmax)
         dP = np.diag(P)
-        rho0 = 0.4 * np.sqrt(lmin * lmax) * self.rho_scale
+        rho0 = 0.5 * np.sqrt(lmin * lmax) * self.rho_scale    # 0.5: swept on the CDU closed loop (0.28 .. 1.1), B200 round 1ae
         self.rho_vec = rho0 * dP / np.exp(np.mean(np.log(dP)))
         Minv = scipy.linalg.inv(P + np.diag(self.rho_vec))
         Minv = 0.5 * (Minv + Minv.T)
