@@ -55,7 +55,7 @@ void prof_end(ProfSpan sp, cudaStream_t st, double flops, long long launches, in
   cudaEventRecord(sp.b, st);
   sp.flops = flops;
   sp.launches = launches;
-  sp.chan = chan & 1;
+  sp.chan = chan & (NNMPC_PROF_CHANNELS - 1);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_spans.push_back(sp);
 }
