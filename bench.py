@@ -411,9 +411,9 @@ def run_native(args):
                     "share_of_step": f64_ms / step_ms_local, "peak_source": dgemm_src,
                     "flops_per_launch": "listed samples x 2 n^2"}
         else:
-            # INT8-sliced exact applies: 28 (anchors, 7 levels) / 36 (checks, 8 levels) INT8 products of 2 n^2 ops per row
+            # INT8-sliced exact applies: 21 (anchors, 6 levels) / 36 (checks, 8 levels) INT8 products of 2 n^2 ops per row
             n_anch, n_chk = st1["anchors"] - st0["anchors"], st1["exact_checks"] - st0["exact_checks"]
-            int8_ops = 2.0 * nvar * nvar * (28.0 * n_anch + 36.0 * n_chk)
+            int8_ops = 2.0 * nvar * nvar * (21.0 * n_anch + 36.0 * n_chk)
             int8_ach = int8_ops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else 0.0
             int8_peak = 2.0 * lp_peak
             r_64 = {"bound": "tensor", "kernel": "oz_gemm2_kernel<.,.,128,OzEpiAnchor|OzEpiVerify> + k_oz_slice (FP64-accurate "
@@ -426,7 +426,7 @@ def run_native(args):
                     "share_of_step": f64_ms / step_ms_local,
                     "peak_source": "2 x the sustained 16-bit dense figure of MEASURED_PEAKS.json (INT8 dense is nominally twice "
                                    "the 16-bit rate; the file carries no measured INT8 entry)",
-                    "flops_per_launch": "listed samples x 2 n^2 FP64-equivalent = x 28 (anchor) or 36 (check) INT8 products; "
+                    "flops_per_launch": "listed samples x 2 n^2 FP64-equivalent = x 21 (anchor) or 36 (check) INT8 products; "
                                         "span includes the digit-plane slicing kernel"}
         roofline, roofline2 = (r_lp, r_64) if gemm_ms >= f64_ms else (r_64, r_lp)
 

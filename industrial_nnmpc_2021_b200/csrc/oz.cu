@@ -11,7 +11,10 @@ namespace nnmpc {
 
 constexpr int OZ_LMAX = 7;     // levels 0..7: 36 INT8 products, truncation (LMAX+1) K 2^(-7 (LMAX+1) - 2) ~ 1.2e-13 at K = 4480
 constexpr int OZ_NS = OZ_LMAX + 1;
-constexpr int OZ_LMAX_ANCHOR = 6;   // anchors (|Top| <= 1, result only steers the iteration; the check certifies): 28 products
+#ifndef NNMPC_OZ_LMAX_ANCHOR
+#define NNMPC_OZ_LMAX_ANCHOR 5
+#endif
+constexpr int OZ_LMAX_ANCHOR = NNMPC_OZ_LMAX_ANCHOR;   // anchors: 6 levels = 21 products (|Top| <= 1; the result only steers the iteration, the 8-level check certifies; measured: same checks per QP as with 7 levels)
 
 // kernel variant: 2 (default) = 128-column tiles, two level windows; 1 = 64-column tiles, one launch, just-in-time
 // operator slices; 0 = first-generation kernel (64 columns, double-buffered slice sets)

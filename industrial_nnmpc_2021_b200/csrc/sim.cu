@@ -691,7 +691,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       if (prof) prof_end(span, st, 0.0, 1);
       // 1c. tail: with few live rows left the same update runs as skinny FP64 GEMMs (counts[E_TAIL] rows, else 0)
       const bool prof64b = prof_begin(&span64, st);
-      k_tail_prep<<<B, 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
+      // at most tail_rows rows are ever listed here (E_TAIL is 0 above that)
+      const int tail_grid = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
+      k_tail_prep<<<tail_grid, 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
       count_launch();
       GemmOperands gi{};
       gi.A = q->W0.p; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
