@@ -119,8 +119,10 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h);
  *   NNMPC_PRECISION_F64    every iteration is an FP64 tensor-core (DMMA) GEMM with Top
  *   NNMPC_PRECISION_MIXED  iterations run on the tcgen05 tensor cores: fp16 increments of the operand
  *                          against a two-term fp16 split of Top, fp32 accumulation in TMEM, all solver
- *                          state in FP64; FP64 "anchor" GEMMs x = Top w - c start every QP and repair
- *                          the drift whenever an exact check fails */
+ *                          state in FP64; an FP64-accurate "anchor" x = Top w - c starts every QP and an
+ *                          FP64-accurate KKT check g = P z + q certifies it (both on the INT8 tensor cores by
+ *                          error-free slicing, or on FP64 DMMA: nnmpc_sim_set_exact_gemm); a check that fails
+ *                          re-anchors the iteration from its own gradient */
 enum { NNMPC_PRECISION_F64 = 0, NNMPC_PRECISION_MIXED = 1 };
 int nnmpc_sim_set_precision(nnmpc_sim_t* h, int mode);
 /* At most `slots` trajectories advance concurrently (default 8192).  A call with B > slots queues the
@@ -139,7 +141,7 @@ int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
 /* Mixed mode only: which tensor pipe evaluates the FP64-exact operator applies (anchors x = Top w - c, KKT checks
  * g = P z + q): 1 (default) = INT8 tcgen05 with error-free slicing (FP64-accurate, see oz_gemm.cuh), 0 = FP64 DMMA. */
 int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
-/* cumulative since create: out4 = {row-iterations, FP64 anchors, exact KKT checks, QPs solved} */
+/* cumulative since create: out4 = {row-iterations, exact anchors, exact KKT checks, QPs solved} */
 int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                   const double* setpoints, const double* disturbances, double* x, double* uprev,

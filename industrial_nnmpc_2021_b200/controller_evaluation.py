@@ -2,11 +2,15 @@
 
 * ``sample_prbs_like``          (:21-47)   scenario input definition, bit-reproducible
 * ``_get_data_for_training``    (:254-271) state scaling of a generated dataset
+* ``_post_process_data``        (:273-295) merge of the per-(task, process) dataset files
+* ``H5pyTool``                  (lib/python_utils.py:41-58) dataset container (h5py, or ``.npz`` with the same keys)
 * ``NeuralNetworkController``   (:780-892) deployment form of the structured network; here a
   *batched* evaluator on the GPU (``control_input_batch``) with the same weight-list layout
   ``[W1,b1,W2,b2,W3,b3,Wout]`` (W stored (in,out)), ``x/xscale`` scaling and output clip.
 """
 from __future__ import annotations
+
+import itertools
 
 import numpy as np
 
@@ -43,6 +47,39 @@ def _get_data_for_training(*, data, num_samples, scale=True):
     out["x"] = out["x"] / xscale
     out["xs"] = out["xs"] / xscale
     return out, xscale
+
+
+class H5pyTool:
+    """lib/python_utils.py:41-58.  Same static methods and file keys; where h5py is not installed the keys go to
+    ``<filename>.npz`` (see linearMPC._save_training_data)."""
+
+    @staticmethod
+    def load_training_data(filename):
+        from .linearMPC import load_training_data
+        return load_training_data(filename)
+
+    @staticmethod
+    def save_training_data(dictionary, filename):
+        from .linearMPC import _save_training_data
+        return _save_training_data(dictionary, filename)
+
+
+def _post_process_data(*, data_filename, num_data_gen_task, num_process_per_task):
+    """Compile the ``{task}-{process}-{data_filename}`` files written by ``OfflineSimulator.generate_data`` /
+    ``simulate_offline`` into one dataset (controller_evaluation.py:273-295): arrays concatenated along axis 0 in
+    ``(task, process)`` order, ``data_gen_time`` averaged; saved under ``data_filename`` and returned."""
+    training_data = dict(x=[], uprev=[], xs=[], us=[], u=[], data_gen_time=[])
+    for task, process in itertools.product(range(num_data_gen_task), range(num_process_per_task)):
+        process_data = H5pyTool.load_training_data(f"{task}-{process}-{data_filename}")
+        for key in process_data.keys():
+            training_data[key].append(process_data[key])
+    for key in training_data.keys():
+        if key == "data_gen_time":
+            training_data[key] = np.mean(np.asarray(training_data[key]))
+        else:
+            training_data[key] = np.concatenate(training_data[key], axis=0)
+    H5pyTool.save_training_data(dictionary=training_data, filename=data_filename)
+    return training_data
 
 
 class NeuralNetworkController:

@@ -9,7 +9,9 @@
 namespace nnmpc {
 
 // which tcgen05 kernel serves the passes: the one-CTA kernel (128 x 128 tiles) unless
-// NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles; same speed today: both are epilogue-bound)
+// NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles).  Measured on B200 (round 1ab/1ae): the
+// pair kernel halves the L2->SMEM operand traffic (5.3 vs 9.0 GB per 8192-row pass) but is not faster (332 vs 372
+// TFLOP/s algorithmic with the slim epilogue), so the one-CTA kernel, which sits at the L2->SMEM ceiling, is the default.
 static bool lp_use_pair() {
   static int v = -1;
   if (v < 0) {

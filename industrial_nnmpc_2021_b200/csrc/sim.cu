@@ -10,10 +10,13 @@
 // count, not the maximum over the batch.
 //
 // One engine loop (all launches stream ordered, row lists and their lengths live on the device):
-//   1. iteration GEMM over the active list (EpiAdmm: DR update + ||d||_inf per row)
+//   1. iteration GEMM over the active list (EpiAdmm: DR update + ||d||_inf per row); in mixed precision the
+//      tcgen05 fp16 pass (lp_gemm.cuh), preceded on full loops by the exact anchors of the rows that start a QP
 //   2. k_select:   rows with kappa*||d||_inf <= tol (or at max_iter) become candidates
-//   3. k_make_z + verification GEMM on the candidates: exact KKT residual with P in FP64
-//   4. k_retire:   candidates that pass are done (iters/kkt rows written), the rest keep iterating
+//   3. k_make_z + verification GEMM on the candidates: exact KKT residual with P (FP64 DMMA, or the INT8-sliced
+//      FP64-accurate tensor-core apply of oz_gemm.cuh in mixed precision)
+//   4. k_retire:   candidates that pass are done (iters/kkt rows written), the rest keep iterating (mixed precision:
+//      re-anchored from the gradient the check just computed)
 //   5. k_advance + plant-step GEMM on the done rows: dataset row u, x+ = [x|u|d][A|B|Bd]'
 //   6. k_step:     t += 1; finished trajectories leave; the rest form the renew list
 //   7. target selector (fused: dataset rows x,uprev,xs,us; x0, lb, ub; warm-start shift dus),
@@ -53,7 +56,7 @@ struct nnmpc_sim {
   nnmpc::DevBuf<int> chunk, cold;              // per slot: the trajectory chunk it works on; cold (re)start pending
   int slot_cap;                                // most trajectories advanced concurrently (further chunks queue up)
   int cadence;                                 // mixed mode: the FP64 phases run every cadence-th loop
-  // mixed-precision iteration (tcgen05 fp16 increments + FP64 anchors), see lp_iter.cuh
+  // mixed-precision iteration (tcgen05 fp16 increments + FP64-accurate anchors / checks), see lp_iter.cuh, oz_gemm.cuh
   int mixed;
   int tail_rows;                    // live rows at or below which the mixed mode finishes in FP64 (-1 = auto)
   nnmpc::LpState lps;
@@ -665,8 +668,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     // 1. one Douglas-Rachford iteration for every live trajectory
     const bool full = (loop % cad) == 0;
     if (mixed) {
-      // 1a. FP64 anchors for the rows that start a QP or failed an exact check: x = Top w - c with the
-      //     DMMA kernel, one full-precision step, first fp16 increment
+      // 1a. exact anchors for the rows that start a QP: x = Top w - c (INT8-sliced tensor-core apply, or the
+      //     DMMA kernel), one full-precision step, first fp16 increment
       int* cnt = e.counts + E_ANCHOR;
       const int rbuf = lay;
       const int* list_r = e.lp_list + (long long)rbuf * B;
@@ -787,7 +790,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   if (h->pin[F_MAXITER]) rc_warn = NNMPC_WARN_MAXITER;
   g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
   prof_add_flops(2.0 * n * (double)n * (double)*pin64);                               // iteration passes
-  prof_add_flops(2.0 * n * (double)n * (double)(pin64[1] + pin64[2]), 1);             // FP64 anchors + checks
+  prof_add_flops(2.0 * n * (double)n * (double)(pin64[1] + pin64[2]), 1);             // exact anchors + checks (FP64-equivalent)
   h->tot_rowiters += (long long)pin64[0];
   h->tot_anchors += (long long)pin64[1];
   h->tot_verifies += (long long)pin64[2];

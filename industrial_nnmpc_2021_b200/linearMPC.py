@@ -551,7 +551,7 @@ class ClosedLoopEngine:
 
     def __init__(self, regulator, target_selector, A, B, Bd, precision=None, tail_rows=None, slots=None):
         """``precision``: "f64" (every iteration an FP64 tensor-core GEMM) or "mixed" (tcgen05 fp16
-        increments with FP64 anchors; every result still passes an FP64 KKT check).  Default: the
+        increments with FP64-accurate anchors; every result still passes an FP64-accurate KKT check).  Default: the
         environment variable NNMPC_PRECISION, else "mixed"."""
         if regulator._dev != target_selector._dev:
             raise ValueError("regulator and target selector live on different devices")

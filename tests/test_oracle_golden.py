@@ -186,3 +186,28 @@ def test_target_selector_oracle_full_vs_reduced(which, cstrs_problem, cdu_small_
         c1 = 0.5 * np.vstack([xs, us]).T @ ts.P @ np.vstack([xs, us]) + q.T @ np.vstack([xs, us])
         c2 = 0.5 * w2.T @ ts.P @ w2 + q.T @ w2
         assert abs(c1.item() - c2.item()) <= 1e-9 * max(1.0, abs(c1.item()))
+
+
+def test_post_process_data_merges_in_task_process_order(tmp_path, monkeypatch):
+    """controller_evaluation.py:273-295: per-(task, process) files -> one dataset, rows in (task, process) order,
+    data_gen_time averaged; the training scaling of :254-271 applied to it."""
+    from industrial_nnmpc_2021_b200 import controller_evaluation as ce
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(5)
+    parts = {}
+    for task in range(2):
+        for proc in range(3):
+            d = dict(x=rng.standard_normal((4, 5)), uprev=rng.standard_normal((4, 2)), xs=rng.standard_normal((4, 5)),
+                     us=rng.standard_normal((4, 2)), u=rng.standard_normal((4, 2)), data_gen_time=float(task + proc))
+            parts[(task, proc)] = d
+            ce.H5pyTool.save_training_data(dictionary=d, filename=f"{task}-{proc}-data.h5py")
+    merged = ce._post_process_data(data_filename="data.h5py", num_data_gen_task=2, num_process_per_task=3)
+    order = [(t, p) for t in range(2) for p in range(3)]
+    for k in ("x", "uprev", "xs", "us", "u"):
+        assert np.array_equal(merged[k], np.concatenate([parts[o][k] for o in order], axis=0))
+    assert merged["data_gen_time"] == np.mean([parts[o]["data_gen_time"] for o in order])
+    back = ce.H5pyTool.load_training_data("data.h5py")
+    assert np.array_equal(back["x"], merged["x"]) and float(back["data_gen_time"]) == merged["data_gen_time"]
+    scaled, xscale = ce._get_data_for_training(data=back, num_samples=20)
+    assert np.allclose(xscale, 0.5 * (back["x"][:20].max(axis=0) - back["x"][:20].min(axis=0)))
+    assert np.allclose(scaled["x"] * xscale, back["x"][:20]) and np.allclose(scaled["xs"] * xscale, back["xs"][:20])
