@@ -210,6 +210,7 @@ def _config(args, traj, slab):
             "Nx": 252, "Nu": 32, "Ny": 90, "horizon": args.horizon, "qp_vars": args.horizon * 32,
             "trajectories_per_gpu": traj, "concurrent_slots_per_gpu": min(traj, getattr(args, "slots", traj)),
             "sim_steps_per_step": slab, "tol_kkt": KKT_TOL,
+            "scenario_slabs": f"{getattr(args, 'unique_slabs', 0)} distinct PRBS slabs at most, cycled over the steps",
             "precision": args.precision,
             "l2": "no flush: operators (2 x 161 MB FP64 + 2 x 40 MB fp16) + solver state exceed the 126 MB L2 every iteration",
             "parallelism": f"trajectories sharded over {args.gpus} GPU(s), no collective on the solve path"}
@@ -241,7 +242,11 @@ def run_native(args):
 
     K, W, B, Ts = args.steps, max(args.warmup, 3), args.traj, args.slab
     nslab = 2 * (W + K)                      # device-resident phase, then the end-to-end phase
-    p, sp, ds = _scenarios(B, nslab * Ts, seed=101 + 2 * rank)
+    # distinct PRBS scenario slabs kept in memory; further steps cycle through them (bounds host memory: one slab
+    # is traj x slab x 95 doubles).  Trajectories that continue across steps (--traj <= --slots) see one extra
+    # set-point jump where the cycle wraps.
+    nuniq = min(nslab, max(1, args.unique_slabs))
+    p, sp, ds = _scenarios(B, nuniq * Ts, seed=101 + 2 * rank)
     if args.horizon != p.N:
         p.N = args.horizon
     t_setup = time.perf_counter()
@@ -259,7 +264,7 @@ def run_native(args):
 
     f64 = dict(dtype=torch.float64, device=dev)
     slabs = [(torch.tensor(np.ascontiguousarray(sp[:, i * Ts:(i + 1) * Ts]), **f64),
-              torch.tensor(np.ascontiguousarray(ds[:, i * Ts:(i + 1) * Ts]), **f64)) for i in range(W + K)]
+              torch.tensor(np.ascontiguousarray(ds[:, i * Ts:(i + 1) * Ts]), **f64)) for i in range(min(W + K, nuniq))]
     out_d = dict(x=torch.empty((B, Ts, nx), **f64), uprev=torch.empty((B, Ts, nu), **f64),
                  xs=torch.empty((B, Ts, nx), **f64), us=torch.empty((B, Ts, nu), **f64),
                  u=torch.empty((B, Ts, nu), **f64), iters=torch.empty((B, Ts), dtype=torch.int32, device=dev),
@@ -284,7 +289,7 @@ def run_native(args):
     it_sum = torch.zeros((), dtype=torch.int64, device=dev)
     it_acc = torch.zeros((), dtype=torch.int32, device=dev)
     for i in range(W):
-        r = eng.run(x, up, *slabs[i], resume=i > 0, out=out_d, max_iter=args.max_iter)
+        r = eng.run(x, up, *slabs[i % len(slabs)], resume=i > 0, out=out_d, max_iter=args.max_iter)
         x, up = r["x_final"], r["uprev_final"]
     barrier()
     _lib.prof_enable(True)
@@ -295,7 +300,7 @@ def run_native(args):
     with ClockSampler(local) as clk:
         ev0.record()
         for i in range(W, W + K):
-            r = eng.run(x, up, *slabs[i], resume=True, out=out_d, max_iter=args.max_iter)
+            r = eng.run(x, up, *slabs[i % len(slabs)], resume=True, out=out_d, max_iter=args.max_iter)
             x, up = r["x_final"], r["uprev_final"]
             hit |= bool(r["maxiter_hit"])
             # validity of the timed work itself (device-side reductions, read after the timing)
@@ -331,8 +336,9 @@ def run_native(args):
             ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ee0.record()
             t_e2e = time.perf_counter()
-        sp_h[...] = sp[:, i * Ts:(i + 1) * Ts]          # this step's inputs staged in pinned host memory
-        ds_h[...] = ds[:, i * Ts:(i + 1) * Ts]
+        j = i % nuniq
+        sp_h[...] = sp[:, j * Ts:(j + 1) * Ts]          # this step's inputs staged in pinned host memory
+        ds_h[...] = ds[:, j * Ts:(j + 1) * Ts]
         r = eng.run(xh, uph, sp_h, ds_h, resume=True, out=out_h, max_iter=args.max_iter)
         xh, uph = r["x_final"], r["uprev_final"]
         e2e_kkt = max(e2e_kkt, float(out_h["kkt"].max()))      # the device->host result is read every step
@@ -467,7 +473,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--traj", type=int, default=32768,
+    ap.add_argument("--unique-slabs", type=int, default=6,
+                    help="distinct scenario slabs generated; steps beyond that cycle through them")
+    ap.add_argument("--traj", type=int, default=65536,
                     help="closed-loop trajectory chunks per GPU and bench step (the reference's per-process chunks, "
                          "lib/linearMPC.py:786-801); with --slots below it they queue up (continuous batching)")
     ap.add_argument("--slab", type=int, default=16, help="simulation steps every trajectory advances per bench step")
