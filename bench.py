@@ -400,10 +400,17 @@ def run_native(args):
     else:
         lp_peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0)
         f64_ach = f64_flops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else 0.0
+        # DRAM traffic per launch, scaled from the one `ncu --set full` capture of this kernel (profiles/
+        # r01af_ncu_full_lp_gemm.txt: dram read 1.2787 GB + write 0.7549 GB at 8192 rows, n = 4480): 80.3 MB of fp16
+        # operator per launch + 238.4 kB per row (algorithmic: 42 B x n = 188.2 kB per row).  Only for n = 4480.
+        rows_per_launch = (gemm_flops / (2.0 * nvar * nvar)) / max(gemm_launches, 1)
+        lp_traffic = (80.3e6 + 238.4e3 * rows_per_launch) if nvar == 4480 else None
         r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
                                              "increments x two-term fp16 operator split, fp32 TMEM accumulators, FP64 state)",
                 "achieved": achieved, "executed_mma": 2.0 * achieved, "peak": lp_peak, "unit": "TFLOP/s",
-                "frac": achieved / lp_peak, "frac_executed": 2.0 * achieved / lp_peak, "traffic": None,
+                "frac": achieved / lp_peak, "frac_executed": 2.0 * achieved / lp_peak, "traffic": lp_traffic,
+                "traffic_algorithmic": 80.3e6 + 188.2e3 * rows_per_launch if nvar == 4480 else None,
+                "rows_per_launch": rows_per_launch,
                 "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "share_of_step": gemm_ms / step_ms_local,
                 "peak_source": f"dense 16-bit tensor throughput, sustained figure of MEASURED_PEAKS.json ({peak_src}); "
