@@ -112,7 +112,70 @@ def main():
     out.update(unst_A=Au, unst_B=Bu, unst_P=regu.P, unst_tq=regu.tq, unst_G=regu.G,
                unst_h=regu._get_h(x0u), unst_x0=x0u, unst_reparam=np.array(regu.reparameterize))
     np.savez_compressed(os.path.join(HERE, "formulation.npz"), **out)
+
+    # ---- 3. closed-loop wiring: the reference's OWN simulate_offline / _split_scenarios /
+    #         _get_data_for_training run with stand-in solvers (cvxopt is not installable): the regulator and the
+    #         target selector are replaced by closed-form laws that USE the mutated bounds, so the fixture pins the
+    #         order of operations (:845-866), the bound shift and deviation variables (:682-689), the data rows
+    #         (state BEFORE the step, :868-872), the chunking (:786-801) and the training scaling (:254-271).
+    out = {}
+    rng = np.random.default_rng(21)
+    nx, nu, ny, nd, N, T = 5, 2, 3, 2, 4, 9
+    A = 0.6 * np.eye(nx) + 0.1 * rng.standard_normal((nx, nx))
+    Bm = rng.standard_normal((nx, nu))
+    Bd = rng.standard_normal((nx, nd))
+    stub = dict(K=0.4 * rng.standard_normal((nu, nx + nu)), Mx=rng.standard_normal((nx, ny)),
+                Nx=rng.standard_normal((nx, nd)), Mu=0.3 * rng.standard_normal((nu, ny)),
+                Nu=0.3 * rng.standard_normal((nu, nd)))
+    ulb, uub = -0.5 * np.ones((nu, 1)), 0.4 * np.ones((nu, 1))
+    sps, dss = rng.standard_normal((T, ny)), rng.standard_normal((T, nd))
+    x0, up0 = rng.standard_normal((nx, 1)), 0.1 * rng.standard_normal((nu, 1))
+    captured = {}
+    ref.H5pyTool.save_training_data = staticmethod(lambda dictionary, filename: captured.update(
+        {**dictionary, "filename": filename}))
+    ref.simulate_offline(3, 1, "golden.h5py", x0, up0, A, Bm, Bd, StubRegulator(stub["K"], N), ulb, uub,
+                         StubTargetSelector(stub, ulb, uub), sps, dss)
+    out.update({f"sim_{k}": np.asarray(v) for k, v in captured.items() if k not in ("filename", "data_gen_time")})
+    out["sim_filename"] = np.array(captured["filename"])
+    out.update(sim_A=A, sim_B=Bm, sim_Bd=Bd, sim_ulb=ulb, sim_uub=uub, sim_setpoints=sps, sim_disturbances=dss,
+               sim_x0=x0, sim_uprev0=up0, sim_N=np.array(N), **{f"sim_stub_{k}": v for k, v in stub.items()})
+    fake = types.SimpleNamespace(num_data_gen_task=3, num_process_per_task=2)
+    big_sp, big_ds = rng.standard_normal((53, ny)), rng.standard_normal((53, nd))
+    sp_split, ds_split = ref.OfflineSimulator._split_scenarios(fake, setpoints=big_sp, disturbances=big_ds)
+    out.update(split_sp=big_sp, split_ds=big_ds,
+               split_sp_out=np.asarray([[c for c in task] for task in sp_split]),
+               split_ds_out=np.asarray([[c for c in task] for task in ds_split]))
+    data = dict(x=rng.standard_normal((40, nx)), uprev=rng.standard_normal((40, nu)), xs=rng.standard_normal((40, nx)),
+                us=rng.standard_normal((40, nu)), u=rng.standard_normal((40, nu)))
+    scaled, xscale = ref_ce._get_data_for_training(data=data, num_samples=31)
+    out.update({f"train_in_{k}": v for k, v in data.items()})
+    out.update({f"train_out_{k}": v for k, v in scaled.items()})
+    out["train_xscale"] = xscale
+    np.savez_compressed(os.path.join(HERE, "closed_loop_glue.npz"), **out)
     print("wrote", os.listdir(HERE))
+
+
+class StubRegulator:
+    """Stand-in for DenseQPRegulator in the wiring fixture: u = clip(-K x0) repeated over the horizon, clipped with
+    the bounds get_control_sequence has just written into the object (linearMPC.py:685-686)."""
+
+    def __init__(self, K, N):
+        self.K, self.N = K, N
+        self.ulb = self.uub = None
+
+    def solve(self, x0):
+        return np.tile(np.clip(-self.K @ x0, self.ulb, self.uub), (self.N, 1))
+
+
+class StubTargetSelector:
+    """Stand-in for TargetSelector: an affine map of (ysp, d) with the input part clipped to the bounds."""
+
+    def __init__(self, m, ulb, uub):
+        self.m, self.ulb, self.uub = m, ulb, uub
+
+    def solve(self, ysp, dhats):
+        return (self.m["Mx"] @ ysp + self.m["Nx"] @ dhats, np.clip(self.m["Mu"] @ ysp + self.m["Nu"] @ dhats,
+                                                                  self.ulb, self.uub))
 
 
 if __name__ == "__main__":

@@ -211,3 +211,77 @@ def test_post_process_data_merges_in_task_process_order(tmp_path, monkeypatch):
     scaled, xscale = ce._get_data_for_training(data=back, num_samples=20)
     assert np.allclose(xscale, 0.5 * (back["x"][:20].max(axis=0) - back["x"][:20].min(axis=0)))
     assert np.allclose(scaled["x"] * xscale, back["x"][:20]) and np.allclose(scaled["xs"] * xscale, back["xs"][:20])
+
+
+# ------------------------------------------------------------------------------------ closed-loop wiring
+@pytest.fixture(scope="module")
+def golden_glue():
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "closed_loop_glue.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+class _StubRegulator:
+    """Same stand-in as tests/golden/make_golden.py: u = clip(-K x0) with the bounds get_control_sequence wrote."""
+
+    def __init__(self, K, N):
+        self.K, self.N = K, N
+        self.ulb = self.uub = None
+
+    def solve(self, x0):
+        return np.tile(np.clip(-self.K @ x0, self.ulb, self.uub), (self.N, 1))
+
+
+class _StubTargetSelector:
+    def __init__(self, g, ulb, uub):
+        self.g, self.ulb, self.uub = g, ulb, uub
+
+    def solve(self, ysp, dhats):
+        g = self.g
+        return (g["sim_stub_Mx"] @ ysp + g["sim_stub_Nx"] @ dhats,
+                np.clip(g["sim_stub_Mu"] @ ysp + g["sim_stub_Nu"] @ dhats, self.ulb, self.uub))
+
+
+def test_oracle_closed_loop_wiring_matches_reference_simulate_offline(golden_glue):
+    """The reference's own simulate_offline (linearMPC.py:827-880), run with stand-in solvers when the fixture was
+    made, against the oracle's restatement with the same stand-ins: order of operations, bound shift, deviation
+    variables, rows = state BEFORE the step - bit for bit."""
+    g = golden_glue
+    N = int(g["sim_N"])
+    od = om.simulate_offline(x0=g["sim_x0"], uprev0=g["sim_uprev0"], A=g["sim_A"], B=g["sim_B"], Bd=g["sim_Bd"],
+                             regulator=_StubRegulator(g["sim_stub_K"], N), ulb=g["sim_ulb"], uub=g["sim_uub"],
+                             target_selector=_StubTargetSelector(g, g["sim_ulb"], g["sim_uub"]),
+                             setpoints=g["sim_setpoints"], disturbances=g["sim_disturbances"])
+    for k in ("x", "uprev", "xs", "us", "u"):
+        assert np.array_equal(od[k], g[f"sim_{k}"]), k
+    assert str(g["sim_filename"]) == "3-1-golden.h5py"
+    # the drop-in's static glue is the same function
+    from industrial_nnmpc_2021_b200.linearMPC import LinearMPCController
+    reg = _StubRegulator(g["sim_stub_K"], N)
+    x, up = g["sim_x"][2][:, None], g["sim_uprev"][2][:, None]
+    xs, us = g["sim_xs"][2][:, None], g["sim_us"][2][:, None]
+    useq = LinearMPCController.get_control_sequence(reg, x, up, xs, us, g["sim_ulb"], g["sim_uub"])
+    assert np.array_equal(useq[:up.shape[0], 0], g["sim_u"][2])
+    assert np.array_equal(reg.ulb, g["sim_ulb"] - us) and np.array_equal(reg.uub, g["sim_uub"] - us)
+
+
+def test_split_scenarios_and_training_scaling_match_reference(golden_glue):
+    """OfflineSimulator._split_scenarios (linearMPC.py:786-801: equal contiguous chunks, remainder dropped,
+    [task][process]) and _get_data_for_training (controller_evaluation.py:254-271) against the reference's outputs."""
+    import types
+    from industrial_nnmpc_2021_b200.linearMPC import OfflineSimulator
+    from industrial_nnmpc_2021_b200 import controller_evaluation as ce
+    g = golden_glue
+    fake = types.SimpleNamespace(num_data_gen_task=3, num_process_per_task=2)
+    sp, ds = OfflineSimulator._split_scenarios(fake, setpoints=g["split_sp"], disturbances=g["split_ds"])
+    assert np.array_equal(np.asarray(sp), g["split_sp_out"]) and np.array_equal(np.asarray(ds), g["split_ds_out"])
+    assert g["split_sp_out"].shape[:3] == (3, 2, 8)            # 53 rows over 6 processes: 8 each, 5 dropped
+    osp, ods = om.split_scenarios(g["split_sp"], g["split_ds"], 6)          # the oracle's flat (task-major) form
+    assert np.array_equal(np.asarray(osp).reshape(3, 2, 8, -1), g["split_sp_out"])
+    assert np.array_equal(np.asarray(ods).reshape(3, 2, 8, -1), g["split_ds_out"])
+    data = {k: g[f"train_in_{k}"] for k in ("x", "uprev", "xs", "us", "u")}
+    scaled, xscale = ce._get_data_for_training(data=data, num_samples=31)
+    assert np.array_equal(xscale, g["train_xscale"])
+    for k in ("x", "uprev", "xs", "us", "u"):
+        assert np.array_equal(scaled[k], g[f"train_out_{k}"]), k
