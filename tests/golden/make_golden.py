@@ -152,6 +152,39 @@ def main():
     out.update({f"train_out_{k}": v for k, v in scaled.items()})
     out["train_xscale"] = xscale
     np.savez_compressed(os.path.join(HERE, "closed_loop_glue.npz"), **out)
+
+    # ---- 4. structured network, NumPy deployment form: the reference's own NeuralNetworkController methods
+    #         (controller_evaluation.py:863-892; __init__ is bypassed - it builds cvxopt objects).  LinearMPCLayers.py
+    #         itself needs tensorflow, which is not installed; the NumPy form is the same function (paper eq. 8).
+    out = {}
+    rng = np.random.default_rng(33)
+    nx, nu = 7, 3
+    for tag, with_uprev in (("with", True), ("without", False)):
+        dims = [2 * nx + (2 if with_uprev else 1) * nu, 16, 12, 9, nu]
+        ws = []
+        for i in range(len(dims) - 1):
+            ws.append(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i]))
+            if i < len(dims) - 2:
+                ws.append(0.1 * rng.standard_normal(dims[i + 1]))
+        ctl = object.__new__(ref_ce.NeuralNetworkController)
+        ctl.regulator_weights, ctl.nnwithuprev = ws, with_uprev
+        ctl.xscale = rng.uniform(0.5, 2.0, nx)[:, np.newaxis]
+        ctl.ulb, ctl.uub = -0.3 * np.ones((nu, 1)), 0.4 * np.ones((nu, 1))
+        cols = []
+        for _ in range(6):
+            x, xs = rng.standard_normal((nx, 1)), rng.standard_normal((nx, 1))
+            up, us = rng.uniform(-1, 1, (nu, 1)), rng.uniform(-0.5, 0.5, (nu, 1))
+            xsc, xssc = ctl._get_scaled_x_xs(x, xs)
+            u = ctl._get_control_input(xsc, up, xssc, us)
+            raw = ctl._get_regulator_nn_output(xsc, up, xssc, us)
+            cols.append(np.concatenate([x, up, xs, us, u, raw], axis=0)[:, 0])
+        out[f"nn_{tag}_cols"] = np.asarray(cols)
+        out[f"nn_{tag}_xscale"] = ctl.xscale[:, 0]
+        out[f"nn_{tag}_nweights"] = np.array(len(ws))
+        for i, w in enumerate(ws):
+            out[f"nn_{tag}_w{i}"] = w
+    out.update(nn_nx=np.array(nx), nn_nu=np.array(nu), nn_ulb=-0.3 * np.ones((nu, 1)), nn_uub=0.4 * np.ones((nu, 1)))
+    np.savez_compressed(os.path.join(HERE, "structured_nn.npz"), **out)
     print("wrote", os.listdir(HERE))
 
 

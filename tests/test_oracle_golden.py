@@ -285,3 +285,33 @@ def test_split_scenarios_and_training_scaling_match_reference(golden_glue):
     assert np.array_equal(xscale, g["train_xscale"])
     for k in ("x", "uprev", "xs", "us", "u"):
         assert np.array_equal(scaled[k], g[f"train_out_{k}"]), k
+
+
+# ------------------------------------------------------------------------------------ structured network
+def test_nn_oracle_matches_reference_numpy_controller():
+    """oracle/nn.py against outputs of the reference's own NeuralNetworkController NumPy methods
+    (controller_evaluation.py:863-892: scaling, f(x,uprev,xs,us) - f(xs,us,xs,us) + us, clip), both network forms;
+    the batched layer form (LinearMPCLayers.py:40-61 restated) must agree with the column form."""
+    import os
+    from conftest import GOLDEN
+    from oracle import nn as onn
+    with np.load(os.path.join(GOLDEN, "structured_nn.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    nx, nu = int(g["nn_nx"]), int(g["nn_nu"])
+    for tag, with_uprev in (("with", True), ("without", False)):
+        ws = [g[f"nn_{tag}_w{i}"] for i in range(int(g[f"nn_{tag}_nweights"]))]
+        xscale = g[f"nn_{tag}_xscale"][:, None]
+        cols = g[f"nn_{tag}_cols"]
+        clipped = 0
+        for c in cols:
+            x, up, xs, us, u_ref, raw_ref = np.split(c[:, None], np.cumsum([nx, nu, nx, nu, nu]))
+            u = onn.control_input(ws, x, up, xs, us, with_uprev, xscale, g["nn_ulb"], g["nn_uub"])
+            assert np.array_equal(u, u_ref)
+            assert np.array_equal(onn.regulator_nn_output(ws, x / xscale, up, xs / xscale, us, with_uprev), raw_ref)
+            clipped += int(np.any(u_ref == g["nn_uub"]) or np.any(u_ref == g["nn_ulb"]))
+            # batched layer form on the scaled inputs, before the clip
+            ins = [(x / xscale).T, up.T, (xs / xscale).T, us.T] if with_uprev else [(x / xscale).T, (xs / xscale).T, us.T]
+            lay = onn.layer_call(ws, ins, with_uprev)
+            unclipped = onn.control_input(ws, x, up, xs, us, with_uprev, xscale)
+            assert np.max(np.abs(lay.T - unclipped)) <= 1e-13
+        assert clipped >= 1, "fixture should exercise the output clip"
