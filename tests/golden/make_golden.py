@@ -185,6 +185,35 @@ def main():
             out[f"nn_{tag}_w{i}"] = w
     out.update(nn_nx=np.array(nx), nn_nu=np.array(nu), nn_ulb=-0.3 * np.ones((nu, 1)), nn_uub=0.4 * np.ones((nu, 1)))
     np.savez_compressed(os.path.join(HERE, "structured_nn.npz"), **out)
+
+    # ---- 5. online-loop host pieces (control_law's estimator side, linearMPC.py:87-176, :606-624): the reference's
+    #         own KalmanFilter / LinearPlantSimulator / setup_filter on a small disturbance-augmented model.
+    out = {}
+    rng = np.random.default_rng(44)
+    nx, nu, ny, nd = 4, 2, 3, 2
+    A = 0.7 * np.eye(nx) + 0.1 * rng.standard_normal((nx, nx))
+    Bm, Cm = rng.standard_normal((nx, nu)), rng.standard_normal((ny, nx))
+    Bd, Cd = rng.standard_normal((nx, nd)), np.vstack([np.eye(nd), np.zeros((ny - nd, nd))])
+    Qwx, Qwd, Rv = 0.1 * np.eye(nx), 0.05 * np.eye(nd), 0.01 * np.eye(ny)
+    xprior, dprior = 0.1 * rng.standard_normal((nx, 1)), np.zeros((nd, 1))
+    kf = ref.LinearMPCController.setup_filter(A=A, B=Bm, C=Cm, Bd=Bd, Cd=Cd, Qwx=Qwx, Qwd=Qwd, Rv=Rv,
+                                              xprior=xprior, dprior=dprior)
+    aug = ref.LinearMPCController.get_augmented_matrices_for_filter(A, Bm, Cm, Bd, Cd, Qwx, Qwd)
+    np.random.seed(5)
+    plant = ref.LinearPlantSimulator(A=A, B=Bm, C=Cm, Bp=Bd, Rv=Rv, sample_time=1.0, x0=xprior)
+    us = rng.uniform(-1, 1, (6, nu, 1))
+    ps = rng.uniform(-1, 1, (6, nd, 1))
+    ys, xhats = [plant.y[0]], []
+    uprev = np.zeros((nu, 1))
+    for k in range(6):
+        xhats.append(kf.solve(ys[-1], uprev))
+        ys.append(plant.step(us[k], ps[k]))
+        uprev = us[k]
+    out.update(kf_A=A, kf_B=Bm, kf_C=Cm, kf_Bd=Bd, kf_Cd=Cd, kf_Qwx=Qwx, kf_Qwd=Qwd, kf_Rv=Rv, kf_xprior=xprior,
+               kf_dprior=dprior, kf_L=kf.L, kf_Aaug=aug[0], kf_Baug=aug[1], kf_Caug=aug[2], kf_Qwaug=aug[3],
+               kf_us=us, kf_ps=ps, kf_ys=np.asarray(ys), kf_xhats=np.asarray(xhats), kf_plant_x=np.asarray(plant.x),
+               kf_seed=np.array(5))
+    np.savez_compressed(os.path.join(HERE, "online_loop.npz"), **out)
     print("wrote", os.listdir(HERE))
 
 

@@ -315,3 +315,32 @@ def test_nn_oracle_matches_reference_numpy_controller():
             unclipped = onn.control_input(ws, x, up, xs, us, with_uprev, xscale)
             assert np.max(np.abs(lay.T - unclipped)) <= 1e-13
         assert clipped >= 1, "fixture should exercise the output clip"
+
+
+# ------------------------------------------------------------------------------------ online-loop host pieces
+def test_filter_and_plant_simulator_match_reference():
+    """The estimator side of control_law (linearMPC.py:87-176, :606-624): the drop-in's host mirrors of
+    setup_filter / get_augmented_matrices_for_filter / KalmanFilter.solve / LinearPlantSimulator.step against a
+    run of the reference's own classes (same legacy NumPy seed for the measurement noise)."""
+    import os
+    from conftest import GOLDEN
+    from industrial_nnmpc_2021_b200.linearMPC import LinearMPCController, LinearPlantSimulator
+    with np.load(os.path.join(GOLDEN, "online_loop.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    aug = LinearMPCController.get_augmented_matrices_for_filter(g["kf_A"], g["kf_B"], g["kf_C"], g["kf_Bd"], g["kf_Cd"],
+                                                                g["kf_Qwx"], g["kf_Qwd"])
+    for a, k in zip(aug, ("kf_Aaug", "kf_Baug", "kf_Caug", "kf_Qwaug")):
+        assert np.array_equal(a, g[k]), k
+    kf = LinearMPCController.setup_filter(g["kf_A"], g["kf_B"], g["kf_C"], g["kf_Bd"], g["kf_Cd"], g["kf_Qwx"],
+                                          g["kf_Qwd"], g["kf_Rv"], g["kf_xprior"], g["kf_dprior"])
+    assert np.allclose(kf.L, g["kf_L"], rtol=1e-12, atol=1e-14)
+    np.random.seed(int(g["kf_seed"]))
+    plant = LinearPlantSimulator(A=g["kf_A"], B=g["kf_B"], C=g["kf_C"], Bp=g["kf_Bd"], Rv=g["kf_Rv"], sample_time=1.0,
+                                 x0=g["kf_xprior"])
+    ys, uprev = [plant.y[0]], np.zeros((g["kf_B"].shape[1], 1))
+    for k in range(g["kf_us"].shape[0]):
+        xhat = kf.solve(ys[-1], uprev)
+        assert np.allclose(xhat, g["kf_xhats"][k], rtol=1e-11, atol=1e-13)
+        ys.append(plant.step(g["kf_us"][k], g["kf_ps"][k]))
+        uprev = g["kf_us"][k]
+    assert np.array_equal(np.asarray(ys), g["kf_ys"]) and np.array_equal(np.asarray(plant.x), g["kf_plant_x"])
