@@ -10,9 +10,18 @@
  *  - "host" pointers are ordinary CPU memory, "dev" pointers are CUDA device memory on the
  *    handle's device (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t (NULL = default);
  *  - every function returns 0 on success, a negative nnmpc_status on error (message through
- *    nnmpc_last_error(), thread-local) and NNMPC_WARN_MAXITER (>0) when some sample hit max_iter;
+ *    nnmpc_last_error(), thread-local) and a positive bit mask of warnings otherwise:
+ *    NNMPC_WARN_MAXITER (some regulator QP hit max_iter), NNMPC_WARN_TARGET (some target-selector
+ *    solve did not reach its optimum);
  *  - the caller owns every buffer it passes; handles own only the replicated operators and
- *    scratch, released by *_destroy.  Handles are immutable after create; one device per handle.
+ *    scratch, released by *_destroy; one device per handle.
+ *  - threading: the OPERATORS of a handle never change after create (nnmpc_qp_set_penalty completes
+ *    the create of a regulator handle and is called once, before the first solve), but a handle also
+ *    owns solver SCRATCH and, for nnmpc_sim, the run options of the nnmpc_sim_set_* calls: one call
+ *    at a time per handle (the reference's objects are single-threaded too, lib/linearMPC.py:685-686
+ *    mutates the regulator on every call).  Different handles are independent and may be driven from
+ *    different host threads / streams concurrently; nothing is global except the launch counters and
+ *    the optional profiling spans of nnmpc_prof_* (mutex protected, off by default).
  */
 #ifndef NNMPC_H
 #define NNMPC_H
@@ -23,6 +32,7 @@ extern "C" {
 typedef enum {
   NNMPC_OK = 0,
   NNMPC_WARN_MAXITER = 1,
+  NNMPC_WARN_TARGET = 2,
   NNMPC_ERR_BADARG = -1,
   NNMPC_ERR_CUDA = -2,
   NNMPC_ERR_NOMEM = -3,
@@ -94,6 +104,8 @@ int nnmpc_ts_create(nnmpc_ts_t** out, int nx, int nu, int ny, int nd, const doub
                     const double* uub_host, int device);
 int nnmpc_ts_destroy(nnmpc_ts_t* h);
 /* ysp: dev B rows of ny doubles, row stride ysp_stride (doubles); d likewise. */
+/* iters (nullable): active-set steps per sample; a sample whose solve stalled at the step cap or went
+ * non-finite gets the NEGATED count -(steps+1) (and the host entry point returns NNMPC_WARN_TARGET). */
 int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride, const double* d,
                    long long d_stride, double* xs, double* us, int* iters, void* stream);
 int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d, double* xs,
@@ -141,6 +153,12 @@ int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
 /* Mixed mode only: which tensor pipe evaluates the FP64-exact operator applies (anchors x = Top w - c, KKT checks
  * g = P z + q): 1 (default) = INT8 tcgen05 with error-free slicing (FP64-accurate, see oz_gemm.cuh), 0 = FP64 DMMA. */
 int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
+/* Optional per-QP sinks for the following nnmpc_sim_run calls (device pointers, either may be NULL; NULL, NULL
+ * switches the capture off): useq [B][T][n] = the whole optimal input sequence of every regulator QP with the
+ * target added back per stage - what get_control_sequence returns (lib/linearMPC.py:689) and DenseQPRegulator
+ * keeps in .useq (:511) - and cost [B][T] = the optimal value 1/2 u'Pu + q'u in deviation variables.  Meant for
+ * parity tests and diagnostics at small B*T (n doubles per sample); nnmpc_sim_run_host ignores it. */
+int nnmpc_sim_set_capture(nnmpc_sim_t* h, double* useq_dev, double* cost_dev);
 /* cumulative since create: out4 = {row-iterations, exact anchors, exact KKT checks, QPs solved} */
 int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,

@@ -80,7 +80,8 @@ class _StructuredRegulatorLayer:
         import torch
         if not torch.cuda.is_available():
             raise _lib.NnmpcError("no CUDA device visible: this package has no CPU fallback")
-        dev = torch.cuda.current_device() if self._device is None else (torch.device(self._device).index or 0)
+        idx = None if self._device is None else torch.device(self._device).index
+        dev = torch.cuda.current_device() if idx is None else idx
         self._free()
         warr = (C.c_void_p * nl)(*[k.ctypes.data for k in kernels])
         barr = (C.c_void_p * nl)(*([b.ctypes.data for b in biases] + [None]))
@@ -132,9 +133,13 @@ class _StructuredRegulatorLayer:
         ub = None if uub is None else torch.as_tensor(np.ravel(uub) if isinstance(uub, np.ndarray) else uub,
                                                       **f64).contiguous()
         out = torch.empty((x.shape[0], self._nu), **f64)
-        rc = L.nnmpc_mlp_forward(self._handle, x.shape[0], _lib.dptr(x), _lib.dptr(uprev), _lib.dptr(xs),
-                                 _lib.dptr(us), _lib.dptr(sc), _lib.dptr(lb), _lib.dptr(ub), _lib.dptr(out),
-                                 _lib.stream_ptr())
+        dv = self._dev
+        if tuple(x.shape) != tuple(xs.shape) or tuple(us.shape) != (x.shape[0], self._nu):
+            raise ValueError("x, xs must be (B, Nx) and us (B, Nu)")
+        rc = L.nnmpc_mlp_forward(self._handle, x.shape[0], _lib.dptr(x, device=dv), _lib.dptr(uprev, device=dv),
+                                 _lib.dptr(xs, device=dv), _lib.dptr(us, device=dv), _lib.dptr(sc, device=dv),
+                                 _lib.dptr(lb, device=dv), _lib.dptr(ub, device=dv), _lib.dptr(out, device=dv),
+                                 _lib.stream_ptr(dv))
         _lib.check(rc, "nnmpc_mlp_forward")
         return out
 

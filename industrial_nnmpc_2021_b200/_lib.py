@@ -48,6 +48,7 @@ SIGNATURES = {
     "nnmpc_sim_set_cadence": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_set_tail_rows": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_set_exact_gemm": (C.c_int, [vp, C.c_int]),
+    "nnmpc_sim_set_capture": (C.c_int, [vp, vp, vp]),
     "nnmpc_sim_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
                                 C.c_int, C.c_int, vp]),
@@ -64,7 +65,8 @@ SIGNATURES = {
                                 vp, vp]),
 }
 
-NNMPC_WARN_MAXITER = 1
+NNMPC_WARN_MAXITER = 1      # warnings are a bit mask (include/nnmpc.h)
+NNMPC_WARN_TARGET = 2
 _lib = None
 
 
@@ -91,11 +93,16 @@ def lib():
 
 
 def check(rc, what=""):
-    """Raise on a negative status; return True when the call only warned (max_iter reached)."""
+    """Raise on a negative status and on a target-selector solve that missed its optimum (a wrong
+    target would silently corrupt everything built on it); return True when some regulator QP
+    reached max_iter (its kkt entry tells which)."""
     if rc < 0:
         msg = lib().nnmpc_last_error().decode(errors="replace")
         raise NnmpcError(f"{what} failed (status {rc}): {msg}")
-    return rc == NNMPC_WARN_MAXITER
+    if rc & NNMPC_WARN_TARGET:
+        raise NnmpcError(f"{what}: a target-selector solve did not reach its optimum (active-set stall or "
+                         "non-finite data)")
+    return bool(rc & NNMPC_WARN_MAXITER)
 
 
 def host(a):
@@ -108,13 +115,25 @@ def hptr(a):
     return None if a is None else a.ctypes.data_as(vp)
 
 
-def dptr(t):
-    """void* of a contiguous CUDA torch tensor (or None)."""
+def dptr(t, dtype=None, device=None):
+    """void* of a contiguous CUDA torch tensor (or None).  The C ABI reinterprets the bytes, so the
+    element type (default float64) and, when given, the device index are checked here."""
     if t is None:
         return None
+    import torch
+    want = torch.float64 if dtype is None else dtype
     if not t.is_cuda or not t.is_contiguous():
         raise NnmpcError("expected a contiguous CUDA tensor")
+    if t.dtype != want:
+        raise NnmpcError(f"expected a {want} tensor, got {t.dtype}")
+    if device is not None and t.device.index != device:
+        raise NnmpcError(f"tensor lives on cuda:{t.device.index}, the handle on cuda:{device}")
     return vp(t.data_ptr())
+
+
+def dptr_i32(t, device=None):
+    import torch
+    return dptr(t, torch.int32, device)
 
 
 def prof_enable(on=True):
@@ -148,6 +167,7 @@ def prof_readn(nchan=4, reset=True):
 PRECISION = {"f64": 0, "mixed": 1}
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on the handle's device."""
     import torch
-    return vp(torch.cuda.current_stream().cuda_stream)
+    return vp(torch.cuda.current_stream(device).cuda_stream)

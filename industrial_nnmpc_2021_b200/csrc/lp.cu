@@ -31,7 +31,7 @@ int device_sm_count(int device) {
   return cache[device & 63];
 }
 
-int lp_state_ensure(LpState* s, long long B, int n) {
+int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st) {
   if (B <= s->cap && n == s->n) return 0;
   const long long cap = B > s->cap ? B : s->cap;
   s->n = n;
@@ -45,7 +45,7 @@ int lp_state_ensure(LpState* s, long long B, int n) {
   const long long cap_pad = (cap + 2 * lp::BM - 1) / (2 * lp::BM) * (2 * lp::BM);
   for (int b = 0; b < 2; ++b) {
     NNMPC_TRY(s->D[b].ensure((size_t)cap_pad * s->ldd));
-    NNMPC_CUDA(cudaMemset(s->D[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half)));
+    NNMPC_CUDA(cudaMemsetAsync(s->D[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half), st));   // ordered before the first writer on st
     if (!lp::make_tmap_f16(&s->tmD[b], s->D[b].p, cap_pad, s->ldd, s->ldd, lp::BM))
       return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the increment buffers");
   }

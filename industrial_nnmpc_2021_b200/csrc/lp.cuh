@@ -36,7 +36,7 @@ __device__ __forceinline__ double pow2_scale(double est) {
 
 int device_sm_count(int device);
 int lp_split_operator(const double* T_dev, int n, double tmax, LpOperator* op, cudaStream_t st);
-int lp_state_ensure(LpState* s, long long B, int n);
+int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st);
 
 // rows listed in rows[0..*count): w = 2 clip(v) - v into W (the FP64 anchor GEMM operand), E = 0
 int lp_anchor_prep(const int* rows, const int* count, int max_rows, const double* V, double* W, LpState* s,

@@ -138,7 +138,7 @@ int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op,
   return 0;
 }
 
-int oz_rows_ensure(OzRows* r, long long cap, int ncols) {
+int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st) {
   const long long ldb = ((long long)ncols + oz::BKB - 1) / oz::BKB * oz::BKB;
   const long long cap_pad = (cap + oz::BM - 1) / oz::BM * oz::BM;
   if (cap_pad <= r->cap_pad && ldb == r->ldb && ncols == r->ncols) return 0;
@@ -146,8 +146,8 @@ int oz_rows_ensure(OzRows* r, long long cap, int ncols) {
   const size_t bytes = (size_t)OZ_NS * cp * ldb;
   NNMPC_TRY(r->S.ensure(bytes));
   NNMPC_TRY(r->fscale.ensure((size_t)cp));
-  NNMPC_CUDA(cudaMemset(r->S.p, 0, bytes));      // the k-padding stays zero: the slicing kernel writes ncols bytes per row
-  NNMPC_CUDA(cudaMemset(r->fscale.p, 0, (size_t)cp * sizeof(double)));
+  NNMPC_CUDA(cudaMemsetAsync(r->S.p, 0, bytes, st));      // the k-padding stays zero: the slicing kernel writes ncols bytes per row
+  NNMPC_CUDA(cudaMemsetAsync(r->fscale.p, 0, (size_t)cp * sizeof(double), st));
   if (!oz::make_tmap_u8(&r->tm, r->S.p, OZ_NS * cp, ldb, ldb, oz::BM))
     return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the sample digit planes");
   r->cap_pad = cp; r->ldb = ldb; r->ncols = ncols;
@@ -232,7 +232,7 @@ int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
   OzOperator op;
   OzRows rows;
   int rc = oz_slice_operator(Bt, N, K, &op, st);
-  if (rc == 0) rc = oz_rows_ensure(&rows, M, K);
+  if (rc == 0) rc = oz_rows_ensure(&rows, M, K, st);
   if (rc == 0) rc = oz_slice_rows(&rows, nullptr, nullptr, M, A, K, st);
   if (rc == 0) rc = oz_apply<OZ_LMAX, OzEpiStore>(&op, &rows, M, nullptr, OzEpiStore::Params{C, N}, dev, st);
   if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess)
@@ -254,7 +254,7 @@ int nnmpc_oz_gemm_bench(int M, int N, int K, const double* A, const double* Bt, 
   OzOperator op;
   OzRows rows;
   int rc = oz_slice_operator(Bt, N, K, &op, st);
-  if (rc == 0) rc = oz_rows_ensure(&rows, M, K);
+  if (rc == 0) rc = oz_rows_ensure(&rows, M, K, st);
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   for (int w = 0; w < 2 && rc == 0; ++w) {

@@ -32,7 +32,7 @@ struct OzRows {
 };
 
 int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st);
-int oz_rows_ensure(OzRows* r, long long cap, int ncols);
+int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st);
 // x = Top w - c for the listed rows (W, C, X are B x n with the sample row as physical row)
 int oz_anchor(const OzOperator* top, OzRows* r, const int* rows, const int* count, int max_rows, const double* W,
               const double* C, double* X, int n, int device, cudaStream_t st);

@@ -190,7 +190,7 @@ int qp_solve_device(nnmpc_qp* h, int B, const double* x0, const double* lb, cons
     const bool prof = prof_begin(&span, st);
     for (int k = 0; k < chunk; ++k) {
       gi.A = Wc;
-      EpiAdmm::Params ep{V, h->C.p, Wn, u, lb, ub, n, nu, h->alpha, k == chunk - 1 ? 1 : 0, nullptr};
+      EpiAdmm::Params ep{V, h->C.p, Wn, u, lb, ub, n, nu, h->alpha, k == chunk - 1 ? 1 : 0, nullptr, nullptr, 0};
       NNMPC_TRY(gemm_auto<EpiAdmm>(gi, ep, st));
       double* t = Wc; Wc = Wn; Wn = t;
     }
@@ -315,14 +315,21 @@ int nnmpc_qp_create(nnmpc_qp_t** out, int n, int nxa, int nu, int N, const doubl
     }
     if (a > h->p_norm_inf) h->p_norm_inf = a;
   }
-  NNMPC_TRY(upload(&h->P, P_host, (size_t)n * n));
-  NNMPC_TRY(upload(&h->Top, Top_host, (size_t)n * n));
-  NNMPC_TRY(upload(&h->tq, tq_host, (size_t)n * nxa));
-  NNMPC_TRY(upload(&h->Mtq, Mtq_host, (size_t)n * nxa));
-  NNMPC_TRY(upload(&h->Kunc, Kunc_host, (size_t)n * nxa));
-  NNMPC_CUDA(cudaMalloc((void**)&h->counts, 4 * sizeof(int)));
-  NNMPC_CUDA(cudaMalloc((void**)&h->iter_sum, sizeof(unsigned long long)));
-  NNMPC_CUDA(cudaMallocHost((void**)&h->h_pinned, 8 * sizeof(int)));
+  h->P = h->Top = h->tq = h->Mtq = h->Kunc = nullptr;
+  h->counts = nullptr; h->iter_sum = nullptr; h->h_pinned = nullptr;
+  int rc = upload(&h->P, P_host, (size_t)n * n);
+  if (rc == 0) rc = upload(&h->Top, Top_host, (size_t)n * n);
+  if (rc == 0) rc = upload(&h->tq, tq_host, (size_t)n * nxa);
+  if (rc == 0) rc = upload(&h->Mtq, Mtq_host, (size_t)n * nxa);
+  if (rc == 0) rc = upload(&h->Kunc, Kunc_host, (size_t)n * nxa);
+  if (rc == 0 && (cudaMalloc((void**)&h->counts, 4 * sizeof(int)) != cudaSuccess ||
+                  cudaMalloc((void**)&h->iter_sum, sizeof(unsigned long long)) != cudaSuccess ||
+                  cudaMallocHost((void**)&h->h_pinned, 8 * sizeof(int)) != cudaSuccess))
+    rc = set_error(NNMPC_ERR_NOMEM, "nnmpc_qp_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc < 0) {          // a half-built handle is released, not leaked
+    nnmpc_qp_destroy(h);
+    return rc;
+  }
   *out = h;
   return 0;
 }
@@ -355,8 +362,11 @@ int nnmpc_qp_destroy(nnmpc_qp_t* h) {
   if (!h) return 0;
   DeviceGuard dg(h->device);
   if (h->rinv) cudaFree(h->rinv);
-  cudaFree(h->P); cudaFree(h->Top); cudaFree(h->tq); cudaFree(h->Mtq); cudaFree(h->Kunc);
-  cudaFree(h->counts); cudaFree(h->iter_sum); cudaFreeHost(h->h_pinned);
+  for (double* p : {h->P, h->Top, h->tq, h->Mtq, h->Kunc})
+    if (p) cudaFree(p);
+  if (h->counts) cudaFree(h->counts);
+  if (h->iter_sum) cudaFree(h->iter_sum);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->V.release(); h->W0.release(); h->W1.release(); h->C.release(); h->Ql.release();
   h->part_max.release(); h->part_sum.release(); h->rows0.release(); h->rows1.release();
   h->hx0.release(); h->hlb.release(); h->hub.release(); h->hu.release(); h->hcost.release(); h->hkkt.release();

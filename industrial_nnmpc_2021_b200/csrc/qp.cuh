@@ -73,6 +73,8 @@ struct EpiAdmm {
     double alpha;
     int write_z;
     unsigned long long* dres;  // nullable, one per physical row
+    const int* state;          // nullable: a row takes part iff state[row] == iter_state (closed-loop engine tail)
+    int iter_state;
   };
   Params p;
   double dmax;
@@ -80,6 +82,7 @@ struct EpiAdmm {
   __device__ void begin_row() { dmax = 0.0; }
   __device__ void apply(int pr, int, int col, double a0, double a1, bool ok0, bool ok1) {
     if (!ok0) return;
+    if (p.state && p.state[pr] != p.iter_state) return;
     const long long off = (long long)pr * p.n + col;
     const double* lbr = p.lb + (long long)pr * p.nu;
     const double* ubr = p.ub + (long long)pr * p.nu;
@@ -111,6 +114,7 @@ struct EpiAdmm {
   }
   __device__ void finish_row(int pr, int, int, bool rok) {
     if (!p.dres) return;
+    if (p.state && rok && p.state[pr] != p.iter_state) rok = false;
     double m = dmax;
     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));

@@ -37,7 +37,9 @@ enum Counter { N_ACTIVE = 0, N_CAND = 1, N_DONE = 2, N_RENEW = 3, N_FINISHED = 4
                // mixed mode: effective row counts of this loop's launches (0 switches a launch off on the device)
                E_ANCHOR = 7, E_LP = 8, E_TAIL = 9, LP_LEN0 = 10, LP_LEN1 = 11,
                // chunk queue: slots that finished a trajectory chunk this loop, cold (re)starts, next chunk to hand out
-               N_SWAP = 12, N_COLD = 13, NEXT_CHUNK = 14, N_COUNTERS = 16 };
+               N_SWAP = 12, N_COLD = 13, NEXT_CHUNK = 14,
+               // a target-selector solve that did not reach its optimum (active-set stall or non-finite data)
+               F_TS_FAIL = 15, N_COUNTERS = 16 };
 constexpr int POLL_RING = 4;
 }  // namespace nnmpc
 
@@ -73,6 +75,10 @@ struct nnmpc_sim {
   // staging for the host entry point
   nnmpc::DevBuf<double> h_sp, h_dist, h_x, h_uprev, h_xs, h_us, h_u, h_kkt, h_xio, h_upio;
   nnmpc::DevBuf<int> h_iters;
+  // optional sinks of the next runs (nnmpc_sim_set_capture): full optimal sequence and optimal cost of every QP
+  double* cap_useq;                 // device [B][T][n] or null
+  double* cap_cost;                 // device [B][T] or null
+  nnmpc::DevBuf<double> gcap;       // f64 mode with capture: the gradient g = P z + q of the last check per slot
 };
 
 namespace nnmpc {
@@ -304,12 +310,16 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
   }
 }
 
-// first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows
+// first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows; with capture sinks also the
+// whole optimal sequence (deviation variables + us per stage, as DenseQPRegulator.solve returns it through
+// get_control_sequence, linearMPC.py:689) and the optimal cost 1/2 z'Pz + q'z = 1/2 z'(g + q) from the gradient
+// g = P z + q of the check that certified z
 __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
                           const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
                           const double* __restrict__ xcur, const double* __restrict__ dist,
                           double* __restrict__ row_u, double* __restrict__ upcur, double* __restrict__ xin, int n,
-                          int nx, int nu, int nd, int kin_ld) {
+                          int nx, int nu, int nd, int kin_ld, const double* __restrict__ G, const double* __restrict__ Ql,
+                          double* __restrict__ cap_useq, double* __restrict__ cap_cost) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   const long long o = (long long)chunk[s] * T + tcur[s];
@@ -328,6 +338,22 @@ __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ 
       v = 0.0;
     }
     xin[s * kin_ld + c] = v;
+  }
+  if (cap_useq)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) cap_useq[o * n + j] = Z[s * n + j] + us[o * nu + (j % nu)];
+  if (cap_cost) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) acc += Z[s * n + j] * (G[s * n + j] + Ql[s * n + j]);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      cap_cost[o] = 0.5 * t;
+    }
   }
 }
 
@@ -421,18 +447,22 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int
   }
 }
 
-// mixed mode, tail: the live rows iterate in FP64; the operand is rebuilt from v every loop
+// mixed mode, tail: the live rows iterate in FP64; the operand is rebuilt from v every loop.  Rows waiting for an
+// exact phase (candidates, re-anchored rows) sit the pass out exactly as they do in a tensor-core pass.
 __global__ void k_tail_prep(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
                             const double* __restrict__ V, double* __restrict__ W, const double* __restrict__ lb,
                             const double* __restrict__ ub, int n, int nu) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
+  const int st = state[s];
+  if (st != SLOT_ITER && st != SLOT_ANCHOR) return;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int k = j % nu;
     const double v = V[s * n + j];
     W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
   }
-  if (threadIdx.x == 0 && state[s] == SLOT_ANCHOR) state[s] = SLOT_ITER;
+  __syncthreads();
+  if (threadIdx.x == 0 && st == SLOT_ANCHOR) state[s] = SLOT_ITER;
 }
 
 // slots that finished a chunk: hand its final state back, load the initial state of the chunk taken next
@@ -526,6 +556,7 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
     e.counts[N_RENEW] = S;
     e.counts[N_FINISHED] = 0;
     e.counts[F_MAXITER] = 0;
+    e.counts[F_TS_FAIL] = 0;
     e.counts[N_ANCHOR] = e.mixed ? S : 0;
     e.counts[N_SWAP] = 0;
     e.counts[N_COLD] = cold_all ? S : 0;
@@ -588,14 +619,17 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     if (!q->rinv)
       return set_error(NNMPC_ERR_BADARG, "mixed precision needs the ADMM penalty vector: call nnmpc_qp_set_penalty first");
     if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
-    NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n));
+    NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n, st));
     if (h->exact_oz) {
       if (!q->ozP.ready) NNMPC_TRY(oz_slice_operator(q->P, n, n, &q->ozP, st));
       if (!q->ozTop.ready) NNMPC_TRY(oz_slice_operator(q->Top, n, n, &q->ozTop, st));
-      NNMPC_TRY(oz_rows_ensure(&h->ozr, h->cap, n));
+      NNMPC_TRY(oz_rows_ensure(&h->ozr, h->cap, n, st));
     }
   }
   const bool oz = mixed && h->exact_oz;
+  // gradient g = P z + q of the exact check: the mixed mode re-anchors from it; the cost capture needs it in any mode
+  if (!mixed && h->cap_cost) NNMPC_TRY(h->gcap.ensure((size_t)h->cap * n));
+  double* gbuf = mixed ? h->lps.Wl.p : (h->cap_cost ? h->gcap.p : nullptr);
   NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
   if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
@@ -626,7 +660,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     F.us_prev = h->us_prev.p; F.dus = h->dus.p;
     F.row_x = ox; F.row_uprev = ouprev; F.row_stride_x = nx; F.row_stride_u = nu;
     TsIndex ix{e.l_renew, e.counts + N_RENEW, e.tcur, T, e.chunk};
-    NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, st));
+    NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, e.counts + F_TS_FAIL, st));
     GemmOperands g{};
     g.A = h->x0.p; g.lda = nxa; g.ldb = nxa; g.M = B; g.N = n; g.K = nxa; g.rows = e.l_renew;
     g.m_count = e.counts + N_RENEW;
@@ -701,14 +735,14 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       GemmOperands gi{};
       gi.A = q->W0.p; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
       gi.N = n; gi.K = n; gi.rows = e.l_active; gi.m_count = e.counts + E_TAIL;
-      EpiAdmm::Params ept{h->V.p, q->C.p, q->W1.p, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres};
+      EpiAdmm::Params ept{h->V.p, q->C.p, q->W1.p, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres, e.state, SLOT_ITER};
       NNMPC_TRY(gemm_by_count<EpiAdmm>(gi, ept, st));
       if (prof64b) prof_end(span64, st, 0.0, 1, 2);
     } else {
       GemmOperands gi{};
       gi.A = Wc; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = B; gi.N = n; gi.K = n; gi.rows = e.l_active;
       gi.m_count = e.counts + N_ACTIVE;
-      EpiAdmm::Params ep{h->V.p, q->C.p, Wn, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres};
+      EpiAdmm::Params ep{h->V.p, q->C.p, Wn, nullptr, h->lb.p, h->ub.p, n, nu, q->alpha, 0, e.dres, nullptr, 0};
       ProfSpan span;
       const bool prof = prof_begin(&span, st);
       NNMPC_TRY(gemm_by_count<EpiAdmm>(gi, ep, st));
@@ -727,7 +761,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       GemmOperands gv{};
       gv.A = h->Z.p; gv.lda = n; gv.Bt = q->P; gv.ldb = n; gv.M = B; gv.N = n; gv.K = n; gv.rows = e.l_cand;
       gv.m_count = e.counts + N_CAND;
-      EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu, mixed ? h->lps.Wl.p : nullptr};
+      EpiVerifyMax::Params ev{h->Z.p, q->Ql.p, h->lb.p, h->ub.p, e.kres, n, nu, gbuf};
       ProfSpan span64;
       const bool prof64 = mixed && prof_begin(&span64, st);
       if (oz) NNMPC_TRY(oz_verify(&q->ozP, &h->ozr, e.l_cand, e.counts + N_CAND, B, h->Z.p, q->Ql.p, h->lb.p, h->ub.p,
@@ -747,7 +781,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     }
     // 5. first move, dataset row, plant step for the done rows
     k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
-                                 h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld);
+                                 h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld, gbuf, q->Ql.p, h->cap_useq,
+                                 h->cap_cost);
     count_launch(2);
     {
       GemmOperands gp{};
@@ -787,7 +822,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   NNMPC_CUDA(cudaGetLastError());
   if (h->pin[N_FINISHED] < Btot)
     return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], Btot);
-  if (h->pin[F_MAXITER]) rc_warn = NNMPC_WARN_MAXITER;
+  if (h->pin[F_MAXITER]) rc_warn |= NNMPC_WARN_MAXITER;
+  if (h->pin[F_TS_FAIL]) rc_warn |= NNMPC_WARN_TARGET;
   g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
   prof_add_flops(2.0 * n * (double)n * (double)*pin64);                               // iteration passes
   prof_add_flops(2.0 * n * (double)n * (double)(pin64[1] + pin64[2]), 1);             // exact anchors + checks (FP64-equivalent)
@@ -821,30 +857,43 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->kin_ld = (kin + 1) & ~1;
   h->cap = 0;
   h->warm_B = 0;
+  h->ABd = nullptr; h->counts = nullptr; h->rowiters = nullptr; h->stats = nullptr; h->pin = nullptr;
+  for (int i = 0; i < POLL_RING; ++i) h->poll_ev[i] = nullptr;
   h->mixed = 0;
   h->tail_rows = -1;
   h->slot_cap = 8192;
   h->cadence = 4;
   h->exact_oz = 1;
+  h->cap_useq = h->cap_cost = nullptr;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
   double* tmp = new (std::nothrow) double[(size_t)nx * h->kin_ld];
-  if (!tmp) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+  if (!tmp) {
+    delete h;
+    return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+  }
   for (int r = 0; r < nx; ++r) {
     for (int c = 0; c < kin; ++c) tmp[(size_t)r * h->kin_ld + c] = ABd_host[(size_t)r * kin + c];
     for (int c = kin; c < h->kin_ld; ++c) tmp[(size_t)r * h->kin_ld + c] = 0.0;
   }
   int rc = upload(&h->ABd, tmp, (size_t)nx * h->kin_ld);
   delete[] tmp;
-  if (rc < 0) return rc;
-  NNMPC_CUDA(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)));
-  NNMPC_CUDA(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)));
-  NNMPC_CUDA(cudaMalloc((void**)&h->stats, 2 * sizeof(unsigned long long)));
-  NNMPC_CUDA(cudaMemset(h->stats, 0, 2 * sizeof(unsigned long long)));
-  NNMPC_CUDA(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 4 * sizeof(unsigned long long)));
-  for (int i = 0; i < POLL_RING; ++i) NNMPC_CUDA(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming));
+  auto cu = [&](cudaError_t e, const char* what) {
+    if (rc == 0 && e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "nnmpc_sim_create: %s: %s", what, cudaGetErrorString(e));
+  };
+  if (rc == 0) cu(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)), "cudaMalloc");
+  if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMalloc((void**)&h->stats, 2 * sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMemset(h->stats, 0, 2 * sizeof(unsigned long long)), "cudaMemset");
+  if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 4 * sizeof(unsigned long long)), "cudaMallocHost");
+  for (int i = 0; i < POLL_RING && rc == 0; ++i) cu(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming), "cudaEventCreate");
+  if (rc < 0) {          // a half-built handle is released, not leaked
+    cudaGetLastError();
+    nnmpc_sim_destroy(h);
+    return rc;
+  }
   *out = h;
   return 0;
 }
@@ -852,15 +901,16 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
 int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   if (!h) return 0;
   DeviceGuard dg(h->device);
-  cudaFree(h->ABd);
-  cudaFree(h->counts);
-  cudaFree(h->rowiters);
-  cudaFree(h->stats);
-  cudaFreeHost(h->pin);
+  if (h->ABd) cudaFree(h->ABd);
+  if (h->counts) cudaFree(h->counts);
+  if (h->rowiters) cudaFree(h->rowiters);
+  if (h->stats) cudaFree(h->stats);
+  if (h->pin) cudaFreeHost(h->pin);
   h->lps.release();
   h->ozr.release();
   h->lp_layout.release();
-  for (int i = 0; i < POLL_RING; ++i) cudaEventDestroy(h->poll_ev[i]);
+  for (int i = 0; i < POLL_RING; ++i)
+    if (h->poll_ev[i]) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
   h->Z.release(); h->xin.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
   h->chunk.release(); h->cold.release();
@@ -868,6 +918,7 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   h->h_sp.release(); h->h_dist.release(); h->h_x.release(); h->h_uprev.release(); h->h_xs.release();
   h->h_us.release(); h->h_u.release(); h->h_kkt.release(); h->h_xio.release(); h->h_upio.release();
   h->h_iters.release();
+  h->gcap.release();
   delete h;
   return 0;
 }
@@ -906,6 +957,13 @@ int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_exact_gemm: null handle");
   if (mode != 0 && mode != 1) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_exact_gemm: mode must be 0 (DMMA) or 1 (INT8 slices)");
   h->exact_oz = mode;
+  return 0;
+}
+
+int nnmpc_sim_set_capture(nnmpc_sim_t* h, double* useq_dev, double* cost_dev) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_capture: null handle");
+  h->cap_useq = useq_dev;
+  h->cap_cost = cost_dev;
   return 0;
 }
 
@@ -953,8 +1011,13 @@ int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev
   if (nd > 0) NNMPC_CUDA(cudaMemcpyAsync(h->h_dist.p, disturbances, bt * nd * 8, cudaMemcpyHostToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->h_xio.p, x_io, (size_t)B * nx * 8, cudaMemcpyHostToDevice, st));
   NNMPC_CUDA(cudaMemcpyAsync(h->h_upio.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyHostToDevice, st));
+  double* const keep_useq = h->cap_useq;
+  double* const keep_cost = h->cap_cost;
+  h->cap_useq = h->cap_cost = nullptr;       // the capture sinks belong to the device entry point
   int rc = sim_run_device(h, B, T, h->h_xio.p, h->h_upio.p, h->h_sp.p, h->h_dist.p, h->h_x.p, h->h_uprev.p, h->h_xs.p,
                           h->h_us.p, h->h_u.p, h->h_iters.p, h->h_kkt.p, tol, max_iter, resume, st);
+  h->cap_useq = keep_useq;
+  h->cap_cost = keep_cost;
   if (rc < 0) return rc;
   NNMPC_CUDA(cudaMemcpyAsync(x, h->h_x.p, bt * nx * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(xs, h->h_xs.p, bt * nx * 8, cudaMemcpyDeviceToHost, st));

@@ -30,6 +30,7 @@ struct TsParams {
   TsFused f;
   int indexed;
   TsIndex ix;
+  int* fail;   // nullable device flag, set when a solve stalls at the iteration cap or produces non-finite targets
 };
 
 __device__ __forceinline__ double warp_min_d(double v) {
@@ -187,8 +188,13 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
     }
     uvec[lane] = u;
     __syncwarp();
+    // The reference's cvxopt call would report a status (linearMPC.py:304-306 ignores it); here a solve that ran
+    // out of active-set steps or went non-finite (NaN pivot of the masked Cholesky, NaN/Inf inputs) raises the
+    // flag the callers turn into NNMPC_WARN_TARGET, and its iteration count is written negated.
+    const bool bad = !done || __any_sync(FULLMASK, act && !(fabs(u) <= 1.7e308));
+    if (bad && p.fail && lane == 0) atomicExch(p.fail, 1);
     if (act) p.us[(long long)b * p.us_stride + lane] = u;
-    if (p.iters && lane == 0) p.iters[(long long)b * p.iters_stride] = it;
+    if (p.iters && lane == 0) p.iters[(long long)b * p.iters_stride] = bad ? -it - 1 : it;
     const TsFused& F = p.f;
     for (int r = lane; r < nx; r += 32) {
       double acc = 0.0;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
                     long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
                     int* iters, long long iters_stride, const TsFused* fused, const TsIndex* index,
-                    cudaStream_t st) {
+                    int* fail_flag, cudaStream_t st) {
   if (B <= 0) return 0;
   TsParams p{};
   p.B = B; p.nx = h->nx; p.nu = h->nu; p.ny = h->ny; p.nd = h->nd;
@@ -234,6 +240,7 @@ int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride,
   if (fused) p.f = *fused;
   p.indexed = index ? 1 : 0;
   if (index) p.ix = *index;
+  p.fail = fail_flag;
   int blocks = (B + TS_WARPS - 1) / TS_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_target_selector<<<blocks, TS_WARPS * 32, 0, st>>>(p);
@@ -263,14 +270,21 @@ int nnmpc_ts_create(nnmpc_ts_t** out, int nx, int nu, int ny, int nd, const doub
   nnmpc_ts* h = new (std::nothrow) nnmpc_ts();
   if (!h) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
   h->nx = nx; h->nu = nu; h->ny = ny; h->nd = nd; h->device = device;
-  NNMPC_TRY(upload(&h->Ht, Ht, (size_t)nu * nu));
-  NNMPC_TRY(upload(&h->Fy, Fy, (size_t)nu * ny));
-  NNMPC_TRY(upload(&h->Fd, Fd, (size_t)nu * (nd > 0 ? nd : 1)));
-  NNMPC_TRY(upload(&h->f0, f0, (size_t)nu));
-  NNMPC_TRY(upload(&h->Gx, Gx, (size_t)nx * nu));
-  NNMPC_TRY(upload(&h->Gd, Gd, (size_t)nx * (nd > 0 ? nd : 1)));
-  NNMPC_TRY(upload(&h->ulb, ulb, (size_t)nu));
-  NNMPC_TRY(upload(&h->uub, uub, (size_t)nu));
+  h->Ht = h->Fy = h->Fd = h->f0 = h->Gx = h->Gd = h->ulb = h->uub = nullptr;
+  int rc = upload(&h->Ht, Ht, (size_t)nu * nu);
+  if (rc == 0) rc = upload(&h->Fy, Fy, (size_t)nu * ny);
+  if (rc == 0) rc = upload(&h->Fd, Fd, (size_t)nu * (nd > 0 ? nd : 1));
+  if (rc == 0) rc = upload(&h->f0, f0, (size_t)nu);
+  if (rc == 0) rc = upload(&h->Gx, Gx, (size_t)nx * nu);
+  if (rc == 0) rc = upload(&h->Gd, Gd, (size_t)nx * (nd > 0 ? nd : 1));
+  if (rc == 0) rc = upload(&h->ulb, ulb, (size_t)nu);
+  if (rc == 0) rc = upload(&h->uub, uub, (size_t)nu);
+  if (rc == 0 && cudaMalloc((void**)&h->fail, sizeof(int)) != cudaSuccess)
+    rc = set_error(NNMPC_ERR_NOMEM, "nnmpc_ts_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc < 0) {          // a half-built handle is released, not leaked
+    nnmpc_ts_destroy(h);
+    return rc;
+  }
   *out = h;
   return 0;
 }
@@ -280,6 +294,7 @@ int nnmpc_ts_destroy(nnmpc_ts_t* h) {
   DeviceGuard dg(h->device);
   cudaFree(h->Ht); cudaFree(h->Fy); cudaFree(h->Fd); cudaFree(h->f0); cudaFree(h->Gx); cudaFree(h->Gd);
   cudaFree(h->ulb); cudaFree(h->uub);
+  if (h->fail) cudaFree(h->fail);
   h->hysp.release(); h->hd.release(); h->hxs.release(); h->hus.release(); h->hiters.release();
   delete h;
   return 0;
@@ -291,7 +306,7 @@ int nnmpc_ts_solve(nnmpc_ts_t* h, int B, const double* ysp, long long ysp_stride
   if (!h || !ysp || !d || !xs || !us) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: null argument");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_solve: negative batch");
   DeviceGuard dg(h->device);
-  return ts_solve_device(h, B, ysp, ysp_stride, d, d_stride, xs, h->nx, us, h->nu, iters, 1, nullptr, nullptr,
+  return ts_solve_device(h, B, ysp, ysp_stride, d, d_stride, xs, h->nx, us, h->nu, iters, 1, nullptr, nullptr, nullptr,
                          (cudaStream_t)stream);
 }
 
@@ -310,13 +325,16 @@ int nnmpc_ts_solve_host(nnmpc_ts_t* h, int B, const double* ysp, const double* d
   cudaStream_t st = 0;
   NNMPC_CUDA(cudaMemcpyAsync(h->hysp.p, ysp, b * h->ny * 8, cudaMemcpyHostToDevice, st));
   if (h->nd > 0) NNMPC_CUDA(cudaMemcpyAsync(h->hd.p, d, b * h->nd * 8, cudaMemcpyHostToDevice, st));
+  NNMPC_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), st));
   NNMPC_TRY(ts_solve_device(h, B, h->hysp.p, h->ny, h->hd.p, h->nd, h->hxs.p, h->nx, h->hus.p, h->nu, h->hiters.p, 1,
-                            nullptr, nullptr, st));
+                            nullptr, nullptr, h->fail, st));
+  int failed = 0;
+  NNMPC_CUDA(cudaMemcpyAsync(&failed, h->fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(xs, h->hxs.p, b * h->nx * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(us, h->hus.p, b * h->nu * 8, cudaMemcpyDeviceToHost, st));
   if (iters) NNMPC_CUDA(cudaMemcpyAsync(iters, h->hiters.p, b * 4, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return failed ? NNMPC_WARN_TARGET : 0;
 }
 
 }  // extern "C"

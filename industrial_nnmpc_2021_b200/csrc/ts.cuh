@@ -4,6 +4,7 @@
 
 struct nnmpc_ts {
   int nx, nu, ny, nd, device;
+  int* fail = nullptr;                               // device flag: some solve of the last call missed its optimum
   double *Ht, *Fy, *Fd, *f0, *Gx, *Gd, *ulb, *uub;  // device operators
   nnmpc::DevBuf<double> hysp, hd, hxs, hus;          // staging for the host entry point
   nnmpc::DevBuf<int> hiters;
@@ -44,6 +45,6 @@ struct TsIndex {
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
                     long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
                     int* iters, long long iters_stride, const TsFused* fused, const TsIndex* index,
-                    cudaStream_t st);
+                    int* fail_flag, cudaStream_t st);
 
 }  // namespace nnmpc

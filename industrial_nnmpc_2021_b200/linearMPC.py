@@ -35,9 +35,8 @@ def _device_index(device):
     torch = _torch()
     if not torch.cuda.is_available():
         raise _lib.NnmpcError("no CUDA device visible: this package has no CPU fallback")
-    if device is None:
-        return torch.cuda.current_device()
-    return torch.device(device).index or 0
+    idx = None if device is None else torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
 
 
 # ------------------------------------------------------------------------------ stability helpers
@@ -197,13 +196,14 @@ class TargetSelector:
         else:
             torch = _torch()
             YSP, D = YSP.contiguous(), D.contiguous()
-            Bn = YSP.shape[0]
+            Bn, dv = YSP.shape[0], self._dev
             xs = torch.empty((Bn, self.Nx), dtype=torch.float64, device=YSP.device)
             us = torch.empty((Bn, self.Nu), dtype=torch.float64, device=YSP.device)
             it = torch.empty(Bn, dtype=torch.int32, device=YSP.device)
-            rc = L.nnmpc_ts_solve(self._handle, Bn, _lib.dptr(YSP), self.Ny, _lib.dptr(D), self.Nd, _lib.dptr(xs),
-                                  _lib.dptr(us), _lib.dptr(it), _lib.stream_ptr())
-            _lib.check(rc, "nnmpc_ts_solve")
+            rc = L.nnmpc_ts_solve(self._handle, Bn, _lib.dptr(YSP, device=dv), self.Ny, _lib.dptr(D, device=dv), self.Nd,
+                                  _lib.dptr(xs, device=dv), _lib.dptr(us, device=dv), _lib.dptr_i32(it, dv),
+                                  _lib.stream_ptr(dv))
+            _lib.check(rc, "nnmpc_ts_solve")     # asynchronous: a failed sample carries a negative entry in `it`
         return (xs, us, it) if return_iters else (xs, us)
 
     def solve(self, ysp, dhats):
@@ -372,6 +372,8 @@ class DenseQPRegulator:
             if UB is None:
                 UB = torch.as_tensor(self.uub.reshape(1, -1), device=dev).repeat(Bn, 1)
             LB, UB = LB.contiguous(), UB.contiguous()
+            if tuple(LB.shape) != (Bn, self.Nu) or tuple(UB.shape) != (Bn, self.Nu):
+                raise ValueError("LB / UB must have shape (B, Nu)")
             U = torch.empty((Bn, n), dtype=torch.float64, device=dev)
             cost = torch.empty(Bn, dtype=torch.float64, device=dev)
             kkt = torch.empty(Bn, dtype=torch.float64, device=dev)
@@ -381,9 +383,11 @@ class DenseQPRegulator:
                 if tuple(warm_state.shape) != (Bn, n) or not warm_state.is_contiguous():
                     raise ValueError("warm_state must be a contiguous (B, n) CUDA tensor")
                 warm = 1 if getattr(warm_state, "_nnmpc_valid", False) else 0
-            rc = L.nnmpc_qp_solve(self._handle, Bn, _lib.dptr(X0p), _lib.dptr(LB), _lib.dptr(UB), _lib.dptr(U),
-                                  _lib.dptr(warm_state), warm, _lib.dptr(cost), _lib.dptr(kkt), _lib.dptr(iters),
-                                  float(tol), int(max_iter), _lib.stream_ptr())
+            dv = self._dev
+            rc = L.nnmpc_qp_solve(self._handle, Bn, _lib.dptr(X0p, device=dv), _lib.dptr(LB, device=dv),
+                                  _lib.dptr(UB, device=dv), _lib.dptr(U, device=dv), _lib.dptr(warm_state, device=dv),
+                                  warm, _lib.dptr(cost, device=dv), _lib.dptr(kkt, device=dv), _lib.dptr_i32(iters, dv),
+                                  float(tol), int(max_iter), _lib.stream_ptr(dv))
             warned = _lib.check(rc, "nnmpc_qp_solve")
             if warm_state is not None:
                 warm_state._nnmpc_valid = True
@@ -537,9 +541,10 @@ def _save_training_data(dictionary, filename):
 
 def load_training_data(filename):
     """H5pyTool.load_training_data (lib/python_utils.py:43-50) for either container."""
-    import os
-    if os.path.exists(filename + ".npz"):
-        with np.load(filename + ".npz") as z:
+    npz, h5 = filename + ".npz", filename
+    have_npz, have_h5 = os.path.exists(npz), os.path.exists(h5)
+    if have_npz and (not have_h5 or os.path.getmtime(npz) >= os.path.getmtime(h5)):    # the newer container wins
+        with np.load(npz) as z:
             return {k: np.asarray(z[k]) for k in z.files}
     import h5py
     with h5py.File(filename, "r") as f:
@@ -613,13 +618,22 @@ class ClosedLoopEngine:
             a = out.get(k)
             if not isinstance(a, kind) or tuple(a.shape) != shp:
                 raise ValueError(f"out[{k!r}] must be a {kind.__name__} of shape {shp}")
+            want = "int32" if k == "iters" else "float64"
+            if str(a.dtype).replace("torch.", "") != want:
+                raise ValueError(f"out[{k!r}] must have dtype {want}")
             contiguous = a.flags["C_CONTIGUOUS"] if isinstance(a, np.ndarray) else a.is_contiguous()
             if not contiguous:
                 raise ValueError(f"out[{k!r}] must be contiguous")
         return {k: out[k] for k in shapes}
 
-    def run(self, x0, uprev0, setpoints, disturbances, *, tol=None, max_iter=None, resume=False, out=None):
+    def run(self, x0, uprev0, setpoints, disturbances, *, tol=None, max_iter=None, resume=False, out=None,
+            capture=False):
         """Advance B trajectories T steps.
+
+        ``capture=True`` additionally returns ``useq`` (B,T,N*Nu) - the whole optimal input sequence of
+        every regulator QP, target added back, i.e. what ``get_control_sequence`` returns upstream
+        (linearMPC.py:689) - and ``cost`` (B,T), the optimal value in deviation variables.  Meant for
+        parity tests / diagnostics (N*Nu doubles per sample).
 
         ``resume=True`` says these are the same B trajectories as in the previous call (a long
         trajectory advanced slab by slab): step 0 is then warm-started from the kept solver
@@ -637,6 +651,15 @@ class ClosedLoopEngine:
         max_iter = reg.max_iter if max_iter is None else max_iter
         Bn, T = setpoints.shape[0], setpoints.shape[1]
         nx, nu = self.nx, self.nu
+        if tuple(setpoints.shape) != (Bn, T, self.ny) or tuple(disturbances.shape) != (Bn, T, self.nd):
+            raise ValueError(f"setpoints / disturbances must have shapes (B,T,{self.ny}) / (B,T,{self.nd})")
+        if capture and isinstance(setpoints, np.ndarray):      # the capture sinks live on the device entry point
+            torch = _torch()
+            f64 = dict(dtype=torch.float64, device=torch.device("cuda", self._dev))
+            res = self.run(torch.as_tensor(np.asarray(x0, float), **f64), torch.as_tensor(np.asarray(uprev0, float), **f64),
+                           torch.as_tensor(_lib.host(setpoints), **f64), torch.as_tensor(_lib.host(disturbances), **f64),
+                           tol=tol, max_iter=max_iter, resume=resume, capture=True)
+            return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
         if isinstance(setpoints, np.ndarray):
             sp, dist = _lib.host(setpoints), _lib.host(disturbances)
             xio = _lib.host(np.broadcast_to(np.asarray(x0, float).reshape(-1, nx), (Bn, nx))).copy()
@@ -663,9 +686,23 @@ class ClosedLoopEngine:
                        iters=torch.empty((Bn, T), dtype=torch.int32, device=dev),
                        kkt=torch.empty((Bn, T), **f64)) if out is None else self._check_out(out, Bn, T, torch.Tensor)
             out = dict(res)
-            rc = L.nnmpc_sim_run(self._handle, Bn, T, _lib.dptr(xio), _lib.dptr(uio), _lib.dptr(sp), _lib.dptr(dist),
-                                 *[_lib.dptr(out[k]) for k in ("x", "uprev", "xs", "us", "u", "iters", "kkt")],
-                                 float(tol), int(max_iter), int(bool(resume)), _lib.stream_ptr())
+            dv = self._dev
+            if sp.dtype != torch.float64 or dist.dtype != torch.float64:
+                raise ValueError("setpoints / disturbances must be float64 tensors")
+            if capture:
+                out["useq"] = torch.empty((Bn, T, reg.N * nu), **f64)
+                out["cost"] = torch.empty((Bn, T), **f64)
+                _lib.check(L.nnmpc_sim_set_capture(self._handle, _lib.dptr(out["useq"], device=dv),
+                                                   _lib.dptr(out["cost"], device=dv)), "nnmpc_sim_set_capture")
+            try:
+                rc = L.nnmpc_sim_run(self._handle, Bn, T, _lib.dptr(xio, device=dv), _lib.dptr(uio, device=dv),
+                                     _lib.dptr(sp, device=dv), _lib.dptr(dist, device=dv),
+                                     *[_lib.dptr(out[k], device=dv) for k in ("x", "uprev", "xs", "us", "u")],
+                                     _lib.dptr_i32(out["iters"], dv), _lib.dptr(out["kkt"], device=dv),
+                                     float(tol), int(max_iter), int(bool(resume)), _lib.stream_ptr(dv))
+            finally:
+                if capture:
+                    L.nnmpc_sim_set_capture(self._handle, None, None)
             out["maxiter_hit"] = _lib.check(rc, "nnmpc_sim_run")
         out["x_final"], out["uprev_final"] = xio, uio
         return out
@@ -676,6 +713,12 @@ def simulate_offline(task_number, process_number, data_filename, x0, uprev0, A, 
     """One trajectory chunk, reference signature (linearMPC.py:827-880); writes
     ``{task}-{process}-{data_filename}`` with keys x, uprev, xs, us, u, data_gen_time."""
     t0 = time.time()
+    # The reference shifts THESE bounds by the target for the regulator (:685-686) while the target selector keeps
+    # its own; both reference scripts pass the same pair.  The fused engine builds the regulator bounds from the
+    # target selector's, so different pairs would silently diverge from the reference: refuse them.
+    if not (np.array_equal(np.asarray(ulb), np.asarray(target_selector.ulb))
+            and np.array_equal(np.asarray(uub), np.asarray(target_selector.uub))):
+        raise NotImplementedError("simulate_offline: ulb/uub must equal the target selector's input bounds")
     regulator.ulb, regulator.uub = ulb, uub
     eng = ClosedLoopEngine(regulator, target_selector, A, B, Bd)
     res = eng.run(x0, uprev0, np.asarray(setpoints)[None], np.asarray(disturbances)[None])

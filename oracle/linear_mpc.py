@@ -123,6 +123,39 @@ class DenseQPRegulatorOracle:
         return (useq, info) if return_info else useq
 
 
+class CondensedRegulatorOracle:
+    """Box-path regulator on GIVEN condensed operators (P, tq): the same exact solve as
+    ``DenseQPRegulatorOracle.solve`` (linearMPC.py:495-512) for sizes where the literal dense
+    condensing above does not fit (CDU: tQ is 12.8 GB).  The operators themselves are pinned
+    separately: against the literal form at small sizes and, at full size, against a literal
+    roll-out of the stage costs (``rollout_cost``)."""
+
+    def __init__(self, *, P, tq, N, Nu, ulb, uub):
+        self.P, self.tq, self.N, self.Nu = P, tq, int(N), int(Nu)
+        self.ulb, self.uub = ulb, uub
+        self.reparameterize = False
+        self._box = _qp.BoxQP(P)
+
+    def solve(self, x0, return_info=False):
+        q = self.tq @ x0
+        useq, info = self._box.solve(q, np.tile(self.ulb, (self.N, 1)), np.tile(self.uub, (self.N, 1)))
+        useq = useq.reshape(-1, 1)
+        return (useq, info) if return_info else useq
+
+
+def rollout_cost(A, B, Q, R, M, Pf, N, x0, useq):
+    """1/2 sum_k (x_k'Q x_k + u_k'R u_k + 2 x_k'M u_k) + 1/2 x_N'Pf x_N along x+ = Ax + Bu: the objective
+    the reference condenses into 1/2 u'Pu + (tq x0)'u + const (linearMPC.py:330-337, :467-474)."""
+    nu = B.shape[1]
+    x = np.asarray(x0, float).reshape(-1)
+    u = np.asarray(useq, float).reshape(N, nu)
+    J = 0.0
+    for k in range(N):
+        J += x @ (Q @ x) + u[k] @ (R @ u[k]) + 2.0 * (x @ (M @ u[k]))
+        x = A @ x + B @ u[k]
+    return 0.5 * (J + x @ (Pf @ x))
+
+
 # ----------------------------------------------------------------------------- target selector
 class TargetSelectorOracle:
     """Steady-state target QP in (xs, us).  linearMPC.py:178-319 (input-bound branch :249-251)."""
