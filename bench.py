@@ -106,11 +106,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _scenarios(traj, steps, seed):
+def _scenarios(traj, steps, seed, gain_norm=None, r_weight=None):
     """PRBS-like set-points / disturbances with the reference's hold statistics, split into `traj`
-    contiguous chunks of `steps` rows (lib/linearMPC.py:786-801) -> (traj, steps, .) arrays."""
+    contiguous chunks of `steps` rows (lib/linearMPC.py:786-801) -> (traj, steps, .) arrays.
+    gain_norm / r_weight: conditioning study of the synthetic stand-in (defaults: plants/cdu.py, R = 0.1 I)."""
     from industrial_nnmpc_2021_b200.plants import get_cdu_problem
-    p = get_cdu_problem(Nsim=traj * steps, seed=seed)
+    from industrial_nnmpc_2021_b200.plants import cdu as _cdu
+    p = get_cdu_problem(Nsim=traj * steps, seed=seed, gain_norm=_cdu.GAIN_NORM if gain_norm is None else gain_norm)
+    if r_weight is not None:
+        p.R = r_weight * np.eye(p.Nu)
     sp = p.setpoints.reshape(traj, steps, p.Ny)
     ds = p.disturbances.reshape(traj, steps, p.Nd)
     return p, sp, ds
@@ -246,7 +250,7 @@ def run_native(args):
     # is traj x slab x 95 doubles).  Trajectories that continue across steps (--traj <= --slots) see one extra
     # set-point jump where the cycle wraps.
     nuniq = min(nslab, max(1, args.unique_slabs))
-    p, sp, ds = _scenarios(B, nuniq * Ts, seed=101 + 2 * rank)
+    p, sp, ds = _scenarios(B, nuniq * Ts, seed=101 + 2 * rank, gain_norm=args.gain_norm, r_weight=args.r_weight)
     if args.horizon != p.N:
         p.N = args.horizon
     t_setup = time.perf_counter()
@@ -455,6 +459,15 @@ def run_native(args):
             "dtype": "f64", "data": "synthetic", "config": _config(args, B, Ts),
             "qp_solves_per_s": {"regulator": value, "target_selector": value},
             "iterations": {"mean": it_sum / (B * Ts * K), "max": it_max, "kkt_max": kkt_max},
+            "conditioning": {"cond_P": reg.eig_range[1] / reg.eig_range[0], "lambda_min": reg.eig_range[0],
+                             "lambda_max": reg.eig_range[1],
+                             "active_bound_frac": (st1["qps_with_active_bounds"] - st0["qps_with_active_bounds"])
+                             / max(st1["qps"] - st0["qps"], 1),
+                             "mean_active_bounds_per_qp": (st1["active_bounds"] - st0["active_bounds"])
+                             / max(st1["qps"] - st0["qps"], 1),
+                             "gain_norm": args.gain_norm, "R": args.r_weight,
+                             "what": "condition number of the condensed Hessian; share of the timed QPs whose optimum "
+                                     "has >= 1 active input bound; active bounds per QP (of n)"},
             "roofline": roofline, "roofline_second_kernel": roofline2, "cpu_baseline": cpu,
             "precision": args.precision,
             "solver_work_per_qp": {k: (st1[k] - st0[k]) / max(st1["qps"] - st0["qps"], 1)
@@ -496,6 +509,9 @@ def main():
                     help="regulator-QP iteration arithmetic: tcgen05 fp16 increments + FP64 anchors, or all FP64 DMMA")
     ap.add_argument("--alpha", type=float, default=None, help="Douglas-Rachford relaxation (solver default 1.8)")
     ap.add_argument("--rho-scale", type=float, default=None, help="multiplier of the default ADMM penalty (solver default 1)")
+    ap.add_argument("--gain-norm", type=float, default=None,
+                    help="conditioning study: steady-state gain-row norm of the synthetic plant (default plants/cdu.py: 0.7)")
+    ap.add_argument("--r-weight", type=float, default=None, help="conditioning study: R = r I (reference tuning: 0.1)")
     ap.add_argument("--max-iter", type=int, default=3000, help="per-QP iteration cap (a hit rejects the number)")
     args = ap.parse_args()
     if args.impl == "reference":

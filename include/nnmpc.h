@@ -161,6 +161,9 @@ int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
 int nnmpc_sim_set_capture(nnmpc_sim_t* h, double* useq_dev, double* cost_dev);
 /* cumulative since create: out4 = {row-iterations, exact anchors, exact KKT checks, QPs solved} */
 int nnmpc_sim_stats(nnmpc_sim_t* h, long long* out4);
+/* cumulative since create: out2 = {QPs whose optimum has at least one active bound, active bounds in total} -
+ * how constrained the workload is (bench.py reports it next to the condition number of P) */
+int nnmpc_sim_active_stats(nnmpc_sim_t* h, long long* out2);
 int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                   const double* setpoints, const double* disturbances, double* x, double* uprev,
                   double* xs, double* us, double* u, int* iters, double* kkt, double tol,

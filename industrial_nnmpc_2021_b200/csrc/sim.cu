@@ -65,8 +65,8 @@ struct nnmpc_sim {
   int exact_oz;                     // mixed mode: anchors and exact checks on the INT8 tensor cores (oz_gemm.cuh) instead of DMMA
   nnmpc::OzRows ozr;
   nnmpc::DevBuf<int> lp_layout;     // 2 x cap operand layouts (position -> row) + 2 x cap inverses (row -> position)
-  unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks
-  long long tot_rowiters, tot_anchors, tot_verifies, tot_qps;   // since create (host)
+  unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks, [2] QPs whose optimum has active bounds, [3] active bounds in total
+  long long tot_rowiters, tot_anchors, tot_verifies, tot_qps, tot_qps_active, tot_active;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
   int* counts;                      // device, N_COUNTERS ints
   unsigned long long* rowiters;     // device: total row-iterations executed (flop accounting)
@@ -319,10 +319,23 @@ __global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ 
                           const double* __restrict__ xcur, const double* __restrict__ dist,
                           double* __restrict__ row_u, double* __restrict__ upcur, double* __restrict__ xin, int n,
                           int nx, int nu, int nd, int kin_ld, const double* __restrict__ G, const double* __restrict__ Ql,
-                          double* __restrict__ cap_useq, double* __restrict__ cap_cost) {
+                          double* __restrict__ cap_useq, double* __restrict__ cap_cost, const double* __restrict__ lb,
+                          const double* __restrict__ ub, unsigned long long* __restrict__ stats) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   const long long o = (long long)chunk[s] * T + tcur[s];
+  {  // workload statistics: how constrained the optimum is (z = clip(v) sits exactly on an active bound)
+    int na = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const double z = Z[s * n + j];
+      na += (z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)]) ? 1 : 0;
+    }
+    if (__syncthreads_or(na > 0)) {
+      na = __reduce_add_sync(0xffffffffu, na);
+      if ((threadIdx.x & 31) == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
+      if (threadIdx.x == 0) atomicAdd(stats + 2, 1ull);
+    }
+  }
   for (int c = threadIdx.x; c < kin_ld; c += blockDim.x) {
     double v;
     if (c < nx) {
@@ -567,7 +580,7 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
     e.counts[E_LP] = (e.mixed && !tail) ? S : 0;
     e.counts[E_TAIL] = (e.mixed && tail) ? S : 0;
     *e.rowiters = 0ull;
-    if (e.mixed) e.stats[0] = e.stats[1] = 0ull;
+    e.stats[0] = e.stats[1] = e.stats[2] = e.stats[3] = 0ull;
   }
 }
 
@@ -782,7 +795,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     // 5. first move, dataset row, plant step for the done rows
     k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
                                  h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld, gbuf, q->Ql.p, h->cap_useq,
-                                 h->cap_cost);
+                                 h->cap_cost, h->lb.p, h->ub.p, h->stats);
     count_launch(2);
     {
       GemmOperands gp{};
@@ -814,10 +827,10 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   }
   // drain: the last loops may not have been polled yet
   unsigned long long* pin64 = reinterpret_cast<unsigned long long*>(h->pin + POLL_RING * N_COUNTERS);
-  pin64[1] = pin64[2] = 0ull;
+  pin64[1] = pin64[2] = pin64[3] = pin64[4] = 0ull;
   NNMPC_CUDA(cudaMemcpyAsync(h->pin, h->counts, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(pin64, h->rowiters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  if (mixed) NNMPC_CUDA(cudaMemcpyAsync(pin64 + 1, h->stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  NNMPC_CUDA(cudaMemcpyAsync(pin64 + 1, h->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));   // final states were handed back chunk by chunk (k_chunk_swap)
   NNMPC_CUDA(cudaGetLastError());
   if (h->pin[N_FINISHED] < Btot)
@@ -831,6 +844,8 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   h->tot_anchors += (long long)pin64[1];
   h->tot_verifies += (long long)pin64[2];
   h->tot_qps += (long long)Btot * T;
+  h->tot_qps_active += (long long)pin64[3];
+  h->tot_active += (long long)pin64[4];
   h->warm_B = Btot == B ? Btot : 0;
   return rc_warn;
 }
@@ -865,7 +880,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
-  h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = 0;
+  h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = h->tot_qps_active = h->tot_active = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
@@ -885,9 +900,9 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   };
   if (rc == 0) cu(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)), "cudaMalloc");
   if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)), "cudaMalloc");
-  if (rc == 0) cu(cudaMalloc((void**)&h->stats, 2 * sizeof(unsigned long long)), "cudaMalloc");
-  if (rc == 0) cu(cudaMemset(h->stats, 0, 2 * sizeof(unsigned long long)), "cudaMemset");
-  if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 4 * sizeof(unsigned long long)), "cudaMallocHost");
+  if (rc == 0) cu(cudaMalloc((void**)&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+  if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 8 * sizeof(unsigned long long)), "cudaMallocHost");
   for (int i = 0; i < POLL_RING && rc == 0; ++i) cu(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming), "cudaEventCreate");
   if (rc < 0) {          // a half-built handle is released, not leaked
     cudaGetLastError();
@@ -964,6 +979,12 @@ int nnmpc_sim_set_capture(nnmpc_sim_t* h, double* useq_dev, double* cost_dev) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_capture: null handle");
   h->cap_useq = useq_dev;
   h->cap_cost = cost_dev;
+  return 0;
+}
+
+int nnmpc_sim_active_stats(nnmpc_sim_t* h, long long* out2) {
+  if (!h || !out2) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_active_stats: null argument");
+  out2[0] = h->tot_qps_active; out2[1] = h->tot_active;
   return 0;
 }
 

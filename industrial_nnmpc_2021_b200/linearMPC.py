@@ -601,7 +601,10 @@ class ClosedLoopEngine:
         """Cumulative solver work since construction: row-iterations, FP64 anchors, exact KKT checks, QPs."""
         out = (C.c_longlong * 4)()
         _lib.check(_lib.lib().nnmpc_sim_stats(self._handle, out), "nnmpc_sim_stats")
-        return dict(row_iterations=out[0], anchors=out[1], exact_checks=out[2], qps=out[3])
+        act = (C.c_longlong * 2)()
+        _lib.check(_lib.lib().nnmpc_sim_active_stats(self._handle, act), "nnmpc_sim_active_stats")
+        return dict(row_iterations=out[0], anchors=out[1], exact_checks=out[2], qps=out[3],
+                    qps_with_active_bounds=act[0], active_bounds=act[1])
 
     def __del__(self):
         try:
