@@ -87,6 +87,47 @@ def condensed_hessian(A, B, Q, R, M, Pf, N):
     return P, tq
 
 
+def reparameterize(A, B, Q, R, M, Krep):
+    """u = Krep x + v for an open-loop unstable A (linearMPC.py:366-382): returns (A, Q, M) of the
+    re-parameterised problem in the reference's statement order (R, B and Pf do not change)."""
+    A2 = A + B @ Krep
+    Q2 = Q + Krep.T @ (R @ Krep)
+    Q2 = Q2 + M @ Krep + Krep.T @ M.T
+    M2 = Krep.T @ R + M
+    return A2, Q2, M2
+
+
+def input_space_operators(A_cl, B, Krep, N, P_v, tq_v):
+    """Re-parameterised QP -> the equivalent BOX QP in the original inputs.
+
+    The reference solves for v with the dense inequality G v <= h(x0),
+    G = tE (tK tB_N + I), h = te - tE tK tA_N x0 (:476-493), and maps back u = tK (tA_N x0 + tB_N v) + v
+    (:507-509).  That map u = T v + S x0, T = I + tK tB_N (unit lower block triangular, hence
+    invertible), S = tK tA_N, is a bijection under which G v <= h becomes the plain box
+    lb <= u_k <= ub, so the minimiser is the image of the reference's and
+
+        P_u = T^-T P_v T^-1,      tq_u = T^-T tq_v - P_u S,
+        V_v(v*) = V_u(u*) + 1/2 x0'(S'P_u S) x0 - (tq_v x0)'T^-1 S x0
+
+    T^-1 is formed by a triangular solve.  (A_cl = A + B Krep is stable, so T, S stay O(1); what an
+    unstable plant costs is the conditioning of P_u, which the caller checks.)  Returns
+    (P_u, tq_u, T, S)."""
+    nx, nu = B.shape
+    n = N * nu
+    pw = state_powers(A_cl, N)
+    T = np.eye(n)
+    S = np.empty((n, nx))
+    for k in range(N):
+        S[k * nu:(k + 1) * nu] = Krep @ pw[k]
+        for j in range(k):
+            T[k * nu:(k + 1) * nu, j * nu:(j + 1) * nu] = Krep @ (pw[k - j - 1] @ B)
+    Ti = scipy.linalg.solve_triangular(T, np.eye(n), lower=True, unit_diagonal=True, check_finite=False)
+    P_u = Ti.T @ P_v @ Ti
+    P_u = 0.5 * (P_u + P_u.T)
+    tq_u = Ti.T @ tq_v - P_u @ S
+    return P_u, tq_u, T, S
+
+
 def prediction_matrices(A, B, N):
     """Literal (tA, tB) of linearMPC.py:397-428 (large: only built on request)."""
     nx, nu = B.shape

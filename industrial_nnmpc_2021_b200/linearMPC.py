@@ -106,8 +106,8 @@ class TargetSelector:
         s.t. [I-A, -B; HC, 0][xs; us] = [Bd dhat; H(ysp - Cd dhat)],  ulb <= us <= uub
 
     Supported configuration = the one both reference examples use: ``H`` empty
-    (cstrs_parameters.py:278, cdu_parameters.py:78), no output bounds, ``A`` open-loop stable,
-    ``Nu <= 32``.  Then ``xs = Gx us + Gd dhat`` and the problem is an exactly equivalent
+    (cstrs_parameters.py:278, cdu_parameters.py:78), no output bounds, ``I - A`` invertible
+    (any A without an eigenvalue at 1, stable or not), ``Nu <= 32``.  Then ``xs = Gx us + Gd dhat`` and the problem is an exactly equivalent
     ``Nu``-dimensional box QP (see csrc/ts.cu).
     """
 
@@ -121,8 +121,9 @@ class TargetSelector:
         if self.Nz != 0 or ylb is not None or yub is not None:
             raise NotImplementedError("TargetSelector on the GPU supports H empty and input bounds only "
                                       "(the configuration of both reference examples)")
-        if np.any(np.abs(np.linalg.eigvals(A)) >= 1.0):
-            raise NotImplementedError("TargetSelector on the GPU needs (I - A) invertible with A stable")
+        if np.linalg.cond(np.eye(self.Nx) - A) > 1e12:
+            raise NotImplementedError("TargetSelector on the GPU eliminates xs through (I - A)^-1: A must not have an "
+                                      "eigenvalue at 1 (an integrating plant needs H to pin the target)")
         self._setup_fixed_matrices()
         self._dev = _device_index(device)
         self._handle = None
@@ -240,6 +241,13 @@ class DenseQPRegulator:
         self._reparameterize()
         self.P, self.tq = condense.condensed_hessian(self.A, self.B, self.Q, self.R, self.M, self.Pf, self.N)
         self._tA = self._tB = self._G = None
+        # operators the GPU solves with: the QP itself on the box path; its exact image in the original inputs
+        # (again a box QP) on the re-parameterised path
+        if self.reparameterize:
+            self._Pu, self._tqu, self._T, self._S = condense.input_space_operators(self.A, self.B, self.Krep, self.N,
+                                                                                 self.P, self.tq)
+        else:
+            self._Pu, self._tqu, self._T, self._S = self.P, self.tq, None, None
         self.x0, self.useq = [], []
         self.last_info = None
         self._dev = _device_index(device)
@@ -247,12 +255,15 @@ class DenseQPRegulator:
         self._setup_solver()
 
     def _reparameterize(self):
-        """linearMPC.py:366-382.  The LQR re-parameterised (unstable A) path is not on the GPU yet."""
+        """linearMPC.py:366-382: with an open-loop unstable A the reference optimises v in u = Krep x + v.
+        ``A, Q, M, P, tq, G`` keep the reference's (v-space) meaning; the GPU solves the equivalent box QP
+        in u (``condense.input_space_operators``) and ``solve`` returns u, as the reference does after
+        mapping back (:507-509)."""
         if np.any(np.abs(np.linalg.eigvals(self.A)) >= 1.0):
-            raise NotImplementedError("DenseQPRegulator on the GPU supports the box-constrained path "
-                                      "(open-loop stable A, G = tE); the re-parameterised path "
-                                      "(linearMPC.py:366-382) is listed as future work in DESIGN.md")
-        self.reparameterize = False
+            self.A, self.Q, self.M = condense.reparameterize(self.A, self.B, self.Q, self.R, self.M, self.Krep)
+            self.reparameterize = True
+        else:
+            self.reparameterize = False
 
     # lazily built reference attributes
     @property
@@ -268,29 +279,51 @@ class DenseQPRegulator:
         return self._tB
 
     @property
-    def G(self):
-        if self._G is None:
-            E = np.vstack([np.eye(self.Nu), -np.eye(self.Nu)])
-            self._G = scipy.linalg.block_diag(*([E] * self.N))
-        return self._G
+    def tE(self):
+        E = np.vstack([np.eye(self.Nu), -np.eye(self.Nu)])
+        return scipy.linalg.block_diag(*([E] * self.N))
 
     @property
-    def tE(self):
-        return self.G
+    def tK(self):
+        """linearMPC.py:462-463 (re-parameterised path only)."""
+        return scipy.linalg.block_diag(*([self.Krep] * self.N)) if self.reparameterize else None
+
+    @property
+    def G(self):
+        """linearMPC.py:476-482: tE, or tE (tK tB_N + I) = tE T on the re-parameterised path."""
+        if self._G is None:
+            self._G = self.tE @ self._T if self.reparameterize else self.tE
+        return self._G
 
     def _get_h(self, x0):
-        """linearMPC.py:484-493 (box path)."""
-        return np.tile(np.vstack([self.uub, -self.ulb]), (self.N, 1))
+        """linearMPC.py:484-493."""
+        te = np.tile(np.vstack([self.uub, -self.ulb]), (self.N, 1))
+        if self.reparameterize:
+            return te - self.tE @ (self._S @ np.asarray(x0, float).reshape(-1, 1))
+        return te
+
+    def to_v(self, useq, x0):
+        """Input sequence(s) (., n) -> the reference's decision variable v = T^-1 (u - S x0) (identity on the box
+        path); with it the reference's objective value is 1/2 v'Pv + (tq x0)'v."""
+        U, X0 = np.atleast_2d(np.asarray(useq, float)), np.atleast_2d(np.asarray(x0, float))
+        if not self.reparameterize:
+            return U
+        rhs = (U - X0[:, :self._S.shape[1]] @ self._S.T).T
+        return scipy.linalg.solve_triangular(self._T, rhs, lower=True, unit_diagonal=True).T
 
     def _setup_solver(self):
         n = self.N * self.Nu
         if n % 2:
             raise NotImplementedError("N*Nu must be even")
-        P = self.P
+        P, tq = self._Pu, self._tqu
         cho = scipy.linalg.cho_factor(P, lower=True)
-        self.Kunc = -scipy.linalg.cho_solve(cho, self.tq)               # unconstrained law u = Kunc x0
+        self.Kunc = -scipy.linalg.cho_solve(cho, tq)                    # unconstrained law u = Kunc x0
         lmin, lmax = condense.extreme_eigs(P, cho)
         self.eig_range = (lmin, lmax)
+        if self.reparameterize and not lmax / lmin < 1e10:
+            raise NotImplementedError(
+                f"re-parameterised regulator: the input-space Hessian has condition number {lmax / lmin:.1e}; plants this "
+                "unstable over the horizon need the v-space general-G splitting, which is not built (DESIGN.md)")
         dP = np.diag(P)
         rho0 = 0.5 * np.sqrt(lmin * lmax) * self.rho_scale    # 0.5: swept on the CDU closed loop (0.28 .. 1.1), B200 round 1ae
         self.rho_vec = rho0 * dP / np.exp(np.mean(np.log(dP)))
@@ -304,8 +337,7 @@ class DenseQPRegulator:
             out = np.zeros((Mx.shape[0], self._nxa_ld))
             out[:, :self.Nx] = Mx
             return out
-        ops = [_lib.host(P), pad(self.tq), _lib.host(Minv * self.rho_vec[None, :]), pad(Minv @ self.tq),
-               pad(self.Kunc)]
+        ops = [_lib.host(P), pad(tq), _lib.host(Minv * self.rho_vec[None, :]), pad(Minv @ tq), pad(self.Kunc)]
         L = _lib.lib()
         hnd = C.c_void_p()
         rc = L.nnmpc_qp_create(C.byref(hnd), n, self._nxa_ld, self.Nu, self.N, *[_lib.hptr(a) for a in ops],

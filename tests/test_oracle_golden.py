@@ -82,6 +82,42 @@ def test_unstable_reparameterised_formulation(golden_formulation):
     assert u.shape == (5, 1) and np.all(np.abs(u) <= 1 + 1e-9)
 
 
+def test_reparameterised_host_operators_and_input_space_equivalence(golden_formulation):
+    """The product's host side of the unstable-A path (linearMPC.py:366-382, :476-493, :507-509): v-space
+    operators equal the reference's, and the input-space box QP the GPU solves has the image u = T v + S x0 of
+    the reference's minimiser as its own (checked with the oracle's two independent exact solvers)."""
+    from industrial_nnmpc_2021_b200 import condense
+    from oracle import qp as oq
+    g = golden_formulation
+    A, B, N = g["unst_A"], g["unst_B"], 5
+    Q, R, M = np.eye(2), np.eye(1), np.zeros((2, 1))
+    K, Pf = condense.dlqr(A, B, Q, R, M)
+    A2, Q2, M2 = condense.reparameterize(A, B, Q, R, M, K)
+    assert np.max(np.abs(np.linalg.eigvals(A2))) < 1.0
+    Pv, tqv = condense.condensed_hessian(A2, B, Q2, R, M2, Pf, N)
+    assert np.allclose(Pv, g["unst_P"], atol=1e-12) and np.allclose(tqv, g["unst_tq"], atol=1e-12)
+    Pu, tqu, T, S = condense.input_space_operators(A2, B, K, N, Pv, tqv)
+    E = np.vstack([np.eye(1), -np.eye(1)])
+    tE = np.kron(np.eye(N), E)
+    assert np.allclose(tE @ T, g["unst_G"], atol=1e-12)
+    x0 = g["unst_x0"]
+    te = np.tile(np.array([[1.0], [1.0]]), (N, 1))
+    assert np.allclose(te - tE @ (S @ x0), g["unst_h"], atol=1e-13)
+    # the input-space Hessian is the ORIGINAL problem condensed directly (same minimiser by construction)
+    Pdir, tqdir = condense.condensed_hessian(A, B, Q, R, M, Pf, N)
+    assert np.allclose(Pu, Pdir, rtol=1e-10, atol=1e-10) and np.allclose(tqu, tqdir, rtol=1e-10, atol=1e-10)
+    rng = np.random.default_rng(0)
+    oreg = om.DenseQPRegulatorOracle(A=A, B=B, Q=Q, R=R, M=M, N=N, ulb=-np.ones((1, 1)), uub=np.ones((1, 1)))
+    nact = 0
+    for trial in range(12):
+        x0 = x0 if trial == 0 else rng.uniform(-1.5, 1.5, (2, 1)) * (1.0 + trial / 4.0)
+        u_ref = oreg.solve(x0)                                   # reference route: general-G QP in v, mapped back
+        u_box, info = oq.BoxQP(Pu).solve((tqu @ x0)[:, 0], -np.ones(N), np.ones(N))
+        nact += info["n_active"] > 0
+        assert np.allclose(u_box, u_ref[:, 0], atol=2e-8), (trial, u_box, u_ref[:, 0])
+    assert nact >= 4
+
+
 def test_stage_cost(golden_formulation):
     g = golden_formulation
     for tag in ("cstrs", "cdu_small"):

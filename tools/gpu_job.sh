@@ -3,9 +3,9 @@
 # keeping are copied to profiles/).
 set -x
 mkdir -p gpurun_out
-timeout -k 10 900 python -m pytest tests/test_gpu_cdu_fullsize.py -x -q -s 2>&1 | tail -40 > gpurun_out/r02a_j3.log
+timeout -k 10 900 python -m pytest tests/test_gpu_cdu_fullsize.py tests/test_gpu_reparam.py -x -q -s 2>&1 | tail -40 > gpurun_out/r02a_j3.log
 tail -25 gpurun_out/r02a_j3.log
-timeout -k 10 600 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_cdu_fullsize.py 2>&1 | tail -8 > gpurun_out/r02a_pytest.log
+timeout -k 10 600 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_cdu_fullsize.py --deselect tests/test_gpu_reparam.py 2>&1 | tail -8 > gpurun_out/r02a_pytest.log
 cat gpurun_out/r02a_pytest.log
 # conditioning sweep of the stand-in plant (short steps: 16384 slots x 8 sim steps, 2 timed steps)
 for cfg in "0.7 0.1" "2 0.1" "5 0.1" "0.7 0.01" "5 0.01"; do
