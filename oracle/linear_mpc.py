@@ -241,3 +241,66 @@ def simulate_offline(*, x0, uprev0, A, B, Bd, regulator, ulb, uub, target_select
         xt = A @ xt + B @ ut + Bd @ d
         upt = ut
     return {k: np.asarray(v) for k, v in rows.items()}
+
+
+# ----------------------------------------------------------------------------- online loop
+def dlqe(A, C, Q, R):
+    """Steady-state Kalman gain.  linearMPC.py:42-48."""
+    P = scipy.linalg.solve_discrete_are(A.T, C.T, Q, R)
+    L = scipy.linalg.solve(C @ P @ C.T + R, C @ P).T
+    return L, P
+
+
+def augmented_matrices_for_filter(A, B, C, Bd, Cd, Qwx, Qwd):
+    """Integrating-disturbance model [x; d].  linearMPC.py:606-624."""
+    nx, nu, nd = A.shape[0], B.shape[1], Bd.shape[1]
+    Aaug = np.block([[A, Bd], [np.zeros((nd, nx)), np.eye(nd)]])
+    Baug = np.vstack([B, np.zeros((nd, nu))])
+    Caug = np.hstack([C, Cd])
+    return Aaug, Baug, Caug, scipy.linalg.block_diag(Qwx, Qwd)
+
+
+class OnlineControllerOracle:
+    """LinearMPCController.control_law (linearMPC.py:646-669): Kalman filter (:133-176) -> target selector
+    -> regulator -> running average stage cost (:691-701), one measurement at a time."""
+
+    def __init__(self, *, A, B, C, H, Qwx, Qwd, Rv, xprior, dprior, Rs, Qs, Bd, Cd, usp, uprev, Q, R, S, ulb, uub, N,
+                 regulator=None):
+        self.Nx, self.Nu = B.shape
+        self.ulb, self.uub = ulb, uub
+        self.Af, self.Bf, self.Cf, Qw = augmented_matrices_for_filter(A, B, C, Bd, Cd, Qwx, Qwd)
+        self.L, _ = dlqe(self.Af, self.Cf, Qw, Rv)
+        self.xhat = np.vstack([xprior, dprior])
+        self.target_selector = TargetSelectorOracle(A=A, B=B, C=C, H=H, Bd=Bd, Cd=Cd, usp=usp, Rs=Rs, Qs=Qs,
+                                                    ulb=ulb, uub=uub)
+        self.regulator = regulator if regulator is not None else setup_regulator(A, B, Q, R, S, N, ulb, uub)
+        _, _, self.Qaug, self.Raug, self.Maug = augmented_matrices_for_regulator(A, B, Q, R, S)
+        self.uprev = uprev
+        self.average_stage_costs = [np.zeros((1, 1))]
+        self.xhats, self.targets = [], []
+
+    def control_law(self, ysp, y):
+        pred = self.Af @ self.xhat + self.Bf @ self.uprev                       # :163-165
+        self.xhat = pred + self.L @ (y - self.Cf @ pred)
+        xhat, dhat = self.xhat[:self.Nx], self.xhat[self.Nx:]
+        xs, us = self.target_selector.solve(ysp, dhat)
+        useq = get_control_sequence(self.regulator, xhat, self.uprev, xs, us, self.ulb, self.uub)
+        u = useq[:self.Nu]
+        self.average_stage_costs.append(updated_average_stage_cost(
+            xhat, self.uprev, xs, us, u, self.Qaug, self.Raug, self.Maug, self.average_stage_costs[-1],
+            len(self.average_stage_costs)))
+        self.uprev = u
+        self.xhats.append(xhat)
+        self.targets.append((xs, us))
+        return u
+
+
+def online_simulation(plant_step, y0, controller, setpoints, disturbances, Nsim):
+    """linearMPC.py:703-718 with the plant given as a callable (u, p) -> y."""
+    y = y0
+    us = []
+    for i in range(min(Nsim, setpoints.shape[0])):
+        u = controller.control_law(setpoints[i][:, None], y)
+        y = plant_step(u, disturbances[i][:, None])
+        us.append(u[:, 0])
+    return np.asarray(us)
