@@ -69,7 +69,7 @@ struct nnmpc_sim {
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps, tot_qps_active, tot_active;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
   int* counts;                      // device, N_COUNTERS ints
-  unsigned long long* rowiters;     // device: total row-iterations executed (flop accounting)
+  unsigned long long* rowiters;     // device: [0] total row-iterations executed (flop accounting), [1] of which in the FP64 tail
   int* pin;                         // pinned: POLL_RING x N_COUNTERS ints + 2 x u64
   cudaEvent_t poll_ev[nnmpc::POLL_RING];
   // staging for the host entry point
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
   if (threadIdx.x == 0) {
     e.counts[N_CAND] = base;
     *e.rowiters += (unsigned long long)tot_it;
+    if (e.mixed && e.counts[E_TAIL] > 0) e.rowiters[1] += (unsigned long long)tot_it;   // of which: FP64 tail iterations
     if (e.mixed && full) e.stats[0] += (unsigned long long)e.counts[E_ANCHOR];   // anchors served at the top of this loop
   }
 }
@@ -579,7 +580,7 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
     e.counts[E_ANCHOR] = (e.mixed && !tail) ? S : 0;
     e.counts[E_LP] = (e.mixed && !tail) ? S : 0;
     e.counts[E_TAIL] = (e.mixed && tail) ? S : 0;
-    *e.rowiters = 0ull;
+    e.rowiters[0] = e.rowiters[1] = 0ull;
     e.stats[0] = e.stats[1] = e.stats[2] = e.stats[3] = 0ull;
   }
 }
@@ -827,9 +828,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   }
   // drain: the last loops may not have been polled yet
   unsigned long long* pin64 = reinterpret_cast<unsigned long long*>(h->pin + POLL_RING * N_COUNTERS);
-  pin64[1] = pin64[2] = pin64[3] = pin64[4] = 0ull;
+  for (int i = 0; i < 8; ++i) pin64[i] = 0ull;
   NNMPC_CUDA(cudaMemcpyAsync(h->pin, h->counts, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
-  NNMPC_CUDA(cudaMemcpyAsync(pin64, h->rowiters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  NNMPC_CUDA(cudaMemcpyAsync(pin64 + 5, h->rowiters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaMemcpyAsync(pin64 + 1, h->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));   // final states were handed back chunk by chunk (k_chunk_swap)
   NNMPC_CUDA(cudaGetLastError());
@@ -837,8 +838,11 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     return set_error(NNMPC_ERR_CUDA, "closed-loop engine stopped with %d of %d trajectories finished", h->pin[N_FINISHED], Btot);
   if (h->pin[F_MAXITER]) rc_warn |= NNMPC_WARN_MAXITER;
   if (h->pin[F_TS_FAIL]) rc_warn |= NNMPC_WARN_TARGET;
+  pin64[0] = pin64[5];
   g_iterations.fetch_add((long long)*pin64, std::memory_order_relaxed);
-  prof_add_flops(2.0 * n * (double)n * (double)*pin64);                               // iteration passes
+  // each channel's flops belong to the kernels whose time it records: tensor-core passes (0), FP64 tail (2)
+  prof_add_flops(2.0 * n * (double)n * (double)(pin64[5] - pin64[6]));                // iteration passes
+  prof_add_flops(2.0 * n * (double)n * (double)pin64[6], 2);                          // FP64 tail iterations
   prof_add_flops(2.0 * n * (double)n * (double)(pin64[1] + pin64[2]), 1);             // exact anchors + checks (FP64-equivalent)
   h->tot_rowiters += (long long)pin64[0];
   h->tot_anchors += (long long)pin64[1];
@@ -899,7 +903,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
     if (rc == 0 && e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "nnmpc_sim_create: %s: %s", what, cudaGetErrorString(e));
   };
   if (rc == 0) cu(cudaMalloc((void**)&h->counts, N_COUNTERS * sizeof(int)), "cudaMalloc");
-  if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, 2 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMalloc((void**)&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
   if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 8 * sizeof(unsigned long long)), "cudaMallocHost");

@@ -365,8 +365,12 @@ class DenseQPRegulator:
         self._setup_solver()
 
     # ---- batched solve -------------------------------------------------------------------
-    def solve_batch(self, X0, LB=None, UB=None, *, warm_state=None, tol=None, max_iter=None, return_info=True):
+    def solve_batch(self, X0, LB=None, UB=None, *, warm_state=None, tol=None, max_iter=None, return_info=True,
+                    out=None):
         """Solve B regulator QPs.
+
+        ``out`` (NumPy form only): dict of preallocated result arrays ``U (B,n), cost (B,), kkt (B,), iters (B,)
+        int32`` - e.g. pinned host memory - written in place.
 
         X0 (B,Nxa); LB, UB (B,Nu) per-sample stage bounds (default: this object's ulb/uub).
         Returns U (B,n) in deviation variables and, with ``return_info``, dict(cost, kkt, iters,
@@ -385,8 +389,17 @@ class DenseQPRegulator:
             LB = np.tile(self.ulb.reshape(1, -1), (Bn, 1)) if LB is None else LB
             UB = np.tile(self.uub.reshape(1, -1), (Bn, 1)) if UB is None else UB
             LB, UB = _lib.host(LB), _lib.host(UB)
-            U, cost, kkt = np.empty((Bn, n)), np.empty(Bn), np.empty(Bn)
-            iters = np.empty(Bn, dtype=np.int32)
+            if tuple(LB.shape) != (Bn, self.Nu) or tuple(UB.shape) != (Bn, self.Nu):
+                raise ValueError("LB / UB must have shape (B, Nu)")
+            if out is None:
+                U, cost, kkt = np.empty((Bn, n)), np.empty(Bn), np.empty(Bn)
+                iters = np.empty(Bn, dtype=np.int32)
+            else:
+                U, cost, kkt, iters = out["U"], out["cost"], out["kkt"], out["iters"]
+                for a, shp, dt in ((U, (Bn, n), np.float64), (cost, (Bn,), np.float64), (kkt, (Bn,), np.float64),
+                                   (iters, (Bn,), np.int32)):
+                    if tuple(a.shape) != shp or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                        raise ValueError("out arrays must be C-contiguous U (B,n), cost (B,), kkt (B,) float64 and iters (B,) int32")
             rc = L.nnmpc_qp_solve_host(self._handle, Bn, _lib.hptr(X0p), _lib.hptr(LB), _lib.hptr(UB), _lib.hptr(U),
                                        _lib.hptr(cost), _lib.hptr(kkt), _lib.hptr(iters), float(tol), int(max_iter))
             warned = _lib.check(rc, "nnmpc_qp_solve_host")
