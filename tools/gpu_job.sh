@@ -22,3 +22,4 @@ except Exception as e:
     print("COND failed", "$1", "$2", e)
 PY
 done
+timeout -k 10 120 python tools/probes/lp_accum_error.py 2>&1 | tail -5 > gpurun_out/r02a_lp_accum.txt; cat gpurun_out/r02a_lp_accum.txt
