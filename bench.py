@@ -498,6 +498,22 @@ def run_cdu(args):
     value_prof = world * B * Ts * Kp / (ctx.maxrank(ms_prof) * 1e-3)
 
     # ---- end-to-end phase: host buffers through the reference-facing API -----------------------
+    if args.no_e2e:          # kernel A/B runs only: a line without "e2e" is not a bench result
+        if rank == 0:
+            t1 = sp1["tiles_one_term"] - sp0["tiles_one_term"]
+            t2 = sp1["tiles_two_terms"] - sp0["tiles_two_terms"]
+            nq = max(sp1["qps"] - sp0["qps"], 1)
+            print(json.dumps({"ab_run": True, "value": value, "value_profiled": value_prof,
+                              "iterations_mean": it_sum / (B * Ts * K), "iterations_max": it_max, "kkt_max": kkt_max,
+                              "lp_tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                              "exact_tflops_fp64eq": f64_flops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else None,
+                              "one_term_tile_share": t1 / max(t1 + t2, 1),
+                              "work_per_qp": {k: (sp1[k] - sp0[k]) / nq for k in ("row_iterations", "anchors", "exact_checks")},
+                              "shares": {"lp": gemm_ms / ms_prof, "exact": f64_ms / ms_prof, "tail": tail_ms / ms_prof,
+                                         "rest": rest_ms / ms_prof}, "clocks": clocks,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("NNMPC_")}}), flush=True)
+        ctx.finish()
+        return
     out_h = dict(x=ctx.pinned((B, Ts, nx)), uprev=ctx.pinned((B, Ts, nu)), xs=ctx.pinned((B, Ts, nx)),
                  us=ctx.pinned((B, Ts, nu)), u=ctx.pinned((B, Ts, nu)), iters=ctx.pinned((B, Ts), torch.int32),
                  kkt=ctx.pinned((B, Ts)))
@@ -577,15 +593,19 @@ def run_cdu(args):
         lp_peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0)
         f64_ach = f64_flops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else 0.0
         rows_per_launch = (gemm_flops / (2.0 * n * n)) / max(gemm_launches, 1)
+        # tiles of late-phase rows run with one operator term (LpShape::need2): executed MMA work per algorithmic flop
+        t1, t2 = sp1["tiles_one_term"] - sp0["tiles_one_term"], sp1["tiles_two_terms"] - sp0["tiles_two_terms"]
+        mma_factor = (t1 + 2.0 * t2) / max(t1 + t2, 1) if (t1 + t2) else 2.0
         # DRAM bytes per launch: a MODEL, not a per-run measurement - two fp16 operator terms read once per pass
         # (2 x 2 n^2 B) plus the per-row state, with the per-row constant taken from the one `ncu --set full` capture of
         # this kernel (profiles/r01af_ncu_full_lp_gemm.txt: 238.4 kB per row at n = 4480 vs 42 B x n = 188.2 kB
         # algorithmic), scaled linearly in n
-        op_bytes = 2.0 * 2.0 * n * n
+        op_bytes = mma_factor * 2.0 * n * n
         r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
                                              "increments x two-term fp16 operator split, fp32 TMEM accumulators, FP64 state)",
-                "achieved": achieved, "executed_mma": 2.0 * achieved, "peak": lp_peak, "unit": "TFLOP/s",
-                "frac": achieved / lp_peak, "frac_executed": 2.0 * achieved / lp_peak,
+                "achieved": achieved, "executed_mma": mma_factor * achieved, "peak": lp_peak, "unit": "TFLOP/s",
+                "one_term_tile_share": t1 / max(t1 + t2, 1),
+                "frac": achieved / lp_peak, "frac_executed": mma_factor * achieved / lp_peak,
                 "traffic": op_bytes + 238.4e3 * (n / 4480.0) * rows_per_launch,
                 "traffic_kind": "model scaled from one ncu capture (see bench.py), not measured in this run",
                 "traffic_algorithmic": op_bytes + 42.0 * n * rows_per_launch,
@@ -1002,6 +1022,7 @@ def main():
                     help="trajectories advanced concurrently per GPU; with --traj above it the other chunks queue up and "
                          "finished slots take the next one (continuous batching)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs: stop after the device-resident passes")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"],
                     help="regulator-QP iteration arithmetic: tcgen05 fp16 increments + FP64 anchors, or all FP64 DMMA")
     ap.add_argument("--qp-precision", default=None, choices=["mixed", "f64"],

@@ -153,6 +153,13 @@ int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
 /* Mixed mode only: which tensor pipe evaluates the FP64-exact operator applies (anchors x = Top w - c, KKT checks
  * g = P z + q): 1 (default) = INT8 tcgen05 with error-free slicing (FP64-accurate, see oz_gemm.cuh), 0 = FP64 DMMA. */
 int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
+/* Mixed mode only: a trajectory whose last Douglas-Rachford residual ||d||_inf is at most factor * tol is in the late
+ * phase of its QP; 128-row operand tiles made of such rows only run the tensor-core pass with the first fp16 operator
+ * term alone (half the MMA work; the 2^-11 relative error of the dropped term is relative to a vanishing increment and
+ * every result is still certified by the exact KKT check).  Default 100; 0 = always both terms. */
+int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor);
+/* cumulative since create: out2 = {128x128 tensor-core tiles run with one operator term, with both terms} */
+int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2);
 /* Optional per-QP sinks for the following nnmpc_sim_run calls (device pointers, either may be NULL; NULL, NULL
  * switches the capture off): useq [B][T][n] = the whole optimal input sequence of every regulator QP with the
  * target added back per stage - what get_control_sequence returns (lib/linearMPC.py:689) and DenseQPRegulator

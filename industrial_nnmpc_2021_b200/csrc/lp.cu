@@ -73,10 +73,10 @@ int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double
 
 int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
                 const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
-                cudaStream_t st) {
+                cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
   k_dr_first<<<max_rows, 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
-                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r);
+                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r, need2);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -93,10 +93,10 @@ int lp_reanchor(const int* rows, const int* count, int max_rows, const int* stat
 
 int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emit_state, int iter_state, LpState* s,
             const double* V, const double* lb, const double* ub, const double* dtrig, int nu, double alpha,
-            const int* pos_r, cudaStream_t st) {
+            const int* pos_r, cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
   k_lp_emit<<<max_rows, 256, 0, st>>>(rows, count, state, emit_state, iter_state, V, s->Wl.p, s->E.p, s->D[s->cur].p,
-                                      s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r);
+                                      s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r, need2);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -104,7 +104,7 @@ int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emi
 
 int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
                const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
-               double alpha, int device, cudaStream_t st) {
+               double alpha, int device, cudaStream_t st, const unsigned char* need2, unsigned long long* tile_stat) {
   if (B <= 0) return 0;
   EpiDelta::Params ep{};
   ep.X = s->X.p; ep.V = V; ep.E = s->E.p; ep.Dn = s->D[s->cur ^ 1].p; ep.ldd = s->ldd; ep.lb = lb; ep.ub = ub;
@@ -115,7 +115,7 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   const double tile_mb = 2.0 * bn_tile * (double)op->ldh * 2.0 / 1048576.0;
   int group_cols = (int)(24.0 / tile_mb);
   if (group_cols < 1) group_cols = 1;
-  lp::LpShape g{B, s->n, s->n, len_r, group_cols};
+  lp::LpShape g{B, s->n, s->n, len_r, group_cols, need2, tile_stat};
   cudaError_t e = lp_use_pair()
                       ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
                       : lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
@@ -186,7 +186,7 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
     if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
       rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
-      lp::LpShape g{M, N, K, nullptr, 2};
+      lp::LpShape g{M, N, K, nullptr, 2, nullptr, nullptr};
       const EpiLpStore::Params ep{C, N, 1.0 / op.scale};
       cudaError_t e = pair ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
                            : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);

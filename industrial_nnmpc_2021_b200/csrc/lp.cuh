@@ -48,19 +48,21 @@ int lp_anchor_gemm(const int* rows, const int* count, int max_rows, const double
 // pos_r: sample row -> row of the operand buffer the next pass reads (null = identity)
 int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, double* V, double* W, const double* lb,
                 const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
-                cudaStream_t st);
+                cudaStream_t st, unsigned char* need2 = nullptr);   // need2: operand tiles of these rows get both operator terms
 // candidates that failed their exact check (state == emit_state; Wl holds g = P z + q): x := z, Wl := w_lp = z + g / rho
 int lp_reanchor(const int* rows, const int* count, int max_rows, const int* state, int emit_state, const double* Z,
                 const double* rinv, LpState* s, cudaStream_t st);
 // listed rows in emit_state: first fp16 increment from the exactly anchored (x, w_lp); state := iter_state
 int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emit_state, int iter_state, LpState* s,
             const double* V, const double* lb, const double* ub, const double* dtrig, int nu, double alpha,
-            const int* pos_r, cudaStream_t st);
+            const int* pos_r, cudaStream_t st, unsigned char* need2 = nullptr);
 // One tensor-core pass over the operand rows [0, *len_r) (at most B); flips s->cur.  Operand row p belongs to
 // sample list_r[p]; it takes part iff state[sample] == iter_state, and its next increment is written to
 // operand row pos_w[sample] of the other buffer (so the layout is re-compacted one pass behind the live list).
 int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
                const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
-               double alpha, int device, cudaStream_t st);
+               double alpha, int device, cudaStream_t st, const unsigned char* need2 = nullptr,
+               unsigned long long* tile_stat = nullptr);
+
 
 }  // namespace nnmpc

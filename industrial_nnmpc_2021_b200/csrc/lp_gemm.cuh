@@ -207,6 +207,12 @@ struct LpShape {
   int K;              // contraction length (TMA zero-fills beyond it)
   const int* m_dev;   // optional: the row count lives in device memory (0 = nothing to do)
   int group_cols;     // column tiles per L2 group (see tile_coords); <= 0: all
+  // Optional: per 128-row tile, does the tile need the second operator term B2?  (null: every tile does.)  Tiles
+  // whose rows are all in the late phase of their QP - increments so small that the 2^-11 relative error of a
+  // one-term product is far below the solver tolerance - run A x B1 only: half the MMA work, a third less operand
+  // traffic.  tile_stat (nullable): [0] += tiles run with one term, [1] += tiles run with both (accounting).
+  const unsigned char* need2;
+  unsigned long long* tile_stat;
 };
 
 // Tile order of the persistent CTAs.  The operator (2 x n x n fp16, 80 MB at n = 4480) does not fit the part of
@@ -288,13 +294,14 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         int bm, bn;
         tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
+        const bool two = !g.need2 || g.need2[bm] != 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * T::STAGE_BYTES;
-          mbar_expect_tx(full + s, T::STAGE_BYTES);
+          mbar_expect_tx(full + s, two ? T::STAGE_BYTES : T::A_BYTES + T::B_BYTES);
           tma_load_2d(st, &tmA, full + s, kb * BK, bm * BM);
           tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
-          tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
+          if (two) tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -307,6 +314,10 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       int i = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+        int bm, bn;
+        tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
+        const bool two = !g.need2 || g.need2[bm] != 0;
+        if (g.tile_stat) atomicAdd(g.tile_stat + (two ? 1 : 0), 1ull);
         const int as = i & 1;
         const uint32_t aph = (uint32_t)(i >> 1) & 1u;
         mbar_wait(acc_empty + as, aph ^ 1);       // epilogue has drained this accumulator
@@ -322,8 +333,10 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
             umma_f16(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          if (two) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+          }
           umma_commit(empty + s);                 // ring slot free once these MMAs have read it
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
         }
@@ -488,13 +501,14 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
         const int arow = bm * 2 * BM + (int)rank * BM;
         const int brow = bn * BN2 + (int)rank * (BN2 / 2);
+        const bool two = !g.need2 || (g.need2[2 * bm] | g.need2[2 * bm + 1]) != 0;     // a pair tile spans two 128-row tiles
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * STAGE2_BYTES;
           tma_load_2d_pair(st, &tmA, full + s, kb * BK, arow);
           tma_load_2d_pair_hint(st + BM * BK * 2, &tmB1, full + s, kb * BK, brow, L2_EVICT_LAST);
-          tma_load_2d_pair_hint(st + BM * BK * 2 + (BN2 / 2) * BK * 2, &tmB2, full + s, kb * BK, brow, L2_EVICT_LAST);
-          if (leader) mbar_expect_tx(full + s, 2 * STAGE2_BYTES);
+          if (two) tma_load_2d_pair_hint(st + BM * BK * 2 + (BN2 / 2) * BK * 2, &tmB2, full + s, kb * BK, brow, L2_EVICT_LAST);
+          if (leader) mbar_expect_tx(full + s, two ? 2 * STAGE2_BYTES : 2 * (BM * BK * 2 + (BN2 / 2) * BK * 2));
           else mbar_arrive_remote(full + s, 0);
           if (++s == STAGES2) { s = 0; ph ^= 1; }
         }
@@ -508,6 +522,10 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       int i = 0;
       for (int t = cluster_id; t < tiles; t += nclusters, ++i) {
+        int bm, bn;
+        tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
+        const bool two = !g.need2 || (g.need2[2 * bm] | g.need2[2 * bm + 1]) != 0;
+        if (g.tile_stat) atomicAdd(g.tile_stat + (two ? 1 : 0), 4ull);      // counted in 128 x 128 tiles
         const int as = i & 1;
         const uint32_t aph = (uint32_t)(i >> 1) & 1u;
         mbar_wait(acc_empty + as, aph ^ 1);
@@ -522,8 +540,10 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db2 = make_sw128_kmajor_desc(sa + BM * BK * 2 + (BN2 / 2) * BK * 2);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_pair(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          if (two) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_pair(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_pair(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+          }
           umma_commit_pair(empty + s);
           if (++s == STAGES2) { s = 0; ph ^= 1; }
         }

@@ -294,7 +294,7 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
            double* __restrict__ W, float* __restrict__ E, __half* __restrict__ D, long long ldd,
            const double* __restrict__ lb, const double* __restrict__ ub, double* __restrict__ sc_in,
            double* __restrict__ sc_out, int* __restrict__ state, int* __restrict__ it, int iter_state, int n, int nu,
-           double alpha, const int* __restrict__ pos_r) {
+           double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   __shared__ double red[2][8];
@@ -339,6 +339,7 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
     sc_out[s] = pow2_scale(3.0 * alpha * dmax);
     state[s] = iter_state;
     it[s] += 1;
+    if (need2 && dpos >= 0) need2[dpos >> 7] = 1;     // a QP starts with large increments: both operator terms
   }
 }
 
@@ -370,7 +371,7 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
           int iter_state, const double* __restrict__ V, double* __restrict__ WL, float* __restrict__ E,
           __half* __restrict__ D, long long ldd, const double* __restrict__ lb, const double* __restrict__ ub,
           double* __restrict__ sc_in, double* __restrict__ sc_out, const double* __restrict__ dtrig, int n, int nu,
-          double alpha, const int* __restrict__ pos_r) {
+          double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
   if ((int)blockIdx.x >= *count) return;
   const long long s = rows[blockIdx.x];
   if (state[s] != emit_state) return;
@@ -406,6 +407,8 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
     sc_in[s] = sq;
     sc_out[s] = pow2_scale(3.0 * alpha * (dtrig[s] + wmax));
     state[s] = iter_state;
+    // a re-anchored row restarts from the gradient of a failed check: its first increments are not small
+    if (need2 && dpos >= 0) need2[dpos >> 7] = 1;
   }
 }
 

@@ -65,6 +65,10 @@ struct nnmpc_sim {
   int exact_oz;                     // mixed mode: anchors and exact checks on the INT8 tensor cores (oz_gemm.cuh) instead of DMMA
   nnmpc::OzRows ozr;
   nnmpc::DevBuf<int> lp_layout;     // 2 x cap operand layouts (position -> row) + 2 x cap inverses (row -> position)
+  nnmpc::DevBuf<double> dlast;      // last ||d|| per slot
+  nnmpc::DevBuf<unsigned char> need2;   // per 128-row operand tile: both operator terms needed in the next pass
+  double t2_factor;                 // a row is "late" when ||d|| <= t2_factor * tol (0: never skip the second term)
+  unsigned long long* tile_stat;    // device: tensor-core tiles run with [0] one, [1] both operator terms (cumulative)
   unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks, [2] QPs whose optimum has active bounds, [3] active bounds in total
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps, tot_qps_active, tot_active;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
@@ -158,6 +162,9 @@ struct EngineArrays {
   int mixed; double* sc_in; double* sc_out; unsigned long long* stats; double alpha;
   int* lp_list; int* lp_pos;   // [2][S] each
   int tail_rows;
+  // one-term tensor-core tiles (lp_gemm.cuh LpShape::need2): last ||d|| per row, threshold below which a row is in
+  // its late phase, per-128-row-tile flags for the next pass (null: every tile runs both operator terms)
+  double* dlast; double t2_thr; unsigned char* need2;
 };
 
 // exclusive prefix of a per-thread count over one 1024-thread block; total to every thread
@@ -195,11 +202,15 @@ __device__ int block_excl_scan(int c, int& total_out) {
 //  mode run every `cadence`-th loop - so the list grows instead of starting over).
 // Four consecutive list entries per thread and round: the dependent loads of a row (list -> state -> residual)
 // overlap across the four, and the candidate list keeps the order of the live list.
-__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int append, int full) {
+__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int append, int full,
+                                                 const int* __restrict__ pos_next, int S) {
   constexpr int RPT = 4;
   const int na = e.counts[N_ACTIVE];
   int base = append ? e.counts[N_CAND] : 0;
   int iterated = 0;
+  // tile flags of the NEXT pass start from "one term is enough"; rows that are not in their late phase raise them
+  if (e.need2)
+    for (int i = threadIdx.x; i < (S + 127) / 128 + 1; i += 1024) e.need2[i] = 0;
   __syncthreads();
   for (int i0 = 0; i0 < na; i0 += 1024 * RPT) {
     int s[RPT];
@@ -227,6 +238,11 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
           e.sc_out[row] = pow2_scale(3.0 * e.alpha * d);
         }
         cand[r] = (e.kappa[row] * d <= tol) || it >= max_iter;
+        if (e.mixed) e.dlast[row] = d;
+        if (e.need2 && !cand[r] && !(d <= e.t2_thr)) {
+          const int pos = pos_next[row];
+          if (pos >= 0) e.need2[pos >> 7] = 1;
+        }
         if (cand[r]) {
           e.state[row] = SLOT_CAND;
           e.dtrig[row] = d;
@@ -421,15 +437,30 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int
     ncold = block_append(take, s, e.l_cold, ncold);
   }
   int na = 0;
-  if (nd > 0) {   // only a finished chunk changes the live list, but rebuilding is cheap
+  if (e.need2) {
+    // sorted by phase: rows in the late phase of their QP first, so that whole 128-row operand tiles of the next
+    // layout can run with one operator term (rows only move early -> late until the next rebuild)
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i0 = 0; i0 < S; i0 += 1024) {
+        const int s = i0 + threadIdx.x;
+        bool live = false, late = false;
+        if (s < S) {
+          const int st = e.state[s];
+          live = st == SLOT_ITER || st == SLOT_RENEW || st == SLOT_ANCHOR || st == SLOT_EMIT;
+          late = st == SLOT_ITER && e.dlast[s] <= e.t2_thr;
+        }
+        na = block_append(live && (late == (pass == 0)), s, e.l_active, na);
+      }
+  } else if (nd > 0) {   // only a finished chunk changes the live list, but rebuilding is cheap
     for (int i0 = 0; i0 < S; i0 += 1024) {
       const int s = i0 + threadIdx.x;
       const bool live = s < S && (e.state[s] == SLOT_ITER || e.state[s] == SLOT_RENEW || e.state[s] == SLOT_ANCHOR ||
                                   e.state[s] == SLOT_EMIT);
       na = block_append(live, s, e.l_active, na);
     }
+  } else {
+    na = e.counts[N_ACTIVE];
   }
-  if (nd == 0) na = e.counts[N_ACTIVE];
   if (e.mixed) {
     // Operand layout for the pass after next = the live list of the next loop (the tensor-core operand is
     // rewritten every pass, so it is re-compacted for free, one pass behind the live list).
@@ -608,6 +639,8 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
   NNMPC_TRY(h->chunk.ensure(B));
   NNMPC_TRY(h->cold.ensure(B));
   NNMPC_TRY(h->lp_layout.ensure(4 * B));
+  NNMPC_TRY(h->dlast.ensure(B));
+  NNMPC_TRY(h->need2.ensure((B + 127) / 128 + 2));
   NNMPC_TRY(h->dres.ensure(B));
   NNMPC_TRY(h->kres.ensure(B));
   h->cap = B;
@@ -659,6 +692,10 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   e.chunk = h->chunk.p; e.cold = h->cold.p; e.n_chunks = Btot;
   e.lp_list = h->lp_layout.p; e.lp_pos = h->lp_layout.p + 2 * (long long)B;
   e.tail_rows = h->tail_rows >= 0 ? h->tail_rows : (B / 16 > 48 ? B / 16 : 48);
+  const bool t2skip = mixed && h->t2_factor > 0.0;
+  e.dlast = h->dlast.p; e.t2_thr = h->t2_factor * tol; e.need2 = t2skip ? h->need2.p : nullptr;
+  if (t2skip) NNMPC_CUDA(cudaMemsetAsync(h->need2.p, 1, (size_t)((B + 127) / 128 + 2), st));   // first pass: both terms everywhere
+  NNMPC_CUDA(cudaMemsetAsync(h->dlast.p, 0x7f, (size_t)B * sizeof(double), st));              // large: nothing is late yet
   e.mixed = mixed; e.sc_in = h->lps.sc_in.p; e.sc_out = h->lps.sc_out.p; e.stats = h->stats; e.alpha = q->alpha;
   k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0, cont ? 0 : 1);
   count_launch();
@@ -715,6 +752,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   for (; loop < max_loops && !finished; ++loop) {
     // 1. one Douglas-Rachford iteration for every live trajectory
     const bool full = (loop % cad) == 0;
+    const int* pos_next = e.lp_pos;      // mixed mode: layout the NEXT pass reads (set below)
     if (mixed) {
       // 1a. exact anchors for the rows that start a QP: x = Top w - c (INT8-sliced tensor-core apply, or the
       //     DMMA kernel), one full-precision step, first fp16 increment
@@ -731,14 +769,15 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
         if (oz) NNMPC_TRY(oz_anchor(&q->ozTop, &h->ozr, e.l_anchor, cnt, B, q->W0.p, q->C.p, h->lps.X.p, n, h->device, st));
         else NNMPC_TRY(lp_anchor_gemm(e.l_anchor, cnt, B, q->W0.p, q->Top, q->C.p, &h->lps, st));
         NNMPC_TRY(lp_dr_first(e.l_anchor, cnt, B, &h->lps, h->V.p, q->W0.p, h->lb.p, h->ub.p, e.state, e.it, SLOT_ITER,
-                              nu, q->alpha, pos_r, st));
+                              nu, q->alpha, pos_r, st, e.need2));
         if (prof64) prof_end(span64, st, 0.0, 1, 1);
       }
       // 1b. tensor-core pass (tcgen05, fp16 increments of the operand, state in FP64) over every live row
       ProfSpan span;
       const bool prof = prof_begin(&span, st);
       NNMPC_TRY(lp_iterate(&q->lpop, &h->lps, B, list_r, e.counts + E_LP, pos_w, h->V.p, h->lb.p, h->ub.p, e.state,
-                           SLOT_ITER, e.dres, nu, q->alpha, h->device, st));
+                           SLOT_ITER, e.dres, nu, q->alpha, h->device, st, e.need2, h->tile_stat));
+      pos_next = pos_w;
       if (prof) prof_end(span, st, 0.0, 1);
       // 1c. tail: with few live rows left the same update runs as skinny FP64 GEMMs (counts[E_TAIL] rows, else 0)
       const bool prof64b = prof_begin(&span64, st);
@@ -764,7 +803,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       double* t = Wc; Wc = Wn; Wn = t;
     }
     // 2-4. candidates -> exact KKT check -> done list
-    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter, (cad > 1 && (loop % cad) != 1 % cad) ? 1 : 0, full ? 1 : 0);
+    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter, (cad > 1 && (loop % cad) != 1 % cad) ? 1 : 0, full ? 1 : 0, pos_next, B);
     if (!full) {
       count_launch();
       continue;
@@ -791,7 +830,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       // for w_lp = z + g / rho; the row goes on with the first increment of what is left to deliver
       NNMPC_TRY(lp_reanchor(e.l_cand, e.counts + N_CAND, B, e.state, SLOT_EMIT, h->Z.p, q->rinv, &h->lps, st));
       NNMPC_TRY(lp_emit(e.l_cand, e.counts + N_CAND, B, e.state, SLOT_EMIT, SLOT_ITER, &h->lps, h->V.p, h->lb.p,
-                        h->ub.p, e.dtrig, nu, q->alpha, e.lp_pos + (long long)(lay ^ 1) * B, st));
+                        h->ub.p, e.dtrig, nu, q->alpha, e.lp_pos + (long long)(lay ^ 1) * B, st, e.need2));
     }
     // 5. first move, dataset row, plant step for the done rows
     k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
@@ -884,6 +923,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
+  h->t2_factor = 100.0;
+  h->tile_stat = nullptr;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = h->tot_qps_active = h->tot_active = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
@@ -906,6 +947,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, 2 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMalloc((void**)&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+  if (rc == 0) cu(cudaMalloc((void**)&h->tile_stat, 2 * sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMemset(h->tile_stat, 0, 2 * sizeof(unsigned long long)), "cudaMemset");
   if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 8 * sizeof(unsigned long long)), "cudaMallocHost");
   for (int i = 0; i < POLL_RING && rc == 0; ++i) cu(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming), "cudaEventCreate");
   if (rc < 0) {          // a half-built handle is released, not leaked
@@ -924,10 +967,13 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   if (h->counts) cudaFree(h->counts);
   if (h->rowiters) cudaFree(h->rowiters);
   if (h->stats) cudaFree(h->stats);
+  if (h->tile_stat) cudaFree(h->tile_stat);
   if (h->pin) cudaFreeHost(h->pin);
   h->lps.release();
   h->ozr.release();
   h->lp_layout.release();
+  h->dlast.release();
+  h->need2.release();
   for (int i = 0; i < POLL_RING; ++i)
     if (h->poll_ev[i]) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
@@ -983,6 +1029,22 @@ int nnmpc_sim_set_capture(nnmpc_sim_t* h, double* useq_dev, double* cost_dev) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_capture: null handle");
   h->cap_useq = useq_dev;
   h->cap_cost = cost_dev;
+  return 0;
+}
+
+int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_one_term_threshold: null handle");
+  if (!(factor >= 0.0) || !(factor <= 1e12)) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_one_term_threshold: factor must be in [0, 1e12]");
+  h->t2_factor = factor;
+  return 0;
+}
+
+int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2) {
+  if (!h || !out2) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_tile_stats: null argument");
+  DeviceGuard dg(h->device);
+  unsigned long long t[2] = {0, 0};
+  NNMPC_CUDA(cudaMemcpy(t, h->tile_stat, sizeof(t), cudaMemcpyDeviceToHost));
+  out2[0] = (long long)t[0]; out2[1] = (long long)t[1];
   return 0;
 }
 

@@ -289,7 +289,11 @@ def ipm_qp(P, q, G, h, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100,
             info = dict(status="optimal", iters=it)
             break
         d = z / s
-        cf = kkt_factor(d)
+        try:
+            cf = kkt_factor(d)
+        except np.linalg.LinAlgError:          # z/s has left the range a Cholesky survives: as converged as FP64 allows
+            info = dict(status="numerical", iters=it)
+            break
         mu = gap / m
 
         def step(rc):
@@ -314,7 +318,32 @@ def ipm_qp(P, q, G, h, abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100,
 
 
 def solve_general_qp(P, q, G, h):
-    """Inequality QP (re-parameterised regulator, linearMPC.py:476-493): IPM to tight tolerance."""
-    x, info = ipm_qp(P, q, G, h, abstol=1e-13, reltol=1e-13, feastol=1e-12, maxiters=200,
-                     rematerialise=False)
-    return x, info
+    """Inequality QP (re-parameterised regulator, linearMPC.py:476-493): interior point to a tight tolerance,
+    then an active-set polish - the constraints the interior point identifies as active are imposed as equalities
+    and the KKT system is solved directly; the polished point is kept when it is feasible with multipliers of the
+    right sign (then it is the exact minimiser), otherwise the interior-point answer stands."""
+    P, G = np.asarray(P, float), np.asarray(G, float)
+    q, h = np.asarray(q, float).reshape(-1), np.asarray(h, float).reshape(-1)
+    x, info = ipm_qp(P, q, G, h, abstol=1e-13, reltol=1e-13, feastol=1e-12, maxiters=200, rematerialise=False)
+    x = x.reshape(-1)
+    slack = h - G @ x
+    act = np.flatnonzero(slack <= 1e-7 * (1.0 + np.abs(h)))
+    if act.size:
+        Ga = G[act]
+        # drop linearly dependent rows (e.g. u <= ub and -u <= -lb with lb == ub)
+        _, r, piv = scipy.linalg.qr(Ga.T, mode="economic", pivoting=True)
+        rank = int(np.sum(np.abs(np.diag(r)) > 1e-10 * max(1.0, abs(r[0, 0]))))
+        act = act[np.sort(piv[:rank])]
+        Ga = G[act]
+        n, k = P.shape[0], act.size
+        K = np.block([[P, Ga.T], [Ga, np.zeros((k, k))]])
+        try:
+            sol = scipy.linalg.solve(K, np.concatenate([-q, h[act]]), assume_a="sym")
+            xp, lam = sol[:n], sol[n:]
+            if np.all(G @ xp <= h + 1e-10 * (1.0 + np.abs(h))) and np.all(lam >= -1e-9 * (1.0 + np.abs(lam).max())):
+                x = xp
+                info = dict(info, polished=True, n_active=int(k))
+        except np.linalg.LinAlgError:
+            pass
+    info["cost"] = float(0.5 * x @ (P @ x) + q @ x)
+    return x.reshape(-1, 1), info

@@ -3,23 +3,32 @@
 # keeping are copied to profiles/).
 set -x
 mkdir -p gpurun_out
-timeout -k 10 900 python -m pytest tests/test_gpu_cdu_fullsize.py tests/test_gpu_reparam.py -x -q -s 2>&1 | tail -40 > gpurun_out/r02a_j3.log
-tail -25 gpurun_out/r02a_j3.log
-timeout -k 10 600 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_cdu_fullsize.py --deselect tests/test_gpu_reparam.py 2>&1 | tail -8 > gpurun_out/r02a_pytest.log
-cat gpurun_out/r02a_pytest.log
-# conditioning sweep of the stand-in plant (short steps: 16384 slots x 8 sim steps, 2 timed steps)
-for cfg in "0.7 0.1" "2 0.1" "5 0.1" "0.7 0.01" "5 0.01"; do
-  set -- $cfg
-  timeout -k 10 400 python bench.py --traj 16384 --slab 8 --steps 2 --warmup 3 --no-cpu-baseline --gain-norm $1 --r-weight $2 --max-iter 20000 \
-    > gpurun_out/r02a_cond_g$1_r$2.json 2> gpurun_out/r02a_cond_g$1_r$2.err
-  tail -c 600 gpurun_out/r02a_cond_g$1_r$2.err
-  python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/r02a_cond_g$1_r$2.json"))
-    print("COND", "$1", "$2", d["conditioning"], d["iterations"], d["value"], d["time_breakdown"])
-except Exception as e:
-    print("COND failed", "$1", "$2", e)
-PY
-done
-timeout -k 10 120 python tools/probes/lp_accum_error.py 2>&1 | tail -5 > gpurun_out/r02a_lp_accum.txt; cat gpurun_out/r02a_lp_accum.txt
+T=r02b
+timeout -k 10 900 python -m pytest tests/test_gpu_cdu_fullsize.py tests/test_gpu_reparam.py tests/test_gpu_online.py -q -s > gpurun_out/${T}_newtests.log 2>&1
+tail -5 gpurun_out/${T}_newtests.log
+timeout -k 10 300 python -m pytest tests/test_gpu_parity.py -q -x -k "closed_loop or sharding or chunk_queue or resume" > gpurun_out/${T}_parity.log 2>&1
+tail -3 gpurun_out/${T}_parity.log
+timeout -k 10 120 python tools/probes/lp_accum_error.py 2>&1 | tail -5 > gpurun_out/${T}_lp_accum.txt; cat gpurun_out/${T}_lp_accum.txt
+# A/B of the tensor-core pass: one-term tiles (factor 0 = off), CTA-pair kernel, 16 epilogue warps
+ab() {  # name, env...
+  name=$1; shift
+  env "$@" timeout -k 10 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ab_$name.json 2> gpurun_out/${T}_ab_$name.err
+  tail -c 300 gpurun_out/${T}_ab_$name.err; cat gpurun_out/${T}_ab_$name.json
+}
+E16=$PWD/industrial_nnmpc_2021_b200/csrc/libnnmpc_e16.so
+ab t2off NNMPC_T2_FACTOR=0
+ab t2_100 NNMPC_T2_FACTOR=100
+ab t2_1000 NNMPC_T2_FACTOR=1000
+ab pair8 NNMPC_LP_KERNEL=pair NNMPC_T2_FACTOR=100
+ab pair16 NNMPC_LP_KERNEL=pair NNMPC_T2_FACTOR=100 NNMPC_LIB_PATH=$E16
+ab single16 NNMPC_T2_FACTOR=100 NNMPC_LIB_PATH=$E16
+# first lines of the other BASELINE workloads (FP64 DMMA paths)
+timeout -k 10 600 python bench.py --workload cstr_qp_1m --steps 2 --warmup 3 > gpurun_out/${T}_cstr_qp_1m.json 2> gpurun_out/${T}_cstr_qp_1m.err
+tail -c 300 gpurun_out/${T}_cstr_qp_1m.err; cut -c1-1500 gpurun_out/${T}_cstr_qp_1m.json
+timeout -k 10 600 python bench.py --workload nn_10m --steps 3 --warmup 3 > gpurun_out/${T}_nn_10m.json 2> gpurun_out/${T}_nn_10m.err
+tail -c 300 gpurun_out/${T}_nn_10m.err; cut -c1-1500 gpurun_out/${T}_nn_10m.json
+# ncu: the tensor-core pass in full (source-level stall reasons), then the launch list of a short run
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:lp_gemm_kernel -s 60 -c 2 -o gpurun_out/${T}_lp_gemm \
+  python bench.py --traj 16384 --slab 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ncu_full.log 2>&1
+tail -3 gpurun_out/${T}_ncu_full.log
+ls -la gpurun_out | tail -30
