@@ -172,7 +172,7 @@ def _config(args, world=None):
     return {"workload": "CDU structured NN batched policy evaluation (BASELINE.json configs[3]): RegulatorLayerWithUprev "
                         "568-832-832-832-32, u = us + f(x,uprev,xs,us) - f(xs,us,xs,us)",
             "Nx": 252, "Nu": 32, "hidden": NN_HIDDEN, "batch_per_gpu": args.batch or 10_000_000,
-            "nn_precision": os.environ.get("NNMPC_MLP", "default"),
+            "nn_precision": os.environ.get("NNMPC_MLP", "tc"),
             "l2": "no flush: 45 GB of inputs per step",
             "parallelism": f"samples sharded over {world} GPU(s), no collective"}
 
@@ -888,7 +888,7 @@ def run_nn(args):
     dims = [2 * nx + 2 * nu] + NN_HIDDEN + [nu]
     flops_state = 2 * sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1))      # both passes f(x,..) and f(xs,..)
     achieved = value / world * flops_state / 1e12
-    lowp = os.environ.get("NNMPC_MLP", "tc") != "f64" and hasattr(L, "nnmpc_mlp_set_precision")
+    lowp = layer.precision == "tc"
     peaks, peak_src = _peaks()
     best = _dgemm_peak(ctx)
     peak = float(peaks.get("bf16_tflops_sustained") or 1386.0) if lowp else best

@@ -189,6 +189,10 @@ int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_
                      const int* dims, const double* const* weights_host,
                      const double* const* biases_host, int device);
 int nnmpc_mlp_destroy(nnmpc_mlp_t* h);
+/* Arithmetic of the Dense layers: 1 (default) = tcgen05 tensor cores, activations and weights as two-term fp16 splits
+ * (three products, 22 significant bits) with fp32 TMEM accumulation and FP64 bias / ReLU / output assembly - within the
+ * 1e-5 output tolerance, steady-state identity u = us exact; 0 = FP64 DMMA GEMMs (~1e-13 of the NumPy form). */
+int nnmpc_mlp_set_precision(nnmpc_mlp_t* h, int mode);
 /* x,xs dev B x nx; uprev,us dev B x nu (uprev ignored when !with_uprev); out dev B x nu.
  * xscale dev nx or NULL (x/xscale, xs/xscale, :863-866); ulb/uub dev nu or NULL (clip, :888-892). */
 int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev,

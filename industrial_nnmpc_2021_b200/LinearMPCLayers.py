@@ -1,5 +1,6 @@
 """Drop-in mirror of the structured-network layers of /root/reference/lib/LinearMPCLayers.py
-(forward pass only), evaluated by the fused FP64 tensor-core kernels of libnnmpc.so.
+(forward pass only), evaluated by the fused tensor-core kernels of libnnmpc.so (tcgen05 split-fp16
+layers by default, FP64 DMMA on request).
 
     RegulatorLayerWithUprev    u = us + NN(x, uprev, xs, us) - NN(xs, us, xs, us)     (:15-64)
     RegulatorLayerWithoutUprev u = us + NN(x, xs, us)        - NN(xs, xs, us)         (:66-115)
@@ -23,7 +24,14 @@ from . import _lib
 class _StructuredRegulatorLayer:
     _with_uprev = True
 
-    def __init__(self, layer_dims, trainable=True, name=None, *, device=None, seed=None):
+    def __init__(self, layer_dims, trainable=True, name=None, *, device=None, seed=None, precision=None):
+        """``precision`` (additive): "tc" - Dense layers on the tcgen05 tensor cores as split-fp16 products, outputs
+        within 1e-5 of the float64 Keras layer - or "f64" (FP64 tensor-core GEMMs).  Default: environment variable
+        NNMPC_MLP, else "tc"."""
+        import os
+        self.precision = precision or os.environ.get("NNMPC_MLP", "tc")
+        if self.precision not in ("tc", "f64"):
+            raise ValueError("precision must be 'tc' or 'f64'")
         self.layer_dims = [int(d) for d in layer_dims]
         self.trainable, self.name = trainable, name
         self._seed = seed
@@ -89,6 +97,7 @@ class _StructuredRegulatorLayer:
         hnd = C.c_void_p()
         rc = L.nnmpc_mlp_create(C.byref(hnd), self._nx, self._nu, int(self._with_uprev), nl, darr, warr, barr, dev)
         _lib.check(rc, "nnmpc_mlp_create")
+        _lib.check(L.nnmpc_mlp_set_precision(hnd, 1 if self.precision == "tc" else 0), "nnmpc_mlp_set_precision")
         self._handle, self._dev = hnd, dev
         self._weights = [np.array(w, dtype=np.float64) for w in weights]
 
@@ -173,10 +182,10 @@ class RegulatorModel:
     """Keras-functional-model look-alike (LinearMPCLayers.py:117-133).  Note the reference drops
     ``regulator_dims[0]`` (``layer_dims = regulator_dims[1:]``, :128-131); so does this class."""
 
-    def __init__(self, Nx, Nu, regulator_dims, nnwithuprev=True, *, device=None, seed=None):
+    def __init__(self, Nx, Nu, regulator_dims, nnwithuprev=True, *, device=None, seed=None, precision=None):
         self.Nx, self.Nu, self.nnwithuprev = Nx, Nu, nnwithuprev
         cls = RegulatorLayerWithUprev if nnwithuprev else RegulatorLayerWithoutUprev
-        self.regulator = cls(layer_dims=regulator_dims[1:], device=device, seed=seed)
+        self.regulator = cls(layer_dims=regulator_dims[1:], device=device, seed=seed, precision=precision)
         self.regulator.build(Nx, Nu)
         self.input_names = ["x", "uprev", "xs", "us"] if nnwithuprev else ["x", "xs", "us"]
 

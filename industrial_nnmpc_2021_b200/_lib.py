@@ -60,6 +60,7 @@ SIGNATURES = {
     "nnmpc_mlp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(vp),
                                    C.POINTER(vp), C.c_int]),
     "nnmpc_mlp_destroy": (C.c_int, [vp]),
+    "nnmpc_mlp_set_precision": (C.c_int, [vp, C.c_int]),
     "nnmpc_mlp_forward": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_mlp_forward_host": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_lp_gemm_test": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, vp, C.c_int, vp]),

@@ -92,7 +92,7 @@ class NeuralNetworkController:
     (:868-875) except that it takes UNscaled x, xs and applies ``xscale`` itself.
     """
 
-    def __init__(self, *, regulator_weights, xscale, nnwithuprev, ulb, uub, device=None):
+    def __init__(self, *, regulator_weights, xscale, nnwithuprev, ulb, uub, device=None, precision=None):
         from .LinearMPCLayers import RegulatorLayerWithUprev, RegulatorLayerWithoutUprev
         self.regulator_weights = regulator_weights
         self.xscale = np.asarray(xscale, dtype=np.float64).reshape(-1)
@@ -100,7 +100,7 @@ class NeuralNetworkController:
         self.ulb, self.uub = ulb, uub
         dims = [w.shape[1] for w in regulator_weights[0::2]]
         cls = RegulatorLayerWithUprev if nnwithuprev else RegulatorLayerWithoutUprev
-        self.layer = cls(layer_dims=dims, device=device)
+        self.layer = cls(layer_dims=dims, device=device, precision=precision)
         self.layer.set_weights(regulator_weights)
 
     def control_input_batch(self, x, uprev, xs, us):

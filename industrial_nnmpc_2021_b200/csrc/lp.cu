@@ -115,7 +115,7 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   const double tile_mb = 2.0 * bn_tile * (double)op->ldh * 2.0 / 1048576.0;
   int group_cols = (int)(24.0 / tile_mb);
   if (group_cols < 1) group_cols = 1;
-  lp::LpShape g{B, s->n, s->n, len_r, group_cols, need2, tile_stat};
+  lp::LpShape g{B, s->n, s->n, len_r, group_cols, need2, tile_stat, 0, 0};
   cudaError_t e = lp_use_pair()
                       ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
                       : lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
@@ -186,7 +186,7 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
     if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
       rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
-      lp::LpShape g{M, N, K, nullptr, 2, nullptr, nullptr};
+      lp::LpShape g{M, N, K, nullptr, 2, nullptr, nullptr, 0, 0};
       const EpiLpStore::Params ep{C, N, 1.0 / op.scale};
       cudaError_t e = pair ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
                            : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);

@@ -213,6 +213,12 @@ struct LpShape {
   // traffic.  tile_stat (nullable): [0] += tiles run with one term, [1] += tiles run with both (accounting).
   const unsigned char* need2;
   unsigned long long* tile_stat;
+  // Three-product form for a two-term A operand (structured-network layers, mlp_tc.cuh): A = [A_hi | A_lo] stacked
+  // along K.  k-blocks >= b_wrap read the operator again from its first k-block (0: no wrap), and only the first
+  // kb2 k-blocks multiply the second operator term (<= 0: all), so that
+  //     acc = A_hi B1' + A_hi B2' + A_lo B1'      (the 2^-22 term A_lo B2' is never formed).
+  int kb2;
+  int b_wrap;
 };
 
 // Tile order of the persistent CTAs.  The operator (2 x n x n fp16, 80 MB at n = 4480) does not fit the part of
@@ -298,10 +304,12 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * T::STAGE_BYTES;
-          mbar_expect_tx(full + s, two ? T::STAGE_BYTES : T::A_BYTES + T::B_BYTES);
+          const bool two_kb = two && (g.kb2 <= 0 || kb < g.kb2);
+          const int kbb = (g.b_wrap > 0 && kb >= g.b_wrap) ? kb - g.b_wrap : kb;
+          mbar_expect_tx(full + s, two_kb ? T::STAGE_BYTES : T::A_BYTES + T::B_BYTES);
           tma_load_2d(st, &tmA, full + s, kb * BK, bm * BM);
-          tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
-          if (two) tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kb * BK, bn * T::BN, L2_EVICT_LAST);
+          tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
+          if (two_kb) tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -333,7 +341,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
             umma_f16(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          if (two) {
+          if (two && (g.kb2 <= 0 || kb < g.kb2)) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
           }

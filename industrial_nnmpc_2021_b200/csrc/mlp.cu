@@ -9,7 +9,12 @@
 // layer is a single FP64 tensor-core GEMM with bias+ReLU fused into the epilogue, and the last
 // layer's epilogue forms us + out(2b) - out(2b+1) (+ clip) with one warp shuffle - the difference
 // never goes through memory.
+//
+// Two arithmetic modes (nnmpc_mlp_set_precision): the layers run on the tcgen05 tensor cores as three-product
+// split-fp16 GEMMs with fp32 TMEM accumulation (mlp_tc.cuh; default, within the 1e-5 tolerance of the north star,
+// steady-state identity exact), or as FP64 DMMA GEMMs (~1e-13).
 #include "qp.cuh"
+#include "mlp_tc.cuh"
 
 struct nnmpc_mlp {
   int nx, nu, with_uprev, L, device;
@@ -20,6 +25,15 @@ struct nnmpc_mlp {
   int maxw;            // widest hidden activation (ld)
   nnmpc::DevBuf<double> act0, act1;
   nnmpc::DevBuf<double> hx, hup, hxs, hus, hout, hscale, hlb, hub;
+  // tcgen05 mode
+  int tc_mode;                      // 1: split-fp16 tcgen05 layers, 0: FP64 DMMA
+  nnmpc::MlpTcLayer tcl[16];
+  int kp_max;
+  long long tc_rows;                // operand rows the buffers / tensor maps below are sized for
+  nnmpc::DevBuf<__half> tcA[2];     // ping-pong operands [rows][2 * kp_max]: [hi | lo]
+  CUtensorMap tmA[16];              // layer l reads tcA[l & 1] as rows x 2 kp_l
+  nnmpc::DevBuf<double> tcsc[2];    // per-row scales
+  nnmpc::DevBuf<float> tcamax[2];   // per-row max |entry|
 };
 
 namespace nnmpc {
@@ -125,6 +139,77 @@ static int mlp_forward_device(nnmpc_mlp* h, long long B, const double* x, const 
   return 0;
 }
 
+// (out x ld) FP64 transposed weights -> two fp16 terms (rows padded with zeros, kp columns)
+__global__ void k_split_weights(const double* __restrict__ Wt, int rows, int cols, int ld, int kp, double s,
+                                __half* __restrict__ T1, __half* __restrict__ T2) {
+  const long long total = (long long)rows * kp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / kp;
+    const int c = (int)(i - r * kp);
+    const double t = c < cols ? Wt[r * ld + c] * s : 0.0;
+    __half h1, h2;
+    mlp_split(t, h1, h2);
+    T1[i] = h1;
+    T2[i] = h2;
+  }
+}
+
+static int mlp_tc_ensure(nnmpc_mlp* h, long long rows, cudaStream_t st) {
+  if (rows <= h->tc_rows) return 0;
+  const long long rows_pad = (rows + 2 * lp::BM - 1) / (2 * lp::BM) * (2 * lp::BM);
+  const long long pitch = 2ll * h->kp_max;
+  for (int b = 0; b < 2; ++b) {
+    NNMPC_TRY(h->tcA[b].ensure((size_t)rows_pad * pitch));
+    NNMPC_CUDA(cudaMemsetAsync(h->tcA[b].p, 0, (size_t)rows_pad * pitch * sizeof(__half), st));
+    NNMPC_TRY(h->tcsc[b].ensure((size_t)rows_pad));
+    NNMPC_TRY(h->tcamax[b].ensure((size_t)rows_pad));
+  }
+  for (int l = 0; l < h->L; ++l)
+    if (!lp::make_tmap_f16(&h->tmA[l], h->tcA[l & 1].p, rows_pad, 2ll * h->tcl[l].kp, pitch, lp::BM))
+      return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the structured-network operands");
+  h->tc_rows = rows_pad;
+  return 0;
+}
+
+static int mlp_forward_tc(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
+                          const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
+                          cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int nx = h->nx, nu = h->nu, L = h->L;
+  long long chunk = B < 131072 ? B : 131072;            // samples per pass: 2 x chunk operand rows
+  NNMPC_TRY(mlp_tc_ensure(h, 2 * chunk, st));
+  const long long pitch = 2ll * h->kp_max;
+  const int sms = device_sm_count(h->device);
+  for (long long b0 = 0; b0 < B; b0 += chunk) {
+    const long long nb = B - b0 < chunk ? B - b0 : chunk;
+    const int M = (int)(2 * nb);
+    k_mlp_pack_tc<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(x + b0 * nx, uprev ? uprev + b0 * nu : nullptr, xs + b0 * nx,
+                                                           us + b0 * nu, xscale, h->tcA[0].p, pitch, h->tcl[0].kp,
+                                                           h->tcsc[0].p, h->tcamax[0].p, nb, nx, nu, h->with_uprev);
+    count_launch();
+    for (int l = 0; l < L; ++l) {
+      const MlpTcLayer& W = h->tcl[l];
+      const int in = l & 1, on = in ^ 1;
+      lp::LpShape g{M, W.out, 2 * W.kp, nullptr, 0, nullptr, nullptr, W.kp / lp::BK, W.kp / lp::BK};
+      cudaError_t e;
+      if (l < L - 1) {
+        NNMPC_CUDA(cudaMemsetAsync(h->tcamax[on].p, 0, (size_t)M * sizeof(float), st));
+        EpiMlpHidden::Params ep{h->tcA[on].p, pitch, h->tcl[l + 1].kp, h->bias[l], h->tcsc[in].p, h->tcamax[in].p,
+                                h->tcsc[on].p, h->tcamax[on].p, 1.0 / W.scale, W.w1norm, W.bmax};
+        e = lp::launch_lp_gemm<MlpTile, EpiMlpHidden>(h->tmA[l], W.tm1, W.tm2, g, ep, sms, st);
+      } else {
+        EpiMlpOut::Params ep{out + b0 * nu, us + b0 * nu, ulb, uub, h->tcsc[in].p, 1.0 / W.scale, nu};
+        e = lp::launch_lp_gemm<MlpTile, EpiMlpOut>(h->tmA[l], W.tm1, W.tm2, g, ep, sms, st);
+      }
+      count_launch();
+      if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "structured-network tcgen05 launch failed: %s", cudaGetErrorString(e));
+    }
+  }
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace nnmpc
 
 using namespace nnmpc;
@@ -153,25 +238,79 @@ int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_
     h->ld[i] = (dims[i] + 1) & ~1;
     if (i < num_layers && h->ld[i] > h->maxw) h->maxw = h->ld[i];
   }
-  for (int l = 0; l < num_layers; ++l) {
+  h->tc_mode = 1;
+  h->tc_rows = 0;
+  h->kp_max = 0;
+  for (int l = 0; l < 16; ++l) h->Wt[l] = h->bias[l] = nullptr;
+  int rc = 0;
+  for (int l = 0; l < num_layers && rc == 0; ++l) {
     const int in = dims[l], outw = dims[l + 1], ld = h->ld[l];
     double* tmp = new (std::nothrow) double[(size_t)outw * ld];
-    if (!tmp) return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+    if (!tmp) { rc = set_error(NNMPC_ERR_NOMEM, "out of host memory"); break; }
     const double* W = weights_host[l];  // in x out, row-major (Keras kernel layout)
+    double wmax = 0.0, w1 = 0.0;
     for (int o = 0; o < outw; ++o) {
-      for (int i = 0; i < in; ++i) tmp[(size_t)o * ld + i] = W[(size_t)i * outw + o];
+      double a = 0.0;
+      for (int i = 0; i < in; ++i) {
+        const double w = W[(size_t)i * outw + o];
+        tmp[(size_t)o * ld + i] = w;
+        a += fabs(w);
+        if (fabs(w) > wmax) wmax = fabs(w);
+      }
       for (int i = in; i < ld; ++i) tmp[(size_t)o * ld + i] = 0.0;
+      if (a > w1) w1 = a;
     }
-    int rc = upload(&h->Wt[l], tmp, (size_t)outw * ld);
+    rc = upload(&h->Wt[l], tmp, (size_t)outw * ld);
     delete[] tmp;
-    if (rc < 0) return rc;
-    h->bias[l] = nullptr;
+    if (rc < 0) break;
+    MlpTcLayer& T = h->tcl[l];
+    T.in = in; T.out = outw; T.kp = (in + lp::BK - 1) / lp::BK * lp::BK;
+    if (T.kp > h->kp_max) h->kp_max = T.kp;
+    T.w1norm = w1 * 1.0000001;
+    T.bmax = 0.0;
     if (l < num_layers - 1) {
-      if (!biases_host || !biases_host[l]) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_create: missing bias %d", l);
-      NNMPC_TRY(upload(&h->bias[l], biases_host[l], (size_t)outw));
+      if (!biases_host || !biases_host[l]) { rc = set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_create: missing bias %d", l); break; }
+      for (int o = 0; o < outw; ++o) T.bmax = fmax(T.bmax, fabs(biases_host[l][o]));
+      rc = upload(&h->bias[l], biases_host[l], (size_t)outw);
+      if (rc < 0) break;
+    }
+    // two-term fp16 operator: scale = the power of two that puts max |s W| in [512, 1024)
+    int ex = 0;
+    frexp(wmax > 0.0 ? wmax : 1.0, &ex);
+    T.scale = ldexp(1.0, 10 - ex);
+    const long long rows_pad = ((long long)outw + lp::BN2 - 1) / lp::BN2 * lp::BN2;
+    rc = T.T1.ensure((size_t)rows_pad * T.kp);
+    if (rc == 0) rc = T.T2.ensure((size_t)rows_pad * T.kp);
+    if (rc < 0) break;
+    if (cudaMemset(T.T1.p, 0, (size_t)rows_pad * T.kp * sizeof(__half)) != cudaSuccess ||
+        cudaMemset(T.T2.p, 0, (size_t)rows_pad * T.kp * sizeof(__half)) != cudaSuccess) {
+      rc = set_error(NNMPC_ERR_CUDA, "nnmpc_mlp_create: cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    k_split_weights<<<148 * 4, 256>>>(h->Wt[l], outw, in, ld, T.kp, T.scale, T.T1.p, T.T2.p);
+    count_launch();
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      rc = set_error(NNMPC_ERR_CUDA, "nnmpc_mlp_create: weight split failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (!lp::make_tmap_f16(&T.tm1, T.T1.p, rows_pad, T.kp, T.kp, MlpTile::BN) ||
+        !lp::make_tmap_f16(&T.tm2, T.T2.p, rows_pad, T.kp, T.kp, MlpTile::BN)) {
+      rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the structured-network weights");
+      break;
     }
   }
+  if (rc < 0) {          // a half-built handle is released, not leaked
+    nnmpc_mlp_destroy(h);
+    return rc;
+  }
   *out = h;
+  return 0;
+}
+
+int nnmpc_mlp_set_precision(nnmpc_mlp_t* h, int mode) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_set_precision: null handle");
+  if (mode != 0 && mode != 1) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_set_precision: mode must be 0 (FP64 DMMA) or 1 (tcgen05 split fp16)");
+  h->tc_mode = mode;
   return 0;
 }
 
@@ -179,9 +318,12 @@ int nnmpc_mlp_destroy(nnmpc_mlp_t* h) {
   if (!h) return 0;
   DeviceGuard dg(h->device);
   for (int l = 0; l < h->L; ++l) {
-    cudaFree(h->Wt[l]);
+    if (h->Wt[l]) cudaFree(h->Wt[l]);
     if (h->bias[l]) cudaFree(h->bias[l]);
+    h->tcl[l].T1.release();
+    h->tcl[l].T2.release();
   }
+  for (int b = 0; b < 2; ++b) { h->tcA[b].release(); h->tcsc[b].release(); h->tcamax[b].release(); }
   h->act0.release(); h->act1.release();
   h->hx.release(); h->hup.release(); h->hxs.release(); h->hus.release(); h->hout.release();
   h->hscale.release(); h->hlb.release(); h->hub.release();
@@ -198,7 +340,8 @@ int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double
   if ((ulb == nullptr) != (uub == nullptr)) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: ulb/uub both or none");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: negative batch");
   DeviceGuard dg(h->device);
-  return mlp_forward_device(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream);
+  return h->tc_mode ? mlp_forward_tc(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream)
+                    : mlp_forward_device(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream);
 }
 
 int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev, const double* xs,
@@ -230,9 +373,9 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
     NNMPC_CUDA(cudaMemcpyAsync(h->hlb.p, ulb, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
     NNMPC_CUDA(cudaMemcpyAsync(h->hub.p, uub, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
   }
-  NNMPC_TRY(mlp_forward_device(h, B, h->hx.p, h->with_uprev ? h->hup.p : nullptr, h->hxs.p, h->hus.p,
-                               xscale ? h->hscale.p : nullptr, ulb ? h->hlb.p : nullptr, ulb ? h->hub.p : nullptr,
-                               h->hout.p, st));
+  NNMPC_TRY((h->tc_mode ? mlp_forward_tc : mlp_forward_device)(
+      h, B, h->hx.p, h->with_uprev ? h->hup.p : nullptr, h->hxs.p, h->hus.p, xscale ? h->hscale.p : nullptr,
+      ulb ? h->hlb.p : nullptr, ulb ? h->hub.p : nullptr, h->hout.p, st));
   NNMPC_CUDA(cudaMemcpyAsync(out, h->hout.p, b * nu * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));
   return 0;

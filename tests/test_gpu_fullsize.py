@@ -77,7 +77,8 @@ def test_million_cstr_qps(torch_cuda, cstrs_problem):
         assert abs(costh[i] - ei["cost"]) <= COST_RTOL * max(abs(ei["cost"]), 1e-6)
 
 
-def test_ten_million_state_structured_network(torch_cuda):
+@pytest.mark.parametrize("nn_precision,nn_tol", [("tc", 1e-5), ("f64", 1e-9)])
+def test_ten_million_state_structured_network(torch_cuda, nn_precision, nn_tol):
     torch = torch_cuda
     from industrial_nnmpc_2021_b200.LinearMPCLayers import RegulatorLayerWithUprev
     nx, nu, hidden, B = 252, 32, [832, 832, 832], 10_000_000
@@ -90,7 +91,7 @@ def test_ten_million_state_structured_network(torch_cuda):
         ws.append(rng.uniform(-lim, lim, (dims[i], dims[i + 1])))
         if i < len(dims) - 2:
             ws.append(0.1 * rng.standard_normal(dims[i + 1]))
-    layer = RegulatorLayerWithUprev(layer_dims=hidden + [nu])
+    layer = RegulatorLayerWithUprev(layer_dims=hidden + [nu], precision=nn_precision)
     layer.set_weights(ws)
     g = torch.Generator(device=dev).manual_seed(11)
     x = torch.randn((B, nx), dtype=torch.float64, device=dev, generator=g)
@@ -103,7 +104,7 @@ def test_ten_million_state_structured_network(torch_cuda):
     e1.record()
     torch.cuda.synchronize()
     assert tuple(out.shape) == (B, nu) and bool(torch.isfinite(out).all())
-    print(f"\n10M-state structured network (568-832-832-832-32, FP64): {B / (e0.elapsed_time(e1) * 1e-3):.3e} states/s")
+    print(f"\n10M-state structured network (568-832-832-832-32, {nn_precision}): {B / (e0.elapsed_time(e1) * 1e-3):.3e} states/s")
     # steady-state invariance for every row: x = xs, uprev = us  =>  u = us exactly, whatever the weights
     inv = layer([xs, us, xs, us])
     assert bool((inv == us).all())
@@ -116,4 +117,6 @@ def test_ten_million_state_structured_network(torch_cuda):
     pick = torch.as_tensor(rng.integers(0, B, 64), device=dev)
     ins = [t[pick].cpu().numpy() for t in (x, up, xs, us)]
     ref = onn.layer_call(ws, ins, True)
-    assert np.max(np.abs(out[pick].cpu().numpy() - ref)) <= 1e-9 <= NN_TOL
+    err = float(np.max(np.abs(out[pick].cpu().numpy() - ref)))
+    print(f"max |out - NumPy restatement| over 64 sampled rows: {err:.2e}")
+    assert err <= nn_tol <= NN_TOL

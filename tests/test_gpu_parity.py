@@ -420,11 +420,15 @@ def _random_weights(rng, dims):
     return ws
 
 
+@pytest.mark.parametrize("nn_precision,nn_tol", [("tc", NN_TOL), ("f64", 1e-10)])
 @pytest.mark.parametrize("with_uprev,nx,nu,hidden,B", [(True, 12, 6, [224, 224, 224], 300),
                                                         (False, 12, 6, [32, 48], 129),
                                                         (False, 252, 32, [832, 832, 832], 70),
+                                                        (True, 252, 32, [832, 1024, 896], 513),
                                                         (True, 7, 3, [33, 17], 50)])
-def test_structured_network_matches_numpy(torch_cuda, with_uprev, nx, nu, hidden, B):
+def test_structured_network_matches_numpy(torch_cuda, with_uprev, nx, nu, hidden, B, nn_precision, nn_tol):
+    """Both arithmetic modes of the layers: "tc" (tcgen05 split-fp16 products, the default) within the north-star
+    1e-5; "f64" (FP64 DMMA) far inside it.  Steady-state invariance is exact in both."""
     torch = torch_cuda
     from industrial_nnmpc_2021_b200.LinearMPCLayers import RegulatorLayerWithUprev, RegulatorLayerWithoutUprev
     from industrial_nnmpc_2021_b200.controller_evaluation import NeuralNetworkController
@@ -433,15 +437,18 @@ def test_structured_network_matches_numpy(torch_cuda, with_uprev, nx, nu, hidden
     ws = _random_weights(rng, [in_w] + hidden + [nu])
     x, xs = rng.standard_normal((B, nx)), rng.standard_normal((B, nx))
     up, us = rng.uniform(-1, 1, (B, nu)), rng.uniform(-1, 1, (B, nu))
-    layer = (RegulatorLayerWithUprev if with_uprev else RegulatorLayerWithoutUprev)(layer_dims=hidden + [nu])
+    layer = (RegulatorLayerWithUprev if with_uprev else RegulatorLayerWithoutUprev)(layer_dims=hidden + [nu],
+                                                                                    precision=nn_precision)
     layer.set_weights(ws)
     got = [w.shape for w in layer.get_weights()]
     assert got == [w.shape for w in ws]
     inputs = [x, up, xs, us] if with_uprev else [x, xs, us]
     out = layer(inputs)
     ref = onn.layer_call(ws, inputs, with_uprev)
-    assert out.shape == (B, nu) and np.max(np.abs(out - ref)) <= NN_TOL
-    assert np.max(np.abs(out - ref)) <= 1e-10                        # FP64 path: far inside the 1e-5 budget
+    assert out.shape == (B, nu) and np.max(np.abs(out - ref)) <= nn_tol, np.max(np.abs(out - ref))
+    # inputs an order of magnitude away from O(1) (unscaled states): the per-row scales follow them
+    big = [a * 37.0 for a in inputs[:-1]] + [inputs[-1]]
+    assert np.max(np.abs(layer(big) - onn.layer_call(ws, big, with_uprev))) <= nn_tol * 37.0
     # device tensors in -> device tensor out, same numbers
     tin = [torch.tensor(a, device="cuda") for a in inputs]
     assert np.array_equal(layer(tin).cpu().numpy(), out)
@@ -451,18 +458,19 @@ def test_structured_network_matches_numpy(torch_cuda, with_uprev, nx, nu, hidden
     # deployment form: scaling + clip, column by column vs controller_evaluation.py:863-892
     xscale = rng.uniform(0.5, 2.0, nx)
     ulb, uub = -0.3 * np.ones((nu, 1)), 0.4 * np.ones((nu, 1))
-    ctl = NeuralNetworkController(regulator_weights=ws, xscale=xscale, nnwithuprev=with_uprev, ulb=ulb, uub=uub)
+    ctl = NeuralNetworkController(regulator_weights=ws, xscale=xscale, nnwithuprev=with_uprev, ulb=ulb, uub=uub,
+                                  precision=nn_precision)
     ub = ctl.control_input_batch(x, up, xs, us)
     for i in range(0, B, max(1, B // 7)):
         col = lambda a: a[i][:, None]
         r = onn.control_input(ws, col(x), col(up), col(xs), col(us), with_uprev, xscale[:, None], ulb, uub)
-        assert np.max(np.abs(ub[i] - r[:, 0])) <= 1e-10
+        assert np.max(np.abs(ub[i] - r[:, 0])) <= nn_tol
     assert np.all(ub <= 0.4) and np.all(ub >= -0.3)
 
 
 def test_regulator_model_wrapper(torch_cuda):
     from industrial_nnmpc_2021_b200.LinearMPCLayers import RegulatorModel
-    m = RegulatorModel(Nx=12, Nu=6, regulator_dims=[999, 64, 64, 6], nnwithuprev=False, seed=1)
+    m = RegulatorModel(Nx=12, Nu=6, regulator_dims=[999, 64, 64, 6], nnwithuprev=False, seed=1, precision="f64")
     ws = m.get_weights()
     assert [w.shape for w in ws] == [(30, 64), (64,), (64, 64), (64,), (64, 6)]     # dims[0] ignored (:128)
     rng = np.random.default_rng(0)
