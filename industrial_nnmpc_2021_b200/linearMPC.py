@@ -316,19 +316,26 @@ class DenseQPRegulator:
         if n % 2:
             raise NotImplementedError("N*Nu must be even")
         P, tq = self._Pu, self._tqu
-        cho = scipy.linalg.cho_factor(P, lower=True)
-        self.Kunc = -scipy.linalg.cho_solve(cho, tq)                    # unconstrained law u = Kunc x0
-        lmin, lmax = condense.extreme_eigs(P, cho)
+        # One-time dense linear algebra of the set-up (Cholesky of P, (P + D)^-1, extreme eigenvalues).  The reference
+        # does its set-up with NumPy/SciPy on the host (:384-395); at n >= 4096 (CDU horizons x1/x2/x4: n = 4480 /
+        # 8960 / 17920, 2 n^3 up to 1.2e13 flop) the same LAPACK-style calls run on the GPU through torch.linalg
+        # (cuSOLVER, FP64) so that the set-up stays in seconds.  Library code at set-up time only - no solve goes
+        # through it.
+        if n >= 4096 and os.environ.get("NNMPC_SETUP", "gpu") != "host":
+            self.Kunc, (lmin, lmax), self.rho_vec, Top, Mtq = self._setup_dense_gpu(P, tq)
+        else:
+            cho = scipy.linalg.cho_factor(P, lower=True)
+            self.Kunc = -scipy.linalg.cho_solve(cho, tq)                # unconstrained law u = Kunc x0
+            lmin, lmax = condense.extreme_eigs(P, cho)
+            self.rho_vec = self._penalty(P, lmin, lmax)
+            Minv = scipy.linalg.inv(P + np.diag(self.rho_vec))
+            Minv = 0.5 * (Minv + Minv.T)
+            Top, Mtq = Minv * self.rho_vec[None, :], Minv @ tq
         self.eig_range = (lmin, lmax)
         if self.reparameterize and not lmax / lmin < 1e10:
             raise NotImplementedError(
                 f"re-parameterised regulator: the input-space Hessian has condition number {lmax / lmin:.1e}; plants this "
                 "unstable over the horizon need the v-space general-G splitting, which is not built (DESIGN.md)")
-        dP = np.diag(P)
-        rho0 = 0.5 * np.sqrt(lmin * lmax) * self.rho_scale    # 0.5: swept on the CDU closed loop (0.28 .. 1.1), B200 round 1ae
-        self.rho_vec = rho0 * dP / np.exp(np.mean(np.log(dP)))
-        Minv = scipy.linalg.inv(P + np.diag(self.rho_vec))
-        Minv = 0.5 * (Minv + Minv.T)
         self._nxa_ld = (self.Nx + 1) & ~1
 
         def pad(Mx):
@@ -337,7 +344,8 @@ class DenseQPRegulator:
             out = np.zeros((Mx.shape[0], self._nxa_ld))
             out[:, :self.Nx] = Mx
             return out
-        ops = [_lib.host(P), pad(tq), _lib.host(Minv * self.rho_vec[None, :]), pad(Minv @ tq), pad(self.Kunc)]
+        ops = [_lib.host(P), pad(tq), _lib.host(Top), pad(Mtq), pad(self.Kunc)]
+        del Top
         L = _lib.lib()
         hnd = C.c_void_p()
         rc = L.nnmpc_qp_create(C.byref(hnd), n, self._nxa_ld, self.Nu, self.N, *[_lib.hptr(a) for a in ops],
@@ -346,6 +354,47 @@ class DenseQPRegulator:
         self._handle = hnd
         rho = _lib.host(self.rho_vec)
         _lib.check(L.nnmpc_qp_set_penalty(hnd, _lib.hptr(rho)), "nnmpc_qp_set_penalty")
+
+    def _penalty(self, P, lmin, lmax):
+        """ADMM penalty vector: 0.5 sqrt(lmin lmax) (swept on the CDU closed loop, 0.28 .. 1.1, B200 round 1ae) spread
+        over the variables proportionally to diag(P)."""
+        dP = np.diag(P)
+        return 0.5 * np.sqrt(lmin * lmax) * self.rho_scale * dP / np.exp(np.mean(np.log(dP)))
+
+    def _setup_dense_gpu(self, P, tq):
+        torch = _torch()
+        dev = torch.device("cuda", self._dev)
+        with torch.no_grad():
+            Pd = torch.as_tensor(P, dtype=torch.float64, device=dev)
+            tqd = torch.as_tensor(tq, dtype=torch.float64, device=dev)
+            Lc = torch.linalg.cholesky(Pd)
+            Kunc = -torch.cholesky_solve(tqd, Lc)
+            # extreme eigenvalues: power iteration on P and on P^-1 (two triangular solves per apply)
+            g = torch.Generator(device=dev).manual_seed(0)
+            v = torch.randn((P.shape[0], 1), dtype=torch.float64, device=dev, generator=g)
+            w = v.clone()
+            lmax = lmin_inv = 0.0
+            ref = (0.0, 0.0)
+            for it in range(3000):
+                v = Pd @ v
+                lmax = float(torch.linalg.vector_norm(v))
+                v /= lmax
+                w = torch.cholesky_solve(w, Lc)
+                lmin_inv = float(torch.linalg.vector_norm(w))
+                w /= lmin_inv
+                if it % 20 == 19:       # both estimates grow monotonically: stop when 20 more applies add < 1e-5
+                    if lmax - ref[0] <= 1e-5 * lmax and lmin_inv - ref[1] <= 1e-5 * lmin_inv:
+                        break
+                    ref = (lmax, lmin_inv)
+            lmin = 1.0 / lmin_inv
+            rho = self._penalty(P, lmin, lmax)
+            rhod = torch.as_tensor(rho, dtype=torch.float64, device=dev)
+            Minv = torch.cholesky_inverse(torch.linalg.cholesky(Pd + torch.diag(rhod)))
+            del Pd, Lc
+            Minv = 0.5 * (Minv + Minv.T)
+            Mtq = (Minv @ tqd).cpu().numpy()
+            Top = (Minv * rhod[None, :]).cpu().numpy()
+            return Kunc.cpu().numpy(), (lmin, lmax), rho, Top, Mtq
 
     def __del__(self):
         try:
