@@ -57,7 +57,7 @@ int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st) {
 int lp_anchor_prep(const int* rows, const int* count, int max_rows, const double* V, double* W, LpState* s,
                    const double* lb, const double* ub, int nu, cudaStream_t st) {
   if (max_rows <= 0) return 0;
-  k_anchor_prep<<<max_rows, 256, 0, st>>>(rows, count, V, W, s->E.p, lb, ub, s->n, nu);
+  k_anchor_prep<<<row_grid(max_rows), 256, 0, st>>>(rows, count, V, W, s->E.p, lb, ub, s->n, nu);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -75,7 +75,7 @@ int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, dou
                 const double* ub, int* state, int* it, int iter_state, int nu, double alpha, const int* pos_r,
                 cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
-  k_dr_first<<<max_rows, 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
+  k_dr_first<<<row_grid(max_rows), 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
                                        s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r, need2);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
@@ -85,7 +85,7 @@ int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, dou
 int lp_reanchor(const int* rows, const int* count, int max_rows, const int* state, int emit_state, const double* Z,
                 const double* rinv, LpState* s, cudaStream_t st) {
   if (max_rows <= 0) return 0;
-  k_reanchor<<<max_rows, 256, 0, st>>>(rows, count, state, emit_state, Z, s->Wl.p, rinv, s->X.p, s->n);
+  k_reanchor<<<row_grid(max_rows), 256, 0, st>>>(rows, count, state, emit_state, Z, s->Wl.p, rinv, s->X.p, s->n);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -95,7 +95,7 @@ int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emi
             const double* V, const double* lb, const double* ub, const double* dtrig, int nu, double alpha,
             const int* pos_r, cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
-  k_lp_emit<<<max_rows, 256, 0, st>>>(rows, count, state, emit_state, iter_state, V, s->Wl.p, s->E.p, s->D[s->cur].p,
+  k_lp_emit<<<row_grid(max_rows), 256, 0, st>>>(rows, count, state, emit_state, iter_state, V, s->Wl.p, s->E.p, s->D[s->cur].p,
                                       s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r, need2);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());

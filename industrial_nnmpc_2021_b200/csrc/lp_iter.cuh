@@ -277,13 +277,15 @@ __global__ void k_split_f16(const double* __restrict__ T, int n, long long ldh, 
 __global__ void k_anchor_prep(const int* __restrict__ rows, const int* __restrict__ count, const double* __restrict__ V,
                               double* __restrict__ W, float* __restrict__ E, const double* __restrict__ lb,
                               const double* __restrict__ ub, int n, int nu) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int k = j % nu;
-    const double v = V[s * n + j];
-    W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
-    E[s * n + j] = 0.f;
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int k = j % nu;
+      const double v = V[s * n + j];
+      W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
+      E[s * n + j] = 0.f;
+    }
   }
 }
 
@@ -295,9 +297,10 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
            const double* __restrict__ lb, const double* __restrict__ ub, double* __restrict__ sc_in,
            double* __restrict__ sc_out, int* __restrict__ state, int* __restrict__ it, int iter_state, int n, int nu,
            double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
   __shared__ double red[2][8];
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+  const long long s = rows[li];
   double dmax = 0.0, wmax = 0.0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int k = j % nu;
@@ -341,6 +344,8 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
     it[s] += 1;
     if (need2 && dpos >= 0) need2[dpos >> 7] = 1;     // a QP starts with large increments: both operator terms
   }
+  __syncthreads();          // red[] is reused by the next row
+  }
 }
 
 // ---- re-anchoring from a failed exact check (no FP64 anchor GEMM) -------------------------------
@@ -351,13 +356,15 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
 __global__ void k_reanchor(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ state,
                            int emit_state, const double* __restrict__ Z, double* __restrict__ GW,
                            const double* __restrict__ rinv, double* __restrict__ X, int n) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  if (state[s] != emit_state) return;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const double z = Z[s * n + j];
-    GW[s * n + j] = z + GW[s * n + j] * rinv[j];          // g -> w_lp
-    X[s * n + j] = z;
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li];
+    if (state[s] != emit_state) continue;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const double z = Z[s * n + j];
+      GW[s * n + j] = z + GW[s * n + j] * rinv[j];          // g -> w_lp
+      X[s * n + j] = z;
+    }
   }
 }
 
@@ -372,10 +379,11 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
           __half* __restrict__ D, long long ldd, const double* __restrict__ lb, const double* __restrict__ ub,
           double* __restrict__ sc_in, double* __restrict__ sc_out, const double* __restrict__ dtrig, int n, int nu,
           double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  if (state[s] != emit_state) return;
   __shared__ double red[8];
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+  const long long s = rows[li];
+  if (state[s] != emit_state) continue;          // uniform over the CTA
   double wmax = 0.0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int k = j % nu;
@@ -409,6 +417,8 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
     state[s] = iter_state;
     // a re-anchored row restarts from the gradient of a failed check: its first increments are not small
     if (need2 && dpos >= 0) need2[dpos >> 7] = 1;
+  }
+  __syncthreads();          // red[] is reused by the next row
   }
 }
 

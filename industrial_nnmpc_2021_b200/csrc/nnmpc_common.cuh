@@ -38,6 +38,13 @@ inline int set_error(int code, const char* fmt, ...) {
 
 inline void count_launch(int k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 
+// Grid of the one-CTA-per-listed-row kernels: the list length lives on the device and is usually far below the slot
+// count, so the grid is capped at one resident wave (148 SMs x 8 CTAs of 256 threads) and the CTAs stride over the list.
+inline unsigned row_grid(long long max_rows) {
+  const long long cap = 148 * 8;
+  return (unsigned)(max_rows < 1 ? 1 : (max_rows < cap ? max_rows : cap));
+}
+
 // RAII-less grow-only device buffer (handles free explicitly in destroy)
 template <class T>
 struct DevBuf {

@@ -156,7 +156,7 @@ int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st) {
 
 static int oz_slice_rows(OzRows* r, const int* rows, const int* count, int max_rows, const double* src, long long ld_src,
                          cudaStream_t st) {
-  oz::k_oz_slice<OZ_NS><<<max_rows, 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
+  oz::k_oz_slice<OZ_NS><<<row_grid(max_rows), 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
                                                   r->fscale.p);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());

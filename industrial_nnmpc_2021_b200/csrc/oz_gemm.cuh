@@ -506,41 +506,44 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 k_oz_slice(const int* __restrict__ rows, const int* __restrict__ count, const double* __restrict__ src, long long ld_src,
            int ncols, int8_t* __restrict__ dst, long long rows_pad, long long ldb, double* __restrict__ scale_out) {
-  if (count && (int)blockIdx.x >= *count) return;
-  const long long p = blockIdx.x;
-  const long long r = rows ? rows[p] : p;
-  const double* a = src + r * ld_src;
+  // grid-stride over the listed rows (the grid is capped by the launcher, the list length lives on the device)
+  const long long total = count ? *count : (long long)gridDim.x;
   __shared__ double red[8];
-  double m = 0.0;
-  for (int k = threadIdx.x; k < ncols; k += blockDim.x) {
-    const double b = fabs(a[k]);
-    m = (b <= m) ? m : b;            // NaN propagates
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double b = __shfl_xor_sync(0xffffffffu, m, o);
-    m = (b <= m) ? m : b;
-  }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  m = red[0];
-  for (int w = 1; w < 8; ++w) m = (red[w] <= m) ? m : red[w];
-  const bool bad = !(m <= 1.7e308);                       // NaN / Inf row: the result must not look finite
-  int ex = 0;
-  if (!bad && m > 0.0) frexp(m, &ex);                     // m = mant 2^ex, mant in [0.5, 1)  =>  m <= 2^ex = 2^(f-1)
-  const double inv = bad ? 0.0 : ldexp(1.0, -(ex + 1));
-  for (int k = threadIdx.x; k < ncols; k += blockDim.x) {
-    double t = bad ? 0.0 : a[k] * inv;                    // |t| <= 1/2, exact
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      t *= 128.0;
-      const double d = rint(t);                           // |d| <= 64
-      t -= d;                                             // exact, |t| <= 1/2
-      dst[((long long)s * rows_pad + p) * ldb + k] = (int8_t)(int)d;
+  for (long long p = blockIdx.x; p < total; p += gridDim.x) {
+    const long long r = rows ? rows[p] : p;
+    const double* a = src + r * ld_src;
+    double m = 0.0;
+    for (int k = threadIdx.x; k < ncols; k += blockDim.x) {
+      const double b = fabs(a[k]);
+      m = (b <= m) ? m : b;            // NaN propagates
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double b = __shfl_xor_sync(0xffffffffu, m, o);
+      m = (b <= m) ? m : b;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < 8; ++w) m = (red[w] <= m) ? m : red[w];
+    __syncthreads();                                        // red[] is reused by the next row
+    const bool bad = !(m <= 1.7e308);                       // NaN / Inf row: the result must not look finite
+    int ex = 0;
+    if (!bad && m > 0.0) frexp(m, &ex);                     // m = mant 2^ex, mant in [0.5, 1)  =>  m <= 2^ex = 2^(f-1)
+    const double inv = bad ? 0.0 : ldexp(1.0, -(ex + 1));
+    for (int k = threadIdx.x; k < ncols; k += blockDim.x) {
+      double t = bad ? 0.0 : a[k] * inv;                    // |t| <= 1/2, exact
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        t *= 128.0;
+        const double d = rint(t);                           // |d| <= 64
+        t -= d;                                             // exact, |t| <= 1/2
+        dst[((long long)s * rows_pad + p) * ldb + k] = (int8_t)(int)d;
+      }
+    }
+    if (threadIdx.x == 0)
+      scale_out[p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
   }
-  if (threadIdx.x == 0)
-    scale_out[p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
 }
 
 // uint8 row-major matrix [rows][cols bytes], leading dimension ld bytes -> tensor map with boxes of box_rows x 128 B

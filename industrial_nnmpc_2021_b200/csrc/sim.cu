@@ -17,7 +17,7 @@
 //      FP64-accurate tensor-core apply of oz_gemm.cuh in mixed precision)
 //   4. k_retire:   candidates that pass are done (iters/kkt rows written), the rest keep iterating (mixed precision:
 //      re-anchored from the gradient the check just computed)
-//   5. k_advance + plant-step GEMM on the done rows: dataset row u, x+ = [x|u|d][A|B|Bd]'
+//   5. k_advance_plant on the done rows: dataset row u and the plant step x+ = [A|B|Bd][x|u|d], one fused kernel
 //   6. k_step:     t += 1; finished trajectories leave; the rest form the renew list
 //   7. target selector (fused: dataset rows x,uprev,xs,us; x0, lb, ub; warm-start shift dus),
 //      q-build GEMMs (c = Mtq x0, q = tq x0) and k_warm_shift on the renew rows
@@ -53,7 +53,7 @@ struct nnmpc_sim {
   double kappa0, kappa_max;
   long long cap;
   long long warm_B;   // batch size whose solver state (V, us_prev, kappa) is valid for `resume`; 0 = none
-  nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, V, Z, xin, xcur, upcur, kappa, dtrig;
+  nnmpc::DevBuf<double> x0, lb, ub, us_prev, dus, V, Z, xcur, upcur, kappa, dtrig;
   nnmpc::DevBuf<int> state, tcur, it, lists;   // lists: 9 x cap (active, cand, done, renew, anchor, cold, swap, swap_old, swap_new)
   nnmpc::DevBuf<int> chunk, cold;              // per slot: the trajectory chunk it works on; cold (re)start pending
   int slot_cap;                                // most trajectories advanced concurrently (further chunks queue up)
@@ -273,13 +273,15 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
 __global__ void k_make_z(const int* __restrict__ rows, const int* __restrict__ count, const double* __restrict__ V,
                          double* __restrict__ Z, const double* __restrict__ lb, const double* __restrict__ ub,
                          int n, int nu) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  const double* v = V + s * n;
-  double* z = Z + s * n;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int k = j % nu;
-    z[j] = clipd(v[j], lb[s * nu + k], ub[s * nu + k]);
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li];
+    const double* v = V + s * n;
+    double* z = Z + s * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int k = j % nu;
+      z[j] = clipd(v[j], lb[s * nu + k], ub[s * nu + k]);
+    }
   }
 }
 
@@ -327,63 +329,99 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
   }
 }
 
-// first move + dataset row u + plant-step input [x | u | d | 0-pad] for the done rows; with capture sinks also the
-// whole optimal sequence (deviation variables + us per stage, as DenseQPRegulator.solve returns it through
-// get_control_sequence, linearMPC.py:689) and the optimal cost 1/2 z'Pz + q'z = 1/2 z'(g + q) from the gradient
-// g = P z + q of the check that certified z
-__global__ void k_advance(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
-                          const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
-                          const double* __restrict__ xcur, const double* __restrict__ dist,
-                          double* __restrict__ row_u, double* __restrict__ upcur, double* __restrict__ xin, int n,
-                          int nx, int nu, int nd, int kin_ld, const double* __restrict__ G, const double* __restrict__ Ql,
-                          double* __restrict__ cap_useq, double* __restrict__ cap_cost, const double* __restrict__ lb,
-                          const double* __restrict__ ub, unsigned long long* __restrict__ stats) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  const long long o = (long long)chunk[s] * T + tcur[s];
-  {  // workload statistics: how constrained the optimum is (z = clip(v) sits exactly on an active bound)
-    int na = 0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const double z = Z[s * n + j];
-      na += (z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)]) ? 1 : 0;
+// First move, dataset row u and the plant step x+ = A x + B u + Bd d of the done rows, fused (linearMPC.py:856-866).
+// A CTA takes ADV_ROWS done rows at a time: it stages their [x | u | d] in shared memory (writing the dataset row
+// u and the new uprev on the way), then every warp streams rows of [A | B | Bd] once per group - coalesced, 8 rows
+// of reuse - and reduces the dot products with shuffles.  The summation order of a row does not depend on which
+// other rows share its group.  With capture sinks also the whole optimal sequence (deviation variables + us per
+// stage, as DenseQPRegulator.solve returns it through get_control_sequence, linearMPC.py:689) and the optimal cost
+// 1/2 z'Pz + q'z = 1/2 z'(g + q) from the gradient g = P z + q of the check that certified z.
+constexpr int ADV_ROWS = 8;
+__global__ void __launch_bounds__(256)
+k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
+                const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
+                double* __restrict__ xcur, const double* __restrict__ dist, double* __restrict__ row_u,
+                double* __restrict__ upcur, const double* __restrict__ ABd, int n, int nx, int nu, int nd, int kin_ld,
+                const double* __restrict__ G, const double* __restrict__ Ql, double* __restrict__ cap_useq,
+                double* __restrict__ cap_cost, const double* __restrict__ lb, const double* __restrict__ ub,
+                unsigned long long* __restrict__ stats) {
+  extern __shared__ double adv_in[];          // ADV_ROWS x kin_ld
+  __shared__ double red[8];
+  const int cnt = *count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g0 = blockIdx.x * ADV_ROWS; g0 < cnt; g0 += gridDim.x * ADV_ROWS) {
+    const int nr = cnt - g0 < ADV_ROWS ? cnt - g0 : ADV_ROWS;
+    for (int idx = threadIdx.x; idx < nr * kin_ld; idx += blockDim.x) {
+      const int r = idx / kin_ld, c = idx - r * kin_ld;
+      const long long s = rows[g0 + r];
+      const long long o = (long long)chunk[s] * T + tcur[s];
+      double v;
+      if (c < nx) {
+        v = xcur[s * nx + c];
+      } else if (c < nx + nu) {
+        const int k = c - nx;
+        v = Z[s * n + k] + us[o * nu + k];
+        row_u[o * nu + k] = v;
+        upcur[s * nu + k] = v;
+      } else if (c < nx + nu + nd) {
+        v = dist[o * nd + (c - nx - nu)];
+      } else {
+        v = 0.0;
+      }
+      adv_in[idx] = v;
     }
-    if (__syncthreads_or(na > 0)) {
-      na = __reduce_add_sync(0xffffffffu, na);
-      if ((threadIdx.x & 31) == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
-      if (threadIdx.x == 0) atomicAdd(stats + 2, 1ull);
-    }
-  }
-  for (int c = threadIdx.x; c < kin_ld; c += blockDim.x) {
-    double v;
-    if (c < nx) {
-      v = xcur[s * nx + c];
-    } else if (c < nx + nu) {
-      const int k = c - nx;
-      v = Z[s * n + k] + us[o * nu + k];
-      row_u[o * nu + k] = v;
-      upcur[s * nu + k] = v;
-    } else if (c < nx + nu + nd) {
-      v = dist[o * nd + (c - nx - nu)];
-    } else {
-      v = 0.0;
-    }
-    xin[s * kin_ld + c] = v;
-  }
-  if (cap_useq)
-    for (int j = threadIdx.x; j < n; j += blockDim.x) cap_useq[o * n + j] = Z[s * n + j] + us[o * nu + (j % nu)];
-  if (cap_cost) {
-    __shared__ double red[32];
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) acc += Z[s * n + j] * (G[s * n + j] + Ql[s * n + j]);
+    for (int r = 0; r < nr; ++r) {
+      const long long s = rows[g0 + r];
+      const long long o = (long long)chunk[s] * T + tcur[s];
+      {  // workload statistics: how constrained the optimum is (z = clip(v) sits exactly on an active bound)
+        int na = 0;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+          const double z = Z[s * n + j];
+          na += (z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)]) ? 1 : 0;
+        }
+        if (__syncthreads_or(na > 0)) {
+          na = __reduce_add_sync(0xffffffffu, na);
+          if (lane == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
+          if (threadIdx.x == 0) atomicAdd(stats + 2, 1ull);
+        }
+      }
+      if (cap_useq)
+        for (int j = threadIdx.x; j < n; j += blockDim.x) cap_useq[o * n + j] = Z[s * n + j] + us[o * nu + (j % nu)];
+      if (cap_cost) {
+        double acc = 0.0;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) acc += Z[s * n + j] * (G[s * n + j] + Ql[s * n + j]);
 #pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-      cap_cost[o] = 0.5 * t;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t = 0.0;
+          for (int w = 0; w < nwarps; ++w) t += red[w];
+          cap_cost[o] = 0.5 * t;
+        }
+        __syncthreads();
+      }
     }
+    __syncthreads();                           // inputs staged (and xcur read) before any x+ is written
+    for (int i = warp; i < nx; i += nwarps) {
+      const double* arow = ABd + (long long)i * kin_ld;
+      double acc[ADV_ROWS];
+#pragma unroll
+      for (int r = 0; r < ADV_ROWS; ++r) acc[r] = 0.0;
+      for (int c = lane; c < kin_ld; c += 32) {
+        const double a = arow[c];
+#pragma unroll
+        for (int r = 0; r < ADV_ROWS; ++r) acc[r] += a * adv_in[r * kin_ld + c];   // rows beyond nr hold stale finite data
+      }
+#pragma unroll
+      for (int r = 0; r < ADV_ROWS; ++r) {
+        double t = acc[r];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
+        if (lane == 0 && r < nr) xcur[(long long)rows[g0 + r] * nx + i] = t;
+      }
+    }
+    __syncthreads();                           // adv_in is rewritten by the next group
   }
 }
 
@@ -497,17 +535,19 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int
 __global__ void k_tail_prep(const int* __restrict__ rows, const int* __restrict__ count, int* __restrict__ state,
                             const double* __restrict__ V, double* __restrict__ W, const double* __restrict__ lb,
                             const double* __restrict__ ub, int n, int nu) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  const int st = state[s];
-  if (st != SLOT_ITER && st != SLOT_ANCHOR) return;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int k = j % nu;
-    const double v = V[s * n + j];
-    W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li];
+    const int st = state[s];
+    __syncthreads();                                   // every thread has read the state before thread 0 may change it
+    if (st != SLOT_ITER && st != SLOT_ANCHOR) continue;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int k = j % nu;
+      const double v = V[s * n + j];
+      W[s * n + j] = 2.0 * clipd(v, lb[s * nu + k], ub[s * nu + k]) - v;
+    }
+    if (threadIdx.x == 0 && st == SLOT_ANCHOR) state[s] = SLOT_ITER;
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && st == SLOT_ANCHOR) state[s] = SLOT_ITER;
 }
 
 // slots that finished a chunk: hand its final state back, load the initial state of the chunk taken next
@@ -515,22 +555,24 @@ __global__ void k_chunk_swap(const int* __restrict__ rows, const int* __restrict
                              const int* __restrict__ c_new, double* __restrict__ xcur, double* __restrict__ upcur,
                              double* __restrict__ x_io, double* __restrict__ uprev_io, double* __restrict__ us_prev,
                              double* __restrict__ kappa, double kappa0, int nx, int nu) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
-  const long long co = c_old[blockIdx.x], cn = c_new[blockIdx.x];
-  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
-    x_io[co * nx + j] = xcur[s * nx + j];
-    if (cn >= 0) xcur[s * nx + j] = x_io[cn * nx + j];
-  }
-  for (int j = threadIdx.x; j < nu; j += blockDim.x) {
-    uprev_io[co * nu + j] = upcur[s * nu + j];
-    if (cn >= 0) {
-      upcur[s * nu + j] = uprev_io[cn * nu + j];
-      us_prev[s * nu + j] = 0.0;
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li];
+    const long long co = c_old[li], cn = c_new[li];
+    for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+      x_io[co * nx + j] = xcur[s * nx + j];
+      if (cn >= 0) xcur[s * nx + j] = x_io[cn * nx + j];
     }
+    for (int j = threadIdx.x; j < nu; j += blockDim.x) {
+      uprev_io[co * nu + j] = upcur[s * nu + j];
+      if (cn >= 0) {
+        upcur[s * nu + j] = uprev_io[cn * nu + j];
+        us_prev[s * nu + j] = 0.0;
+      }
+    }
+    // a new chunk starts like a fresh trajectory: results do not depend on which slot serves it
+    if (threadIdx.x == 0 && cn >= 0) kappa[s] = kappa0;
   }
-  // a new chunk starts like a fresh trajectory: results do not depend on which slot serves it
-  if (threadIdx.x == 0 && cn >= 0) kappa[s] = kappa0;
 }
 
 // renew rows: v <- shifted previous solution re-centred on the new target (or the cold-start law
@@ -540,8 +582,9 @@ __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict
                              double* __restrict__ Zs, double* __restrict__ W, const double* __restrict__ dus,
                              const double* __restrict__ lb, const double* __restrict__ ub, int n, int nu,
                              int* __restrict__ cold_flag, int next_state, int write_w) {
-  if ((int)blockIdx.x >= *count) return;
-  const long long s = rows[blockIdx.x];
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+  const long long s = rows[li];
   const int cold = cold_flag[s];   // cold start: V already holds the unconstrained law of this QP
   double* v = V + s * n;
   double* z = Zs + s * n;
@@ -566,6 +609,8 @@ __global__ void k_warm_shift(const int* __restrict__ rows, const int* __restrict
     state[s] = next_state;
     it[s] = 0;
     dres[s] = 0ull;
+  }
+  __syncthreads();          // thread 0 has cleared the cold flag: nobody may still be reading it
   }
 }
 
@@ -627,7 +672,6 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
   NNMPC_TRY(h->dus.ensure(B * h->nu));
   NNMPC_TRY(h->V.ensure(B * n));
   NNMPC_TRY(h->Z.ensure(B * n));
-  NNMPC_TRY(h->xin.ensure(B * h->kin_ld));
   NNMPC_TRY(h->xcur.ensure(B * h->nx));
   NNMPC_TRY(h->upcur.ensure(B * h->nu));
   NNMPC_TRY(h->kappa.ensure(B));
@@ -731,7 +775,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     // the first fp16 increment, makes nearly every first check fail - the stage shift is an O(1e-2) increment
     // whose fp32-accumulation error is far above the 1e-10 the trigger needs - and costs 2 checks + 53
     // iterations per QP instead of 1.1 + 30.)
-    k_warm_shift<<<B, 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
+    k_warm_shift<<<row_grid(B), 256, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.state, e.it, e.dres, h->V.p, h->Z.p, Wc,
                                     h->dus.p, h->lb.p, h->ub.p, n, nu, e.cold, mixed ? SLOT_ANCHOR : SLOT_ITER,
                                     mixed ? 0 : 1);
     count_launch();
@@ -783,7 +827,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       const bool prof64b = prof_begin(&span64, st);
       // at most tail_rows rows are ever listed here (E_TAIL is 0 above that)
       const int tail_grid = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
-      k_tail_prep<<<tail_grid, 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
+      k_tail_prep<<<row_grid(tail_grid), 256, 0, st>>>(e.l_active, e.counts + E_TAIL, e.state, h->V.p, q->W0.p, h->lb.p, h->ub.p, n, nu);
       count_launch();
       GemmOperands gi{};
       gi.A = q->W0.p; gi.lda = n; gi.Bt = q->Top; gi.ldb = n; gi.M = e.tail_rows < B ? (e.tail_rows > 0 ? e.tail_rows : 1) : B;
@@ -808,7 +852,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       count_launch();
       continue;
     }
-    k_make_z<<<B, 256, 0, st>>>(e.l_cand, e.counts + N_CAND, h->V.p, h->Z.p, h->lb.p, h->ub.p, n, nu);
+    k_make_z<<<row_grid(B), 256, 0, st>>>(e.l_cand, e.counts + N_CAND, h->V.p, h->Z.p, h->lb.p, h->ub.p, n, nu);
     count_launch(2);
     {
       GemmOperands gv{};
@@ -833,22 +877,14 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
                         h->ub.p, e.dtrig, nu, q->alpha, e.lp_pos + (long long)(lay ^ 1) * B, st, e.need2));
     }
     // 5. first move, dataset row, plant step for the done rows
-    k_advance<<<B, 128, 0, st>>>(e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou,
-                                 h->upcur.p, h->xin.p, n, nx, nu, nd, h->kin_ld, gbuf, q->Ql.p, h->cap_useq,
-                                 h->cap_cost, h->lb.p, h->ub.p, h->stats);
+    k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, (size_t)ADV_ROWS * h->kin_ld * sizeof(double), st>>>(
+        e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou, h->upcur.p, h->ABd, n, nx, nu, nd,
+        h->kin_ld, gbuf, q->Ql.p, h->cap_useq, h->cap_cost, h->lb.p, h->ub.p, h->stats);
     count_launch(2);
-    {
-      GemmOperands gp{};
-      gp.A = h->xin.p; gp.lda = h->kin_ld; gp.Bt = h->ABd; gp.ldb = h->kin_ld; gp.M = B; gp.N = nx; gp.K = h->kin_ld;
-      gp.rows = e.l_done; gp.m_count = e.counts + N_DONE;
-      cudaError_t ce = launch_gemm<TileMid, EpiStore>(gp, EpiStore::Params{h->xcur.p, nx, nullptr, 0}, st);
-      count_launch();
-      if (ce != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(ce));
-    }
     // 6-7. next time step for the done rows
     k_step<<<1, 1024, 0, st>>>(e, T, B, lay);
     lay ^= 1;
-    k_chunk_swap<<<B, 128, 0, st>>>(e.l_swap, e.counts + N_SWAP, e.swap_old, e.swap_new, h->xcur.p, h->upcur.p, x_io,
+    k_chunk_swap<<<row_grid(B), 128, 0, st>>>(e.l_swap, e.counts + N_SWAP, e.swap_old, e.swap_new, h->xcur.p, h->upcur.p, x_io,
                                     uprev_io, h->us_prev.p, h->kappa.p, h->kappa0, nx, nu);
     count_launch(2);
     NNMPC_TRY(renew(0));
@@ -977,7 +1013,7 @@ int nnmpc_sim_destroy(nnmpc_sim_t* h) {
   for (int i = 0; i < POLL_RING; ++i)
     if (h->poll_ev[i]) cudaEventDestroy(h->poll_ev[i]);
   h->x0.release(); h->lb.release(); h->ub.release(); h->us_prev.release(); h->dus.release(); h->V.release();
-  h->Z.release(); h->xin.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
+  h->Z.release(); h->xcur.release(); h->upcur.release(); h->kappa.release(); h->dtrig.release();
   h->chunk.release(); h->cold.release();
   h->state.release(); h->tcur.release(); h->it.release(); h->lists.release(); h->dres.release(); h->kres.release();
   h->h_sp.release(); h->h_dist.release(); h->h_x.release(); h->h_uprev.release(); h->h_xs.release();
