@@ -156,7 +156,8 @@ int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
 /* Mixed mode only: a trajectory whose last Douglas-Rachford residual ||d||_inf is at most factor * tol is in the late
  * phase of its QP; 128-row operand tiles made of such rows only run the tensor-core pass with the first fp16 operator
  * term alone (half the MMA work; the 2^-11 relative error of the dropped term is relative to a vanishing increment and
- * every result is still certified by the exact KKT check).  Default 100; 0 = always both terms. */
+ * every result is still certified by the exact KKT check).  Default 1000 (measured on B200: same iterations and
+ * exact checks per QP as with both terms everywhere); 0 = always both terms. */
 int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor);
 /* cumulative since create: out2 = {128x128 tensor-core tiles run with one operator term, with both terms} */
 int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2);
@@ -207,7 +208,7 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
  * (T1, T2, s) the two-term fp16 split of the square FP64 operator Bt (N == K, bt_max = max |Bt|);
  * A, Bt, C are dense row-major FP64 device matrices. */
 int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, double bt_max, double* C, int pair,
-                       void* stream);   /* pair != 0: the CTA-pair (cta_group::2) kernel, else the one-CTA kernel */
+                       void* stream);   /* pair: 0 = one-CTA kernel with 128 x 128 tiles, 1 = CTA-pair (cta_group::2) kernel, 2 = one-CTA kernel with 256 x 128 tiles */
 /* nnmpc_oz_gemm_test: the FP64-accurate GEMM on the INT8 tcgen05 tensor cores (error-free base-128 slicing of both
  * operands, exact INT32 accumulation, 36 INT8 products), C[M x N] = A[M x K] Bt[N x K]^T; dense row-major FP64
  * device matrices, K <= 32768. */

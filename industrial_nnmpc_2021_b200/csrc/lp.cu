@@ -12,6 +12,16 @@ namespace nnmpc {
 // NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles).  Measured on B200 (round 1ab/1ae): the
 // pair kernel halves the L2->SMEM operand traffic (5.3 vs 9.0 GB per 8192-row pass) but is not faster (332 vs 372
 // TFLOP/s algorithmic with the slim epilogue), so the one-CTA kernel, which sits at the L2->SMEM ceiling, is the default.
+// 0 = 128 x 128 tiles, 1 = 256 x 128 tiles (default; NNMPC_LP_TILE=m128 selects the former)
+static int lp_tile_m256() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNMPC_LP_TILE");
+    v = (e && strcmp(e, "m128") == 0) ? 0 : 1;
+  }
+  return v;
+}
+
 static bool lp_use_pair() {
   static int v = -1;
   if (v < 0) {
@@ -46,7 +56,8 @@ int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st) {
   for (int b = 0; b < 2; ++b) {
     NNMPC_TRY(s->D[b].ensure((size_t)cap_pad * s->ldd));
     NNMPC_CUDA(cudaMemsetAsync(s->D[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half), st));   // ordered before the first writer on st
-    if (!lp::make_tmap_f16(&s->tmD[b], s->D[b].p, cap_pad, s->ldd, s->ldd, lp::BM))
+    if (!lp::make_tmap_f16(&s->tmD[b], s->D[b].p, cap_pad, s->ldd, s->ldd, lp::BM) ||
+        !lp::make_tmap_f16(&s->tmD256[b], s->D[b].p, cap_pad, s->ldd, s->ldd, 2 * lp::BM))
       return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the increment buffers");
   }
   s->cap = cap;
@@ -118,6 +129,8 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   lp::LpShape g{B, s->n, s->n, len_r, group_cols, need2, tile_stat, 0, 0};
   cudaError_t e = lp_use_pair()
                       ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
+                  : lp_tile_m256()
+                      ? lp::launch_lp_gemm<LpTileM256, EpiDelta>(s->tmD256[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
                       : lp::launch_lp_gemm<LpTileN128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st);
   count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));
@@ -183,13 +196,14 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
     k_to_half<<<148 * 4, 256, 0, st>>>(A, M, K, op.ldh, Ah.p);
     count_launch();
     CUtensorMap tmA;
-    if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, lp::BM)) {
+    if (!lp::make_tmap_f16(&tmA, Ah.p, m_pad, op.ldh, op.ldh, pair == 2 ? 2 * lp::BM : lp::BM)) {
       rc = set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
       lp::LpShape g{M, N, K, nullptr, 2, nullptr, nullptr, 0, 0};
       const EpiLpStore::Params ep{C, N, 1.0 / op.scale};
-      cudaError_t e = pair ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
-                           : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);
+      cudaError_t e = pair == 1 ? lp::launch_lp_gemm_pair<EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
+                    : pair == 2 ? lp::launch_lp_gemm<LpTileM256, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st)
+                                : lp::launch_lp_gemm<LpTileN128, EpiLpStore>(tmA, op.tm1, op.tm2, g, ep, device_sm_count(dev), st);
       count_launch();
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));

@@ -17,6 +17,7 @@ struct LpState {
   DevBuf<float> E;
   DevBuf<__half> D[2];               // double buffered: the TMA reads D[cur], the epilogue writes D[cur ^ 1]
   CUtensorMap tmD[2];
+  CUtensorMap tmD256[2];             // the same buffers with 256-row boxes (LpTile<.,.,2>)
   int cur = 0;
   void release() { Wl.release(); X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release(); cap = 0; }
 };

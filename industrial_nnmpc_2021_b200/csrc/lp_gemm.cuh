@@ -64,13 +64,18 @@ constexpr int EPI_SMEM_BYTES = EPI_WARPS * (int)sizeof(EpiWarpSmem);
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
-template <int BN_, int STAGES_>
+// MR_ = 128-row blocks per CTA tile (1 or 2).  With MR = 2 a CTA owns 256 x BN outputs: one staged operator tile
+// (B1, B2) feeds the MMAs of both row blocks, so the operator bytes pulled from L2 per flop halve - the pass is
+// bound by L2->SM throughput (ncu: 7.5 kB/clk chip-wide at 48 % tensor-pipe activity with MR = 1).
+template <int BN_, int STAGES_, int MR_ = 1>
 struct LpTile {
-  static constexpr int BN = BN_, STAGES = STAGES_;
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int BN = BN_, STAGES = STAGES_, MR = MR_;
+  static constexpr int TILE_M = MR * BM;
+  static constexpr int A_BYTES = TILE_M * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*1 KB alignment slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
-  static constexpr int TMEM_COLS = ACC_STAGES * BN;
+  static constexpr int TMEM_COLS = ACC_STAGES * MR * BN;
+  static_assert(MR == 1 || MR == 2, "row blocks per tile");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -268,9 +273,17 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
   const int ntn = (g.N + T::BN - 1) / T::BN;
-  const int ntm = (M + BM - 1) / BM;
+  const int ntm = (M + T::TILE_M - 1) / T::TILE_M;
   const int tiles = ntn * ntm;
   const int KB = (g.K + BK - 1) / BK;
+  // does row tile bm need the second operator term?  (flags are per 128 rows)
+  auto tile_two = [&](int bm) -> bool {
+    if (!g.need2) return true;
+    bool two = false;
+#pragma unroll
+    for (int r = 0; r < T::MR; ++r) two = two || g.need2[bm * T::MR + r] != 0;
+    return two;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -300,14 +313,14 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         int bm, bn;
         tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
-        const bool two = !g.need2 || g.need2[bm] != 0;
+        const bool two = tile_two(bm);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           uint8_t* st = ring + s * T::STAGE_BYTES;
           const bool two_kb = two && (g.kb2 <= 0 || kb < g.kb2);
           const int kbb = (g.b_wrap > 0 && kb >= g.b_wrap) ? kb - g.b_wrap : kb;
           mbar_expect_tx(full + s, two_kb ? T::STAGE_BYTES : T::A_BYTES + T::B_BYTES);
-          tma_load_2d(st, &tmA, full + s, kb * BK, bm * BM);
+          tma_load_2d(st, &tmA, full + s, kb * BK, bm * T::TILE_M);      // the A map's box is TILE_M rows
           tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
           if (two_kb) tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
@@ -324,26 +337,31 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
         int bm, bn;
         tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
-        const bool two = !g.need2 || g.need2[bm] != 0;
-        if (g.tile_stat) atomicAdd(g.tile_stat + (two ? 1 : 0), 1ull);
+        const bool two = tile_two(bm);
+        if (g.tile_stat) atomicAdd(g.tile_stat + (two ? 1 : 0), (unsigned long long)T::MR);   // in 128 x BN units
         const int as = i & 1;
         const uint32_t aph = (uint32_t)(i >> 1) & 1u;
         mbar_wait(acc_empty + as, aph ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(as * T::BN);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * T::MR * T::BN);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(full + s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + s * T::STAGE_BYTES);
-          const uint64_t da = make_sw128_kmajor_desc(sa);
           const uint64_t db1 = make_sw128_kmajor_desc(sa + T::A_BYTES);
           const uint64_t db2 = make_sw128_kmajor_desc(sa + T::A_BYTES + T::B_BYTES);
+          const bool two_kb = two && (g.kb2 <= 0 || kb < g.kb2);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
-            umma_f16(tacc, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          if (two && (g.kb2 <= 0 || kb < g.kb2)) {
+          for (int r = 0; r < T::MR; ++r) {       // row block r: 128 rows of A (16 KB apart in the box), own accumulator
+            const uint64_t da = make_sw128_kmajor_desc(sa + r * (BM * BK * 2));
+            const uint32_t tr = tacc + (uint32_t)(r * T::BN);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tacc, da + 2 * k, db2 + 2 * k, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
+              umma_f16(tr, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            if (two_kb) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tr, da + 2 * k, db2 + 2 * k, idesc, 1u);
+            }
           }
           umma_commit(empty + s);                 // ring slot free once these MMAs have read it
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
@@ -362,18 +380,23 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
       const int as = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      epi.begin_tile(bm * BM + q * 32, M);
-      mbar_wait(acc_full + as, aph);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * T::BN);
 #pragma unroll 1
-      for (int cc = 0; cc < T::BN / 32; ++cc) {
-        uint32_t acc[CW];
-        tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
-        tmem_ld_wait();
-        epi.chunk(bn * T::BN + cc * 32 + hsel * CW, acc, g.N);
+      for (int r = 0; r < T::MR; ++r) {
+        epi.begin_tile(bm * T::TILE_M + r * BM + q * 32, M);
+        if (r == 0) {
+          mbar_wait(acc_full + as, aph);
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * T::MR + r) * T::BN);
+#pragma unroll 1
+        for (int cc = 0; cc < T::BN / 32; ++cc) {
+          uint32_t acc[CW];
+          tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
+          tmem_ld_wait();
+          epi.chunk(bn * T::BN + cc * 32 + hsel * CW, acc, g.N);
+        }
+        epi.end_tile();
       }
-      epi.end_tile();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);
@@ -644,7 +667,7 @@ inline cudaError_t launch_lp_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB
     configured[dev & 63] = true;
   }
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
-  const long long tiles = (long long)((g.N + T::BN - 1) / T::BN) * ((g.M + BM - 1) / BM);
+  const long long tiles = (long long)((g.N + T::BN - 1) / T::BN) * ((g.M + T::TILE_M - 1) / T::TILE_M);
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
   lp_gemm_kernel<T, Epi><<<grid, THREADS, T::SMEM_BYTES, st>>>(tmA, tmB1, tmB2, g, ep);
   return cudaGetLastError();

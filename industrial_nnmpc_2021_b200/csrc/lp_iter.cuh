@@ -19,6 +19,7 @@
 namespace nnmpc {
 
 using LpTileN128 = lp::LpTile<128, 4>;
+using LpTileM256 = lp::LpTile<128, 3, 2>;     // 256 x 128 outputs per CTA tile: operator bytes per flop halved
 
 // one element of the Douglas-Rachford delta update (shared by the tensor-core epilogue and k_dr_first)
 __device__ __forceinline__ void dr_delta_one(double& x, double& v, double wl, double l, double u, double alpha,

@@ -485,7 +485,9 @@ __global__ void __launch_bounds__(1024) k_step(EngineArrays e, int T, int S, int
         if (s < S) {
           const int st = e.state[s];
           live = st == SLOT_ITER || st == SLOT_RENEW || st == SLOT_ANCHOR || st == SLOT_EMIT;
-          late = st == SLOT_ITER && e.dlast[s] <= e.t2_thr;
+          // the layout built here is read 5 to 8 passes from now: rows whose residual is within ~two decades of
+          // the threshold will be late by then (rows that finish in between idle until a later rebuild)
+          late = st == SLOT_ITER && e.dlast[s] <= 64.0 * e.t2_thr;
         }
         na = block_append(live && (late == (pass == 0)), s, e.l_active, na);
       }
@@ -959,7 +961,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
-  h->t2_factor = 100.0;
+  h->t2_factor = 1000.0;
   h->tile_stat = nullptr;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = h->tot_qps_active = h->tot_active = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;

@@ -2,8 +2,13 @@
 structured network (tolerance 1e-5, lib/LinearMPCLayers.py) can run its layers on the split-fp16 path.
 C = fp16(A) (T1 + T2)' / s against FP64 of the same fp16(A): what is left is the operator split (2^-22) and the
 accumulation error."""
+import os
+import sys
+
 import numpy as np
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from industrial_nnmpc_2021_b200 import _lib, build
 
 build.build()
