@@ -43,6 +43,7 @@ typedef struct nnmpc_qp nnmpc_qp_t;    /* condensed regulator QP operators + sol
 typedef struct nnmpc_ts nnmpc_ts_t;    /* target-selector operators */
 typedef struct nnmpc_sim nnmpc_sim_t;  /* closed-loop offline data generator */
 typedef struct nnmpc_mlp nnmpc_mlp_t;  /* structured-network weights */
+typedef struct nnmpc_online nnmpc_online_t;  /* batched online closed loop (filter + controller + plant) */
 
 int nnmpc_version(void);
 const char* nnmpc_last_error(void);
@@ -202,6 +203,31 @@ int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double
 int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev,
                            const double* xs, const double* us, const double* xscale,
                            const double* ulb, const double* uub, double* out);
+
+/* ---- batched online closed loop: LinearMPCController.control_law / online_simulation (lib/linearMPC.py:646-669,
+ * :703-718) and the validation study of lib/controller_evaluation.py:322-523 for S scenarios in lock step ---------
+ * Every step: Kalman filter (:133-176) -> target selector -> controller -> running average stage cost (:691-701)
+ * -> plant step and next measurement (:87-131).  Host operators (row-major):
+ *   Fkf  (nx+nd) x (nx+nd+nu+ny)   [(I - L Caug) Aaug | (I - L Caug) Baug | L]  acting on [xhat; dhat; uprev; y]
+ *   Fpl  (nx+ny) x (nx+nu+np)      [A B Bp; CA CB CBp]                           acting on [x; u; p]
+ *   Kaug nu x (nx+nu)              saturated-LQR gain (nullable), Qaug/Raug/Maug the augmented stage cost (:626-644)
+ *   xscale nx (nullable)           state scaling of the network inputs (controller_evaluation.py:863-866)
+ * qp / mlp may be NULL when the corresponding controller kind is not used; handles must live on `device`. */
+enum { NNMPC_ONLINE_MPC = 0, NNMPC_ONLINE_NN = 1, NNMPC_ONLINE_SATDLQR = 2 };
+int nnmpc_online_create(nnmpc_online_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, nnmpc_mlp_t* mlp, int nx, int nu, int ny,
+                        int nd, int np, const double* Fkf_host, const double* Fpl_host, const double* Kaug_host,
+                        const double* Qaug_host, const double* Raug_host, const double* Maug_host,
+                        const double* ulb_host, const double* uub_host, const double* xscale_host, int device);
+int nnmpc_online_destroy(nnmpc_online_t* h);
+/* All pointers are device memory.  In/out per scenario: x_io S x nx (plant state), xhat_io S x (nx+nd) (filter state
+ * [xhat; dhat]), uprev_io S x nu.  Inputs: setpoints [S][T][ny], disturbances [S][T][np], noise [S][T+1][ny]
+ * (measurement noise added to C x, entry 0 unused; nullable), y [S][T+1][ny] with y[:,0] = the first measurement.
+ * Outputs: y[:,1:], u [S][T][nu]; nullable: x [S][T+1][nx] (plant states), xhat, xs [S][T][nx], us [S][T][nu],
+ * ell_avg [S][T] (running average stage cost after each step), iters / kkt [S][T] (kind = MPC only). */
+int nnmpc_online_run(nnmpc_online_t* h, int kind, int S, int T, double* x_io, double* xhat_io, double* uprev_io,
+                     const double* setpoints, const double* disturbances, const double* noise, double* y, double* u,
+                     double* x, double* xhat, double* xs, double* us, double* ell_avg, int* iters, double* kkt,
+                     double tol, int max_iter, void* stream);
 
 /* ---- self tests (used by tests/) -----------------------------------------------------------------
  * nnmpc_lp_gemm_test: the tcgen05 split-operator GEMM, C[M x N] = fp16(A)[M x K] (T1 + T2)[N x K]^T / s with

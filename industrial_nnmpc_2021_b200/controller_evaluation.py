@@ -109,3 +109,132 @@ class NeuralNetworkController:
     def _get_control_input(self, x, uprev, xs, us):
         row = lambda a: np.asarray(a, float).reshape(1, -1)
         return self.control_input_batch(row(x), row(uprev), row(xs), row(us)).reshape(-1, 1)
+
+
+class BatchedOnlineSimulation:
+    """S closed-loop scenarios advanced in lock step on the GPU: the batched form of ``online_simulation`` with a
+    ``LinearMPCController`` / ``NeuralNetworkController`` / ``SatDlqrController`` in the loop, as the reference's
+    validation study runs them one scenario after the other (controller_evaluation.py:322-523; control laws
+    lib/linearMPC.py:646-669, controller_evaluation.py:841-862, :975-993).
+
+    Plant: ``x+ = A x + B u + Bp p``, ``y = C x + v`` (LinearPlantSimulator, linearMPC.py:87-131); the controller
+    arguments are those of ``LinearMPCController`` (:525-528).  ``kind``: "mpc", "nn" (needs ``regulator_weights``,
+    ``xscale``, ``nnwithuprev``) or "satdlqr".
+    """
+    KINDS = {"mpc": 0, "nn": 1, "satdlqr": 2}
+
+    def __init__(self, *, kind, A, B, C, H, Qwx, Qwd, Rv, xprior, dprior, Rs, Qs, Bd, Cd, usp, uprev, Q, R, S, ulb, uub,
+                 N=None, Bp=None, regulator_weights=None, xscale=None, nnwithuprev=True, device=None, precision=None,
+                 **solver_kwargs):
+        import ctypes as Ct
+        from . import _lib
+        from .linearMPC import LinearMPCController, dlqr, _device_index
+        if kind not in self.KINDS:
+            raise ValueError(f"kind must be one of {sorted(self.KINDS)}")
+        self.kind = kind
+        self.Nx, self.Nu, self.Ny, self.Nd = A.shape[0], B.shape[1], C.shape[0], Bd.shape[1]
+        Bp = Bd if Bp is None else Bp
+        self.Np = Bp.shape[1]
+        self.xprior, self.dprior, self.uprev0 = xprior, dprior, uprev
+        self.C, self.Rv = C, Rv
+        self._dev = _device_index(device)
+        self.filter = LinearMPCController.setup_filter(A=A, B=B, C=C, Bd=Bd, Cd=Cd, Qwx=Qwx, Qwd=Qwd, Rv=Rv,
+                                                       xprior=xprior, dprior=dprior)
+        f = self.filter
+        ILC = np.eye(self.Nx + self.Nd) - f.L @ f.C
+        Fkf = np.hstack([ILC @ f.A, ILC @ f.B, f.L])
+        Fpl = np.block([[A, B, Bp], [C @ A, C @ B, C @ Bp]])
+        self.target_selector = LinearMPCController.setup_target_selector(A=A, B=B, C=C, H=H, Bd=Bd, Cd=Cd, usp=usp, Qs=Qs,
+                                                                         Rs=Rs, ulb=ulb, uub=uub, device=self._dev)
+        Aaug, Baug, self.Qaug, self.Raug, self.Maug = LinearMPCController.get_augmented_matrices_for_regulator(A, B, Q, R, S)
+        self.regulator = self.layer = None
+        Kaug = None
+        if kind == "mpc":
+            self.regulator = LinearMPCController.setup_regulator(A=A, B=B, Q=Q, R=R, S=S, N=N, ulb=ulb, uub=uub,
+                                                                 device=self._dev, **solver_kwargs)
+        elif kind == "nn":
+            ctl = NeuralNetworkController(regulator_weights=regulator_weights, xscale=xscale, nnwithuprev=nnwithuprev,
+                                          ulb=ulb, uub=uub, device=self._dev, precision=precision)
+            self.layer, self._nn = ctl.layer, ctl
+        else:
+            Kaug, _ = dlqr(Aaug, Baug, self.Qaug, self.Raug, self.Maug)      # controller_evaluation.py:958-960
+        self.Kaug = Kaug
+        L = _lib.lib()
+        hnd = Ct.c_void_p()
+        hp = lambda a: None if a is None else _lib.hptr(_lib.host(a))
+        keep = [_lib.host(a) for a in (Fkf, Fpl, self.Qaug, self.Raug, self.Maug, ulb, uub)]
+        kk = None if Kaug is None else _lib.host(Kaug)
+        xsc = None if xscale is None or kind != "nn" else _lib.host(np.ravel(xscale))
+        rc = L.nnmpc_online_create(Ct.byref(hnd), self.regulator._handle if self.regulator else None,
+                                   self.target_selector._handle, self.layer._handle if self.layer else None,
+                                   self.Nx, self.Nu, self.Ny, self.Nd, self.Np, _lib.hptr(keep[0]), _lib.hptr(keep[1]),
+                                   None if kk is None else _lib.hptr(kk), _lib.hptr(keep[2]), _lib.hptr(keep[3]),
+                                   _lib.hptr(keep[4]), _lib.hptr(keep[5]), _lib.hptr(keep[6]),
+                                   None if xsc is None else _lib.hptr(xsc), self._dev)
+        _lib.check(rc, "nnmpc_online_create")
+        self._handle = hnd
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                from . import _lib
+                _lib.lib().nnmpc_online_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def run(self, setpoints, disturbances, *, noise=None, x0=None, seed=None, tol=1e-9, max_iter=20000):
+        """setpoints (S,T,Ny), disturbances (S,T,Np).  ``noise`` (S,T+1,Ny) measurement noise; default: drawn like
+        the reference does - ``np.random.seed(seed)`` before every scenario, ``std * randn(Ny,1)`` at construction
+        and after every step (controller_evaluation.py:347, linearMPC.py:103, :119).  Returns a dict of NumPy arrays:
+        u (S,T,Nu), y (S,T+1,Ny), x (S,T+1,Nx), xhat, xs (S,T,Nx), us (S,T,Nu), average_stage_costs (S,T) and, for
+        the MPC, iters / kkt (S,T)."""
+        import torch
+        from . import _lib
+        L = _lib.lib()
+        sp, ds = _lib.host(setpoints), _lib.host(disturbances)
+        S_, T = sp.shape[0], sp.shape[1]
+        if tuple(sp.shape) != (S_, T, self.Ny) or tuple(ds.shape) != (S_, T, self.Np):
+            raise ValueError(f"setpoints / disturbances must have shapes (S,T,{self.Ny}) / (S,T,{self.Np})")
+        if noise is None:
+            std = np.sqrt(np.diag(self.Rv))
+            noise = np.empty((S_, T + 1, self.Ny))
+            for s in range(S_):
+                if seed is not None:
+                    np.random.seed(seed)
+                for t in range(T + 1):
+                    noise[s, t] = std * np.random.randn(self.Ny)
+        noise = _lib.host(noise)
+        x0 = np.zeros((S_, self.Nx)) if x0 is None else np.broadcast_to(np.asarray(x0, float).reshape(-1, self.Nx), (S_, self.Nx))
+        dev = torch.device("cuda", self._dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        t_ = lambda a: torch.as_tensor(np.ascontiguousarray(a), **f64)
+        x_io = t_(x0)
+        xhat_io = t_(np.tile(np.vstack([self.xprior, self.dprior]).T, (S_, 1)))
+        up_io = t_(np.tile(np.asarray(self.uprev0, float).reshape(1, -1), (S_, 1)))
+        y = torch.zeros((S_, T + 1, self.Ny), **f64)
+        y[:, 0] = t_(x0 @ self.C.T + noise[:, 0])
+        out = dict(u=torch.empty((S_, T, self.Nu), **f64), x=torch.empty((S_, T + 1, self.Nx), **f64),
+                   xhat=torch.empty((S_, T, self.Nx), **f64), xs=torch.empty((S_, T, self.Nx), **f64),
+                   us=torch.empty((S_, T, self.Nu), **f64), average_stage_costs=torch.empty((S_, T), **f64))
+        iters = torch.zeros((S_, T), dtype=torch.int32, device=dev)
+        kkt = torch.zeros((S_, T), **f64)
+        d = lambda a: _lib.dptr(a, device=self._dev)
+        rc = L.nnmpc_online_run(self._handle, self.KINDS[self.kind], S_, T, d(x_io), d(xhat_io), d(up_io), d(t_(sp)),
+                                d(t_(ds)), d(t_(noise)), d(y), d(out["u"]), d(out["x"]), d(out["xhat"]), d(out["xs"]),
+                                d(out["us"]), d(out["average_stage_costs"]), _lib.dptr_i32(iters, self._dev), d(kkt),
+                                float(tol), int(max_iter), _lib.stream_ptr(self._dev))
+        hit = _lib.check(rc, "nnmpc_online_run")
+        res = {k: v.cpu().numpy() for k, v in out.items()}
+        res.update(y=y.cpu().numpy(), xhat_final=xhat_io.cpu().numpy(), maxiter_hit=hit)
+        if self.kind == "mpc":
+            res.update(iters=iters.cpu().numpy(), kkt=kkt.cpu().numpy())
+        return res
+
+    @staticmethod
+    def performance_loss(controller_result, mpc_result):
+        """100 (Lambda_controller - Lambda_mpc) / Lambda_mpc per scenario (controller_evaluation.py:396-397), Lambda =
+        the final average stage cost."""
+        lc = controller_result["average_stage_costs"][:, -1]
+        lm = mpc_result["average_stage_costs"][:, -1]
+        return 100.0 * (lc - lm) / lm

@@ -210,6 +210,18 @@ static int mlp_forward_tc(nnmpc_mlp* h, long long B, const double* x, const doub
   return 0;
 }
 
+// device-pointer forward in the handle's arithmetic mode, for other translation units (online.cu)
+int mlp_forward_dispatch(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
+                         const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
+                         cudaStream_t st) {
+  return h->tc_mode ? mlp_forward_tc(h, B, x, uprev, xs, us, xscale, ulb, uub, out, st)
+                    : mlp_forward_device(h, B, x, uprev, xs, us, xscale, ulb, uub, out, st);
+}
+int mlp_dims(const nnmpc_mlp* h, int* nx, int* nu, int* with_uprev) {
+  *nx = h->nx; *nu = h->nu; *with_uprev = h->with_uprev;
+  return h->device;
+}
+
 }  // namespace nnmpc
 
 using namespace nnmpc;

@@ -284,8 +284,7 @@ class OnlineControllerOracle:
         self.xhat = pred + self.L @ (y - self.Cf @ pred)
         xhat, dhat = self.xhat[:self.Nx], self.xhat[self.Nx:]
         xs, us = self.target_selector.solve(ysp, dhat)
-        useq = get_control_sequence(self.regulator, xhat, self.uprev, xs, us, self.ulb, self.uub)
-        u = useq[:self.Nu]
+        u = self.control_input(xhat, xs, us)
         self.average_stage_costs.append(updated_average_stage_cost(
             xhat, self.uprev, xs, us, u, self.Qaug, self.Raug, self.Maug, self.average_stage_costs[-1],
             len(self.average_stage_costs)))
@@ -293,6 +292,39 @@ class OnlineControllerOracle:
         self.xhats.append(xhat)
         self.targets.append((xs, us))
         return u
+
+
+    def control_input(self, xhat, xs, us):
+        """The MPC law (:658-661); NeuralNetworkController / SatDlqrController replace exactly this step
+        (controller_evaluation.py:849-852, :985-987)."""
+        useq = get_control_sequence(self.regulator, xhat, self.uprev, xs, us, self.ulb, self.uub)
+        return useq[:self.Nu]
+
+
+class OnlineNNControllerOracle(OnlineControllerOracle):
+    """NeuralNetworkController.control_law (controller_evaluation.py:841-862)."""
+
+    def __init__(self, *, regulator_weights, xscale, nnwithuprev, **kw):
+        super().__init__(regulator=object(), **kw)
+        self.weights, self.xscale, self.nnwithuprev = regulator_weights, np.asarray(xscale, float).reshape(-1, 1), nnwithuprev
+
+    def control_input(self, xhat, xs, us):
+        from . import nn as _nn
+        return _nn.control_input(self.weights, xhat, self.uprev, xs, us, self.nnwithuprev, self.xscale, self.ulb, self.uub)
+
+
+class OnlineSatDlqrControllerOracle(OnlineControllerOracle):
+    """SatDlqrController.control_law (controller_evaluation.py:975-993)."""
+
+    def __init__(self, **kw):
+        super().__init__(regulator=object(), **kw)
+        Aa, Ba, Qa, Ra, Ma = augmented_matrices_for_regulator(kw["A"], kw["B"], kw["Q"], kw["R"], kw["S"])
+        self.Kaug, _ = dlqr(Aa, Ba, Qa, Ra, Ma)
+
+    def control_input(self, xhat, xs, us):
+        u = self.Kaug @ np.vstack([xhat - xs, self.uprev - us]) + us
+        u = np.where(u > self.uub, self.uub, u)
+        return np.where(u < self.ulb, self.ulb, u)
 
 
 def online_simulation(plant_step, y0, controller, setpoints, disturbances, Nsim):
