@@ -720,7 +720,7 @@ def run_cstr_qp(args):
     t_setup = time.perf_counter() - t_setup
     n = p.N * p.Nu
     X0, LB, UB = _cstr_batch(p, ts, B, dev, torch, 2021 + rank)
-    mode = {}
+    mode = dict(precision=args.qp_precision) if args.qp_precision != "lockstep" else {}
 
     def solve():
         return reg.solve_batch(X0, LB, UB, max_iter=args.max_iter, **mode)
@@ -1025,8 +1025,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs: stop after the device-resident passes")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"],
                     help="regulator-QP iteration arithmetic: tcgen05 fp16 increments + FP64 anchors, or all FP64 DMMA")
-    ap.add_argument("--qp-precision", default=None, choices=["mixed", "f64"],
-                    help="cstr_qp_1m: arithmetic of solve_batch (default: the library's)")
+    ap.add_argument("--qp-precision", default="mixed", choices=["mixed", "f64", "lockstep"],
+                    help="cstr_qp_1m: solve_batch through the continuously batched engine (tcgen05 tiers or FP64), or the "
+                         "lock-step FP64 solver")
     ap.add_argument("--prof-steps", type=int, default=2, help="steps of the separate profiled pass")
     ap.add_argument("--alpha", type=float, default=None, help="Douglas-Rachford relaxation (solver default 1.8)")
     ap.add_argument("--rho-scale", type=float, default=None, help="multiplier of the default ADMM penalty (solver default 1)")

@@ -177,6 +177,14 @@ int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                   const double* setpoints, const double* disturbances, double* x, double* uprev,
                   double* xs, double* us, double* u, int* iters, double* kkt, double tol,
                   int max_iter, int resume, void* stream);
+/* Batched regulator QPs through the engine (the data-parallel form of DenseQPRegulator.solve, lib/linearMPC.py:495-512):
+ * B independent QPs, each its own x0 (B x nxa) and stage bounds lb/ub (B x nu), solved cold with continuous batching
+ * over the handle's slots - the arithmetic (nnmpc_sim_set_precision: tcgen05 fp16 increments + INT8-exact anchors and
+ * KKT checks, or FP64) and the certification are those of nnmpc_sim_run.  u (B x n) minimisers in deviation
+ * variables; cost, kkt, iters (B, nullable).  The handle may have been created with ts = NULL, ABd_host = NULL,
+ * nx = nxa - nu, nd = ny = 0. */
+int nnmpc_sim_solve_qps(nnmpc_sim_t* h, int B, const double* x0, const double* lb, const double* ub, double* u,
+                        double* cost, double* kkt, int* iters, double tol, int max_iter, void* stream);
 int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io,
                        const double* setpoints, const double* disturbances, double* x, double* uprev,
                        double* xs, double* us, double* u, int* iters, double* kkt, double tol,

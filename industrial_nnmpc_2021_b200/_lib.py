@@ -55,6 +55,7 @@ SIGNATURES = {
     "nnmpc_sim_active_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
                                 C.c_int, C.c_int, vp]),
+    "nnmpc_sim_solve_qps": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int, vp]),
     "nnmpc_sim_run_host": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,
                                      C.c_int, C.c_int]),
     "nnmpc_mlp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(vp),

@@ -561,15 +561,17 @@ __global__ void k_chunk_swap(const int* __restrict__ rows, const int* __restrict
   for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
     const long long s = rows[li];
     const long long co = c_old[li], cn = c_new[li];
-    for (int j = threadIdx.x; j < nx; j += blockDim.x) {
-      x_io[co * nx + j] = xcur[s * nx + j];
-      if (cn >= 0) xcur[s * nx + j] = x_io[cn * nx + j];
-    }
-    for (int j = threadIdx.x; j < nu; j += blockDim.x) {
-      uprev_io[co * nu + j] = upcur[s * nu + j];
-      if (cn >= 0) {
-        upcur[s * nu + j] = uprev_io[cn * nu + j];
-        us_prev[s * nu + j] = 0.0;
+    if (x_io) {                                   // (null in batched-QP mode: chunks carry no plant state)
+      for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+        x_io[co * nx + j] = xcur[s * nx + j];
+        if (cn >= 0) xcur[s * nx + j] = x_io[cn * nx + j];
+      }
+      for (int j = threadIdx.x; j < nu; j += blockDim.x) {
+        uprev_io[co * nu + j] = upcur[s * nu + j];
+        if (cn >= 0) {
+          upcur[s * nu + j] = uprev_io[cn * nu + j];
+          us_prev[s * nu + j] = 0.0;
+        }
       }
     }
     // a new chunk starts like a fresh trajectory: results do not depend on which slot serves it
@@ -663,6 +665,71 @@ __global__ void k_engine_init(EngineArrays e, int S, int keep_kappa, double kapp
   }
 }
 
+// Batched-QP mode of the engine (nnmpc_sim_solve_qps): every "trajectory chunk" is one regulator QP with its own
+// x0 and bounds, one step long; the continuous batching, the tensor-core tiers and the exact certification are
+// those of the closed loop, the target selector and the plant step drop out.
+struct QpBatch {
+  const double* X0;   // Btot x nxa_ld
+  const double* LB;   // Btot x nu
+  const double* UB;
+  double* U;          // Btot x n
+  double* cost;       // Btot, nullable
+};
+
+// renew rows in batched-QP mode: regulator inputs of the chunk (= QP) the slot now works on
+__global__ void k_qp_load(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ chunk,
+                          QpBatch qb, double* __restrict__ x0, double* __restrict__ lb, double* __restrict__ ub,
+                          double* __restrict__ dus, int nxa_ld, int nu) {
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li], c = chunk[s];
+    for (int j = threadIdx.x; j < nxa_ld; j += blockDim.x) x0[s * nxa_ld + j] = qb.X0[c * nxa_ld + j];
+    for (int j = threadIdx.x; j < nu; j += blockDim.x) {
+      lb[s * nu + j] = qb.LB[c * nu + j];
+      ub[s * nu + j] = qb.UB[c * nu + j];
+      dus[s * nu + j] = 0.0;
+    }
+  }
+}
+
+// done rows in batched-QP mode: minimiser, optimal cost 1/2 z'(g + q) and the workload statistics
+__global__ void __launch_bounds__(256)
+k_qp_store(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ chunk, QpBatch qb,
+           const double* __restrict__ Z, const double* __restrict__ G, const double* __restrict__ Ql,
+           const double* __restrict__ lb, const double* __restrict__ ub, unsigned long long* __restrict__ stats, int n,
+           int nu) {
+  __shared__ double red[8];
+  const int cnt = *count;
+  for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+    const long long s = rows[li], c = chunk[s];
+    double acc = 0.0;
+    int na = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const double z = Z[s * n + j];
+      qb.U[c * n + j] = z;
+      if (qb.cost) acc += z * (G[s * n + j] + Ql[s * n + j]);
+      na += (z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)]) ? 1 : 0;
+    }
+    if (__syncthreads_or(na > 0)) {
+      na = __reduce_add_sync(0xffffffffu, na);
+      if ((threadIdx.x & 31) == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
+      if (threadIdx.x == 0) atomicAdd(stats + 2, 1ull);
+    }
+    if (qb.cost) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        qb.cost[c] = 0.5 * t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 static int sim_ensure(nnmpc_sim* h, long long B) {
   if (B <= h->cap) return 0;
   const long long n = h->qp->n;
@@ -695,7 +762,8 @@ static int sim_ensure(nnmpc_sim* h, long long B) {
 
 static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* uprev_io, const double* sp,
                           const double* dist, double* ox, double* ouprev, double* oxs, double* ous, double* ou,
-                          int* oiters, double* okkt, double tol, int max_iter, int resume, cudaStream_t st) {
+                          int* oiters, double* okkt, double tol, int max_iter, int resume, cudaStream_t st,
+                          const QpBatch* qb = nullptr) {
   if (Btot <= 0 || T <= 0) return 0;
   if (max_iter < 1) max_iter = 1;
   // B trajectory slots advance concurrently; with more chunks than slots the rest queue up and a slot that
@@ -721,10 +789,13 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   }
   const bool oz = mixed && h->exact_oz;
   // gradient g = P z + q of the exact check: the mixed mode re-anchors from it; the cost capture needs it in any mode
-  if (!mixed && h->cap_cost) NNMPC_TRY(h->gcap.ensure((size_t)h->cap * n));
-  double* gbuf = mixed ? h->lps.Wl.p : (h->cap_cost ? h->gcap.p : nullptr);
-  NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
-  NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
+  const bool want_g = h->cap_cost || (qb && qb->cost);
+  if (!mixed && want_g) NNMPC_TRY(h->gcap.ensure((size_t)h->cap * n));
+  double* gbuf = mixed ? h->lps.Wl.p : (want_g ? h->gcap.p : nullptr);
+  if (!qb) {
+    NNMPC_CUDA(cudaMemcpyAsync(h->xcur.p, x_io, (size_t)B * nx * 8, cudaMemcpyDeviceToDevice, st));
+    NNMPC_CUDA(cudaMemcpyAsync(h->upcur.p, uprev_io, (size_t)B * nu * 8, cudaMemcpyDeviceToDevice, st));
+  }
   if (!cont) NNMPC_CUDA(cudaMemsetAsync(h->us_prev.p, 0, (size_t)B * nu * 8, st));
 
   EngineArrays e{};
@@ -757,7 +828,12 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     F.us_prev = h->us_prev.p; F.dus = h->dus.p;
     F.row_x = ox; F.row_uprev = ouprev; F.row_stride_x = nx; F.row_stride_u = nu;
     TsIndex ix{e.l_renew, e.counts + N_RENEW, e.tcur, T, e.chunk};
-    NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, e.counts + F_TS_FAIL, st));
+    if (qb) {
+      k_qp_load<<<row_grid(B), 128, 0, st>>>(e.l_renew, e.counts + N_RENEW, e.chunk, *qb, h->x0.p, h->lb.p, h->ub.p, h->dus.p, nxa, nu);
+      count_launch();
+    } else {
+      NNMPC_TRY(ts_solve_device(h->ts, B, sp, ny, dist, nd, oxs, nx, ous, nu, nullptr, 0, &F, &ix, e.counts + F_TS_FAIL, st));
+    }
     GemmOperands g{};
     g.A = h->x0.p; g.lda = nxa; g.ldb = nxa; g.M = B; g.N = n; g.K = nxa; g.rows = e.l_renew;
     g.m_count = e.counts + N_RENEW;
@@ -879,14 +955,18 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
                         h->ub.p, e.dtrig, nu, q->alpha, e.lp_pos + (long long)(lay ^ 1) * B, st, e.need2));
     }
     // 5. first move, dataset row, plant step for the done rows
-    k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, (size_t)ADV_ROWS * h->kin_ld * sizeof(double), st>>>(
-        e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou, h->upcur.p, h->ABd, n, nx, nu, nd,
-        h->kin_ld, gbuf, q->Ql.p, h->cap_useq, h->cap_cost, h->lb.p, h->ub.p, h->stats);
+    if (qb)
+      k_qp_store<<<row_grid(B), 256, 0, st>>>(e.l_done, e.counts + N_DONE, e.chunk, *qb, h->Z.p, gbuf, q->Ql.p, h->lb.p, h->ub.p,
+                                              h->stats, n, nu);
+    else
+      k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, (size_t)ADV_ROWS * h->kin_ld * sizeof(double), st>>>(
+          e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou, h->upcur.p, h->ABd, n, nx, nu, nd,
+          h->kin_ld, gbuf, q->Ql.p, h->cap_useq, h->cap_cost, h->lb.p, h->ub.p, h->stats);
     count_launch(2);
     // 6-7. next time step for the done rows
     k_step<<<1, 1024, 0, st>>>(e, T, B, lay);
     lay ^= 1;
-    k_chunk_swap<<<row_grid(B), 128, 0, st>>>(e.l_swap, e.counts + N_SWAP, e.swap_old, e.swap_new, h->xcur.p, h->upcur.p, x_io,
+    k_chunk_swap<<<row_grid(B), 128, 0, st>>>(e.l_swap, e.counts + N_SWAP, e.swap_old, e.swap_new, h->xcur.p, h->upcur.p, qb ? nullptr : x_io,
                                     uprev_io, h->us_prev.p, h->kappa.p, h->kappa0, nx, nu);
     count_launch(2);
     NNMPC_TRY(renew(0));
@@ -927,7 +1007,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   h->tot_qps += (long long)Btot * T;
   h->tot_qps_active += (long long)pin64[3];
   h->tot_active += (long long)pin64[4];
-  h->warm_B = Btot == B ? Btot : 0;
+  h->warm_B = (Btot == B && !qb) ? Btot : 0;
   return rc_warn;
 }
 
@@ -939,10 +1019,11 @@ extern "C" {
 
 int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, int nu, int nd, int ny,
                      const double* ABd_host, int device) {
-  if (!out || !qp || !ts || !ABd_host) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_create: null argument");
-  if (qp->device != device || ts->device != device)
+  // ts == NULL (with ABd_host == NULL): a handle for nnmpc_sim_solve_qps only
+  if (!out || !qp || (ts && !ABd_host)) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_create: null argument");
+  if (qp->device != device || (ts && ts->device != device))
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_create: handles live on different devices");
-  if (qp->nu != nu || ts->nu != nu || ts->nx != nx || ts->nd != nd || ts->ny != ny || qp->nxa < nx + nu)
+  if (qp->nu != nu || qp->nxa < nx + nu || (ts && (ts->nu != nu || ts->nx != nx || ts->nd != nd || ts->ny != ny)))
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_create: inconsistent sizes");
   DeviceGuard dg(device);
   nnmpc_sim* h = new (std::nothrow) nnmpc_sim();
@@ -967,17 +1048,20 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->kappa0 = 0.25 * qp->p_norm_inf;
   h->kappa_max = 8.0 * qp->p_norm_inf;
   // pad [A|B|Bd] rows to an even leading dimension for the 16-byte operand loader
-  double* tmp = new (std::nothrow) double[(size_t)nx * h->kin_ld];
-  if (!tmp) {
-    delete h;
-    return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+  int rc = 0;
+  if (ABd_host) {
+    double* tmp = new (std::nothrow) double[(size_t)nx * h->kin_ld];
+    if (!tmp) {
+      delete h;
+      return set_error(NNMPC_ERR_NOMEM, "out of host memory");
+    }
+    for (int r = 0; r < nx; ++r) {
+      for (int c = 0; c < kin; ++c) tmp[(size_t)r * h->kin_ld + c] = ABd_host[(size_t)r * kin + c];
+      for (int c = kin; c < h->kin_ld; ++c) tmp[(size_t)r * h->kin_ld + c] = 0.0;
+    }
+    rc = upload(&h->ABd, tmp, (size_t)nx * h->kin_ld);
+    delete[] tmp;
   }
-  for (int r = 0; r < nx; ++r) {
-    for (int c = 0; c < kin; ++c) tmp[(size_t)r * h->kin_ld + c] = ABd_host[(size_t)r * kin + c];
-    for (int c = kin; c < h->kin_ld; ++c) tmp[(size_t)r * h->kin_ld + c] = 0.0;
-  }
-  int rc = upload(&h->ABd, tmp, (size_t)nx * h->kin_ld);
-  delete[] tmp;
   auto cu = [&](cudaError_t e, const char* what) {
     if (rc == 0 && e != cudaSuccess) rc = set_error(NNMPC_ERR_CUDA, "nnmpc_sim_create: %s: %s", what, cudaGetErrorString(e));
   };
@@ -1105,9 +1189,21 @@ int nnmpc_sim_run(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, 
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: null argument");
   if (B < 0 || T < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: negative size");
+  if (!h->ts) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run: this handle was created without a target selector (batched-QP use only)");
   DeviceGuard dg(h->device);
   return sim_run_device(h, B, T, x_io, uprev_io, setpoints, disturbances, x, uprev, xs, us, u, iters, kkt, tol,
                         max_iter, resume, (cudaStream_t)stream);
+}
+
+int nnmpc_sim_solve_qps(nnmpc_sim_t* h, int B, const double* x0, const double* lb, const double* ub, double* u, double* cost,
+                        double* kkt, int* iters, double tol, int max_iter, void* stream) {
+  if (B == 0 && h) return 0;
+  if (!h || !x0 || !lb || !ub || !u) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_solve_qps: null argument");
+  if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_solve_qps: negative batch");
+  DeviceGuard dg(h->device);
+  QpBatch qb{x0, lb, ub, u, cost};
+  return sim_run_device(h, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, iters, kkt,
+                        tol, max_iter, 0, (cudaStream_t)stream, &qb);
 }
 
 int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev_io, const double* setpoints,
@@ -1117,6 +1213,7 @@ int nnmpc_sim_run_host(nnmpc_sim_t* h, int B, int T, double* x_io, double* uprev
   if (!h || !x_io || !uprev_io || !setpoints || !disturbances || !x || !uprev || !xs || !us || !u)
     return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: null argument");
   if (B <= 0 || T <= 0) return (B == 0 || T == 0) ? 0 : set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: negative size");
+  if (!h->ts) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_run_host: this handle was created without a target selector");
   DeviceGuard dg(h->device);
   const size_t bt = (size_t)B * T;
   const int nx = h->nx, nu = h->nu, nd = h->nd, ny = h->ny;

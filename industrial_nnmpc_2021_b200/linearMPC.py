@@ -398,6 +398,9 @@ class DenseQPRegulator:
 
     def __del__(self):
         try:
+            if getattr(self, "_qp_engine", None):
+                _lib.lib().nnmpc_sim_destroy(self._qp_engine)
+                self._qp_engine = None
             if getattr(self, "_handle", None):
                 _lib.lib().nnmpc_qp_destroy(self._handle)
                 self._handle = None
@@ -407,6 +410,7 @@ class DenseQPRegulator:
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_handle"] = None
+        d.pop("_qp_engine", None)
         return d
 
     def __setstate__(self, d):
@@ -414,9 +418,27 @@ class DenseQPRegulator:
         self._setup_solver()
 
     # ---- batched solve -------------------------------------------------------------------
+    def _batch_engine(self, precision, slots):
+        """QP-only engine handle (no target selector, no plant) behind ``solve_batch(precision=...)``."""
+        eng = getattr(self, "_qp_engine", None)
+        L = _lib.lib()
+        if eng is None:
+            hnd = C.c_void_p()
+            rc = L.nnmpc_sim_create(C.byref(hnd), self._handle, None, self._nxa_ld - self.Nu, self.Nu, 0, 0, None, self._dev)
+            _lib.check(rc, "nnmpc_sim_create")
+            eng = self._qp_engine = hnd
+        _lib.check(L.nnmpc_sim_set_precision(eng, _lib.PRECISION[precision]), "nnmpc_sim_set_precision")
+        _lib.check(L.nnmpc_sim_set_slots(eng, int(slots)), "nnmpc_sim_set_slots")
+        return eng
+
     def solve_batch(self, X0, LB=None, UB=None, *, warm_state=None, tol=None, max_iter=None, return_info=True,
-                    out=None):
+                    out=None, precision=None, slots=16384):
         """Solve B regulator QPs.
+
+        ``precision`` (CUDA-tensor form): None - the lock-step FP64 solver (supports ``warm_state``); "mixed" / "f64"
+        - cold solves through the continuously batched engine (``nnmpc_sim_solve_qps``): ``slots`` QPs iterate
+        concurrently, a finished slot takes the next QP, iterations run on the tcgen05 fp16-increment tier with
+        INT8-exact anchors and KKT checks ("mixed") or in FP64.
 
         ``out`` (NumPy form only): dict of preallocated result arrays ``U (B,n), cost (B,), kkt (B,), iters (B,)
         int32`` - e.g. pinned host memory - written in place.
@@ -431,6 +453,21 @@ class DenseQPRegulator:
         tol = self.tol if tol is None else tol
         max_iter = self.max_iter if max_iter is None else max_iter
         n = self.N * self.Nu
+        if isinstance(X0, np.ndarray) and precision is not None:
+            # host buffers through the engine form: copies in, device solve, copies out (into ``out`` when given)
+            torch = _torch()
+            dev = torch.device("cuda", self._dev)
+            up = lambda a: None if a is None else torch.from_numpy(_lib.host(a)).to(dev, non_blocking=True)
+            Ud, info = self.solve_batch(up(X0), up(LB), up(UB), tol=tol, max_iter=max_iter, precision=precision, slots=slots)
+            if out is None:
+                res = (Ud.cpu().numpy(), {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in info.items()})
+            else:
+                for k, v in (("U", Ud), ("cost", info["cost"]), ("kkt", info["kkt"]), ("iters", info["iters"])):
+                    torch.from_numpy(out[k]).copy_(v, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                res = (out["U"], dict(cost=out["cost"], kkt=out["kkt"], iters=out["iters"], maxiter_hit=info["maxiter_hit"]))
+            self.last_info = res[1]
+            return res if return_info else res[0]
         if isinstance(X0, np.ndarray):
             Bn = X0.shape[0]
             X0p = np.zeros((Bn, self._nxa_ld))
@@ -478,6 +515,20 @@ class DenseQPRegulator:
                     raise ValueError("warm_state must be a contiguous (B, n) CUDA tensor")
                 warm = 1 if getattr(warm_state, "_nnmpc_valid", False) else 0
             dv = self._dev
+            if precision is not None:
+                if precision not in _lib.PRECISION:
+                    raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)} or None")
+                if warm_state is not None:
+                    raise ValueError("warm_state is a feature of the lock-step solver (precision=None)")
+                eng = self._batch_engine(precision, slots)
+                rc = L.nnmpc_sim_solve_qps(eng, Bn, _lib.dptr(X0p, device=dv), _lib.dptr(LB, device=dv),
+                                           _lib.dptr(UB, device=dv), _lib.dptr(U, device=dv), _lib.dptr(cost, device=dv),
+                                           _lib.dptr(kkt, device=dv), _lib.dptr_i32(iters, dv), float(tol), int(max_iter),
+                                           _lib.stream_ptr(dv))
+                warned = _lib.check(rc, "nnmpc_sim_solve_qps")
+                info = dict(cost=cost, kkt=kkt, iters=iters, maxiter_hit=warned)
+                self.last_info = info
+                return (U, info) if return_info else U
             rc = L.nnmpc_qp_solve(self._handle, Bn, _lib.dptr(X0p, device=dv), _lib.dptr(LB, device=dv),
                                   _lib.dptr(UB, device=dv), _lib.dptr(U, device=dv), _lib.dptr(warm_state, device=dv),
                                   warm, _lib.dptr(cost, device=dv), _lib.dptr(kkt, device=dv), _lib.dptr_i32(iters, dv),

@@ -480,3 +480,41 @@ def test_regulator_model_wrapper(torch_cuda):
     rng = np.random.default_rng(0)
     x, xs, us = rng.standard_normal((10, 12)), rng.standard_normal((10, 12)), rng.standard_normal((10, 6))
     assert np.max(np.abs(m([x, xs, us]) - onn.layer_call(ws, [x, xs, us], False))) <= 1e-10
+
+
+# ------------------------------------------------------------------------------------ batched QPs through the engine
+@pytest.mark.parametrize("qp_precision", ["mixed", "f64"])
+def test_regulator_batch_through_engine_matches_oracle(torch_cuda, cstrs_problem, cstr_case, qp_precision):
+    """solve_batch(precision=...): cold QPs through the continuously batched engine (nnmpc_sim_solve_qps), more QPs
+    than slots, against the exact CPU optimum and the lock-step FP64 solver."""
+    torch = torch_cuda
+    from industrial_nnmpc_2021_b200.linearMPC import LinearMPCController
+    p = cstrs_problem
+    oreg, _, datas = cstr_case
+    d = {k: np.vstack([x[k] for x in datas]) for k in datas[0]}
+    X0 = np.hstack([d["x"] - d["xs"], d["uprev"] - d["us"]])
+    LB, UB = p.ulb.T - d["us"], p.uub.T - d["us"]
+    rng = np.random.default_rng(1)
+    X0 = np.vstack([X0, X0 * rng.uniform(0.2, 3.0, (X0.shape[0], 1))])          # 160 QPs
+    LB, UB = np.vstack([LB, LB]), np.vstack([UB, UB])
+    reg = LinearMPCController.setup_regulator(p.A, p.B, p.Q, p.R, p.S, p.N, p.ulb, p.uub)
+    t = lambda a: torch.tensor(a, device="cuda")
+    U, info = reg.solve_batch(t(X0), t(LB), t(UB), precision=qp_precision, slots=48)
+    Uref, iref = reg.solve_batch(t(X0), t(LB), t(UB))
+    assert not info["maxiter_hit"] and float(info["kkt"].max()) <= KKT_TOL
+    assert float((U - Uref).abs().max()) <= 1e-7
+    U, cost = U.cpu().numpy(), info["cost"].cpu().numpy()
+    box = oq.BoxQP(oreg.P)
+    nact = 0
+    for i in range(0, X0.shape[0], 3):
+        q = oreg.tq @ X0[i]
+        lb, ub = np.tile(LB[i], p.N), np.tile(UB[i], p.N)
+        ue, ei = box.solve(q, lb, ub)
+        nact += ei["n_active"] > 0
+        assert oq.box_kkt_residual(oreg.P, q, U[i], lb, ub) <= KKT_TOL
+        assert _rel(U[i][:p.Nu], ue[:p.Nu])[0] <= U0_RTOL
+        assert abs(cost[i] - ei["cost"]) <= COST_RTOL * max(abs(ei["cost"]), 1e-6)
+    assert nact > 10
+    # NumPy in -> NumPy out through the same engine
+    U2, info2 = reg.solve_batch(X0, LB, UB, precision=qp_precision, slots=48)
+    assert np.max(np.abs(U2 - U)) <= 1e-7 and float(np.max(info2["kkt"])) <= KKT_TOL
