@@ -891,7 +891,12 @@ def run_nn(args):
     lowp = layer.precision == "tc"
     peaks, peak_src = _peaks()
     best = _dgemm_peak(ctx)
-    peak = float(peaks.get("bf16_tflops_sustained") or 1386.0) if lowp else best
+    int8_meas = _int8_peak(ctx) if lowp else None
+    if lowp:            # INT8 tier: 10 digit-plane products per FP64-equivalent flop
+        achieved *= 10.0
+        peak = int8_meas if int8_meas else 2.0 * float(peaks.get("bf16_tflops_sustained") or 1386.0)
+    else:
+        peak = best
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -905,15 +910,18 @@ def run_nn(args):
         line.update({
             "max_abs_err_vs_numpy": err,
             "roofline": {"bound": "tensor",
-                         "kernel": ("lp_gemm_kernel<EpiMlp*> (tcgen05 kind::f16, three-product fp16 split of activations and "
-                                    "weights, fp32 TMEM accumulation)" if lowp else
+                         "kernel": ("oz_gemm2_kernel<0,3,128,OzEpiDense> + k_oz_slice<4> (tcgen05 kind::i8: 4 base-128 digit planes "
+                                    "of activations and weights, 10 products, exact INT32 accumulation)" if lowp else
                                     "gemm_f64_kernel<EpiStore|EpiStructOut> (FP64 DMMA, bias + ReLU fused)"),
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None,
-                         "flops_per_launch": f"{flops_state / 1e6:.2f} MFLOP per state (both network passes, all layers); whole "
-                                             "forward timed, achieved = states/s x flops per state",
-                         "peak_source": (f"sustained 16-bit dense figure of MEASURED_PEAKS.json ({peak_src})" if lowp else
-                                         "cuBLAS DGEMM 6144^3 measured in this run")},
+                         "achieved": achieved, "peak": peak, "unit": "TOP/s" if lowp else "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "fp64_equivalent_tflops": achieved / 10.0 if lowp else achieved, "cublas_dgemm_tflops": best,
+                         "flops_per_launch": f"{flops_state / 1e6:.2f} MFLOP per state (both network passes, all layers)"
+                                             + (" x 10 INT8 digit-plane products" if lowp else "") + "; whole forward timed "
+                                             "(slicing kernels included), achieved = states/s x ops per state",
+                         "peak_source": (("dense INT8 GEMM 8192^3 through the library (torch._int_mm) measured in this run"
+                                          if int8_meas else f"2 x the sustained 16-bit dense figure of MEASURED_PEAKS.json ({peak_src})")
+                                         if lowp else "cuBLAS DGEMM 6144^3 measured in this run")},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": sum(h.nbytes for h in host) * nblk * world,
                     "d2h_bytes_per_step": oh.nbytes * nblk * world, "ms_per_step": ms_e2e / K,

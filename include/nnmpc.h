@@ -149,7 +149,7 @@ int nnmpc_sim_set_slots(nnmpc_sim_t* h, int slots);
 int nnmpc_sim_set_cadence(nnmpc_sim_t* h, int cadence);
 /* Mixed mode only: once at most `rows` trajectories of a call are still running, the rest of the call
  * iterates with skinny FP64 GEMMs over just those rows instead of full tensor-core passes
- * (rows < 0: automatic, max(48, B/16); 0: never). */
+ * (rows < 0: automatic, max(48, B/256); 0: never). */
 int nnmpc_sim_set_tail_rows(nnmpc_sim_t* h, int rows);
 /* Mixed mode only: which tensor pipe evaluates the FP64-exact operator applies (anchors x = Top w - c, KKT checks
  * g = P z + q): 1 (default) = INT8 tcgen05 with error-free slicing (FP64-accurate, see oz_gemm.cuh), 0 = FP64 DMMA. */
@@ -157,8 +157,9 @@ int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
 /* Mixed mode only: a trajectory whose last Douglas-Rachford residual ||d||_inf is at most factor * tol is in the late
  * phase of its QP; 128-row operand tiles made of such rows only run the tensor-core pass with the first fp16 operator
  * term alone (half the MMA work; the 2^-11 relative error of the dropped term is relative to a vanishing increment and
- * every result is still certified by the exact KKT check).  Default 1000 (measured on B200: same iterations and
- * exact checks per QP as with both terms everywhere); 0 = always both terms. */
+ * every result is still certified by the exact KKT check).  Default 0 = always both terms: measured on B200, only
+ * 0.4 - 6 % of the tiles qualify (trajectories restart inside late tiles between re-layouts) and a row's arithmetic would
+ * depend on its neighbours; factors up to 1e4 left iterations and exact checks per QP unchanged. */
 int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor);
 /* cumulative since create: out2 = {128x128 tensor-core tiles run with one operator term, with both terms} */
 int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2);
@@ -199,9 +200,10 @@ int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_
                      const int* dims, const double* const* weights_host,
                      const double* const* biases_host, int device);
 int nnmpc_mlp_destroy(nnmpc_mlp_t* h);
-/* Arithmetic of the Dense layers: 1 (default) = tcgen05 tensor cores, activations and weights as two-term fp16 splits
- * (three products, 22 significant bits) with fp32 TMEM accumulation and FP64 bias / ReLU / output assembly - within the
- * 1e-5 output tolerance, steady-state identity u = us exact; 0 = FP64 DMMA GEMMs (~1e-13 of the NumPy form). */
+/* Arithmetic of the Dense layers: 1 (default) = INT8 tcgen05 tensor cores - activations and weights as 4 signed
+ * base-128 digit planes, the 10 digit-plane products of levels 0..3 accumulated exactly in INT32, FP64 bias / ReLU /
+ * output assembly: ~1e-7 of the float64 layer, steady-state identity u = us exact; 0 = FP64 DMMA GEMMs (~1e-13);
+ * 2 = split-fp16 tcgen05 GEMMs with fp32 TMEM accumulation (~2e-5: outside the 1e-5 tolerance, comparison only). */
 int nnmpc_mlp_set_precision(nnmpc_mlp_t* h, int mode);
 /* x,xs dev B x nx; uprev,us dev B x nu (uprev ignored when !with_uprev); out dev B x nu.
  * xscale dev nx or NULL (x/xscale, xs/xscale, :863-866); ulb/uub dev nu or NULL (clip, :888-892). */

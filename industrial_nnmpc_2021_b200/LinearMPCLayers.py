@@ -1,6 +1,6 @@
 """Drop-in mirror of the structured-network layers of /root/reference/lib/LinearMPCLayers.py
-(forward pass only), evaluated by the fused tensor-core kernels of libnnmpc.so (tcgen05 split-fp16
-layers by default, FP64 DMMA on request).
+(forward pass only), evaluated by the fused tensor-core kernels of libnnmpc.so (INT8 tcgen05 layers with
+exact INT32 accumulation by default, FP64 DMMA on request).
 
     RegulatorLayerWithUprev    u = us + NN(x, uprev, xs, us) - NN(xs, us, xs, us)     (:15-64)
     RegulatorLayerWithoutUprev u = us + NN(x, xs, us)        - NN(xs, xs, us)         (:66-115)
@@ -23,15 +23,17 @@ from . import _lib
 
 class _StructuredRegulatorLayer:
     _with_uprev = True
+    _MODES = {"f64": 0, "tc": 1, "fp16": 2}
 
     def __init__(self, layer_dims, trainable=True, name=None, *, device=None, seed=None, precision=None):
-        """``precision`` (additive): "tc" - Dense layers on the tcgen05 tensor cores as split-fp16 products, outputs
-        within 1e-5 of the float64 Keras layer - or "f64" (FP64 tensor-core GEMMs).  Default: environment variable
-        NNMPC_MLP, else "tc"."""
+        """``precision`` (additive): "tc" - Dense layers on the INT8 tcgen05 tensor cores (digit-plane products with
+        exact INT32 accumulation), outputs within ~1e-7 of the float64 Keras layer; "f64" - FP64 tensor-core GEMMs;
+        "fp16" - split-fp16 tcgen05 GEMMs with fp32 accumulation (~2e-5, outside the 1e-5 tolerance: comparison only).
+        Default: environment variable NNMPC_MLP, else "tc"."""
         import os
         self.precision = precision or os.environ.get("NNMPC_MLP", "tc")
-        if self.precision not in ("tc", "f64"):
-            raise ValueError("precision must be 'tc' or 'f64'")
+        if self.precision not in self._MODES:
+            raise ValueError(f"precision must be one of {sorted(self._MODES)}")
         self.layer_dims = [int(d) for d in layer_dims]
         self.trainable, self.name = trainable, name
         self._seed = seed
@@ -97,7 +99,7 @@ class _StructuredRegulatorLayer:
         hnd = C.c_void_p()
         rc = L.nnmpc_mlp_create(C.byref(hnd), self._nx, self._nu, int(self._with_uprev), nl, darr, warr, barr, dev)
         _lib.check(rc, "nnmpc_mlp_create")
-        _lib.check(L.nnmpc_mlp_set_precision(hnd, 1 if self.precision == "tc" else 0), "nnmpc_mlp_set_precision")
+        _lib.check(L.nnmpc_mlp_set_precision(hnd, self._MODES[self.precision]), "nnmpc_mlp_set_precision")
         self._handle, self._dev = hnd, dev
         self._weights = [np.array(w, dtype=np.float64) for w in weights]
 

@@ -10,11 +10,18 @@
 // layer's epilogue forms us + out(2b) - out(2b+1) (+ clip) with one warp shuffle - the difference
 // never goes through memory.
 //
-// Two arithmetic modes (nnmpc_mlp_set_precision): the layers run on the tcgen05 tensor cores as three-product
-// split-fp16 GEMMs with fp32 TMEM accumulation (mlp_tc.cuh; default, within the 1e-5 tolerance of the north star,
-// steady-state identity exact), or as FP64 DMMA GEMMs (~1e-13).
+// Arithmetic modes (nnmpc_mlp_set_precision):
+//   1 (default)  INT8 tcgen05 tensor cores: activations and weights as 4 signed base-128 digit planes, the 10
+//                digit-plane products of levels 0..3 accumulated EXACTLY in INT32 (oz_gemm.cuh), bias / ReLU / output
+//                assembly in FP64 - ~1e-7 of the float64 Keras layer, no accumulation error;
+//   0            FP64 DMMA GEMMs (~1e-13);
+//   2            split-fp16 tcgen05 GEMMs with fp32 TMEM accumulation (mlp_tc.cuh) - measured on B200: the fp32
+//                accumulation of kind::f16 loses ~2^-22 of the running sum per MMA step (2e-6 rms, 1.4e-5 max per
+//                832-wide layer, tools/probes/lp_accum_error.py), which leaves the 1e-5 tolerance in the tails, so
+//                this mode is kept for comparison only.
 #include "qp.cuh"
 #include "mlp_tc.cuh"
+#include "oz.cuh"
 
 struct nnmpc_mlp {
   int nx, nu, with_uprev, L, device;
@@ -25,8 +32,12 @@ struct nnmpc_mlp {
   int maxw;            // widest hidden activation (ld)
   nnmpc::DevBuf<double> act0, act1;
   nnmpc::DevBuf<double> hx, hup, hxs, hus, hout, hscale, hlb, hub;
-  // tcgen05 mode
-  int tc_mode;                      // 1: split-fp16 tcgen05 layers, 0: FP64 DMMA
+  // INT8 tcgen05 mode
+  nnmpc::OzOperator ozW[16];        // weight digit planes per layer
+  nnmpc::OzRows ozA[16];            // activation digit planes per layer (distinct contraction lengths)
+  nnmpc::DevBuf<double> fout;       // last layer: f of both passes, 2 B x nu
+  // split-fp16 tcgen05 mode
+  int tc_mode;                      // 1: INT8 tcgen05 layers, 2: split-fp16 tcgen05 layers, 0: FP64 DMMA
   nnmpc::MlpTcLayer tcl[16];
   int kp_max;
   long long tc_rows;                // operand rows the buffers / tensor maps below are sized for
@@ -139,6 +150,51 @@ static int mlp_forward_device(nnmpc_mlp* h, long long B, const double* x, const 
   return 0;
 }
 
+// out[b] = us[b] + (f[2b] - f[2b+1]), optional clip (LinearMPCLayers.py:58-60, controller_evaluation.py:888-892)
+__global__ void k_struct_out(const double* __restrict__ f, const double* __restrict__ us, const double* __restrict__ ulb,
+                             const double* __restrict__ uub, double* __restrict__ out, long long B, int nu) {
+  const long long total = B * nu;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / nu;
+    const int c = (int)(i - b * nu);
+    double v = us[i] + (f[(2 * b) * nu + c] - f[(2 * b + 1) * nu + c]);
+    if (ulb) v = fmin(fmax(v, ulb[c]), uub[c]);
+    out[i] = v;
+  }
+}
+
+// INT8 tensor-core forward: every layer = slice the FP64 activations into digit planes + one exact-accumulation GEMM
+static int mlp_forward_i8(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
+                          const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
+                          cudaStream_t st) {
+  if (B <= 0) return 0;
+  long long chunk = (long long)(1ll << 28) / (2ll * h->maxw);
+  chunk = chunk < 1024 ? 1024 : (chunk > (1 << 18) ? (1 << 18) : chunk);
+  if (chunk > B) chunk = B;
+  NNMPC_TRY(h->act0.ensure((size_t)2 * chunk * h->maxw));
+  NNMPC_TRY(h->act1.ensure((size_t)2 * chunk * h->maxw));
+  NNMPC_TRY(h->fout.ensure((size_t)2 * chunk * h->nu));
+  const int nx = h->nx, nu = h->nu, L = h->L;
+  for (long long b0 = 0; b0 < B; b0 += chunk) {
+    const long long nb = B - b0 < chunk ? B - b0 : chunk;
+    k_pack_inputs<<<148 * 16, 256, 0, st>>>(x + b0 * nx, uprev ? uprev + b0 * nu : nullptr, xs + b0 * nx,
+                                            us + b0 * nu, xscale, h->act0.p, nb, nx, nu, h->with_uprev, h->ld[0]);
+    count_launch();
+    double* cur = h->act0.p;
+    double* nxt = h->act1.p;
+    for (int l = 0; l < L; ++l) {
+      const bool last = l == L - 1;
+      NNMPC_TRY(oz_dense_layer(&h->ozW[l], &h->ozA[l], (int)(2 * nb), cur, h->ld[l], last ? nullptr : h->bias[l], last ? 0 : 1,
+                               last ? h->fout.p : nxt, last ? nu : h->ld[l + 1], h->device, st));
+      double* t = cur; cur = nxt; nxt = t;
+    }
+    k_struct_out<<<148 * 4, 256, 0, st>>>(h->fout.p, us + b0 * nu, ulb, uub, out + b0 * nu, nb, nu);
+    count_launch();
+  }
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // (out x ld) FP64 transposed weights -> two fp16 terms (rows padded with zeros, kp columns)
 __global__ void k_split_weights(const double* __restrict__ Wt, int rows, int cols, int ld, int kp, double s,
                                 __half* __restrict__ T1, __half* __restrict__ T2) {
@@ -214,8 +270,8 @@ static int mlp_forward_tc(nnmpc_mlp* h, long long B, const double* x, const doub
 int mlp_forward_dispatch(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
                          const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
                          cudaStream_t st) {
-  return h->tc_mode ? mlp_forward_tc(h, B, x, uprev, xs, us, xscale, ulb, uub, out, st)
-                    : mlp_forward_device(h, B, x, uprev, xs, us, xscale, ulb, uub, out, st);
+  return (h->tc_mode == 1 ? mlp_forward_i8 : h->tc_mode == 2 ? mlp_forward_tc : mlp_forward_device)(
+      h, B, x, uprev, xs, us, xscale, ulb, uub, out, st);
 }
 int mlp_dims(const nnmpc_mlp* h, int* nx, int* nu, int* with_uprev) {
   *nx = h->nx; *nu = h->nu; *with_uprev = h->with_uprev;
@@ -275,6 +331,8 @@ int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_
     rc = upload(&h->Wt[l], tmp, (size_t)outw * ld);
     delete[] tmp;
     if (rc < 0) break;
+    rc = oz_slice_operator(h->Wt[l], outw, in, &h->ozW[l], 0, ld);       // INT8 digit planes of the weights
+    if (rc < 0) break;
     MlpTcLayer& T = h->tcl[l];
     T.in = in; T.out = outw; T.kp = (in + lp::BK - 1) / lp::BK * lp::BK;
     if (T.kp > h->kp_max) h->kp_max = T.kp;
@@ -321,7 +379,8 @@ int nnmpc_mlp_create(nnmpc_mlp_t** out, int nx, int nu, int with_uprev, int num_
 
 int nnmpc_mlp_set_precision(nnmpc_mlp_t* h, int mode) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_set_precision: null handle");
-  if (mode != 0 && mode != 1) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_set_precision: mode must be 0 (FP64 DMMA) or 1 (tcgen05 split fp16)");
+  if (mode < 0 || mode > 2)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_set_precision: mode must be 0 (FP64 DMMA), 1 (INT8 tcgen05) or 2 (split-fp16 tcgen05)");
   h->tc_mode = mode;
   return 0;
 }
@@ -334,7 +393,10 @@ int nnmpc_mlp_destroy(nnmpc_mlp_t* h) {
     if (h->bias[l]) cudaFree(h->bias[l]);
     h->tcl[l].T1.release();
     h->tcl[l].T2.release();
+    h->ozW[l].release();
+    h->ozA[l].release();
   }
+  h->fout.release();
   for (int b = 0; b < 2; ++b) { h->tcA[b].release(); h->tcsc[b].release(); h->tcamax[b].release(); }
   h->act0.release(); h->act1.release();
   h->hx.release(); h->hup.release(); h->hxs.release(); h->hus.release(); h->hout.release();
@@ -352,8 +414,7 @@ int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double
   if ((ulb == nullptr) != (uub == nullptr)) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: ulb/uub both or none");
   if (B < 0) return set_error(NNMPC_ERR_BADARG, "nnmpc_mlp_forward: negative batch");
   DeviceGuard dg(h->device);
-  return h->tc_mode ? mlp_forward_tc(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream)
-                    : mlp_forward_device(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream);
+  return mlp_forward_dispatch(h, B, x, uprev, xs, us, xscale, ulb, uub, out, (cudaStream_t)stream);
 }
 
 int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev, const double* xs,
@@ -385,9 +446,9 @@ int nnmpc_mlp_forward_host(nnmpc_mlp_t* h, long long B, const double* x, const d
     NNMPC_CUDA(cudaMemcpyAsync(h->hlb.p, ulb, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
     NNMPC_CUDA(cudaMemcpyAsync(h->hub.p, uub, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
   }
-  NNMPC_TRY((h->tc_mode ? mlp_forward_tc : mlp_forward_device)(
-      h, B, h->hx.p, h->with_uprev ? h->hup.p : nullptr, h->hxs.p, h->hus.p, xscale ? h->hscale.p : nullptr,
-      ulb ? h->hlb.p : nullptr, ulb ? h->hub.p : nullptr, h->hout.p, st));
+  NNMPC_TRY(mlp_forward_dispatch(h, B, h->hx.p, h->with_uprev ? h->hup.p : nullptr, h->hxs.p, h->hus.p,
+                                 xscale ? h->hscale.p : nullptr, ulb ? h->hlb.p : nullptr, ulb ? h->hub.p : nullptr,
+                                 h->hout.p, st));
   NNMPC_CUDA(cudaMemcpyAsync(out, h->hout.p, b * nu * 8, cudaMemcpyDeviceToHost, st));
   NNMPC_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -116,7 +116,7 @@ struct OzEpiVerify {
 };
 
 // ---- host side ---------------------------------------------------------------------------------
-int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st) {
+int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st, long long ld) {
   if (ncols > 32768) return set_error(NNMPC_ERR_BADARG, "oz_slice_operator: contraction length %d above 32768 (int32 accumulators)", ncols);
   op->nrows = nrows; op->ncols = ncols;
   op->ldb = ((long long)ncols + oz::BKB - 1) / oz::BKB * oz::BKB;
@@ -126,8 +126,8 @@ int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op,
   NNMPC_TRY(op->escale.ensure((size_t)op->rows_pad));
   NNMPC_CUDA(cudaMemsetAsync(op->S.p, 0, bytes, st));
   NNMPC_CUDA(cudaMemsetAsync(op->escale.p, 0, (size_t)op->rows_pad * sizeof(double), st));
-  oz::k_oz_slice<OZ_NS><<<nrows, 256, 0, st>>>(nullptr, nullptr, T_dev, ncols, ncols, op->S.p, op->rows_pad, op->ldb,
-                                               op->escale.p);
+  oz::k_oz_slice<OZ_NS><<<nrows, 256, 0, st>>>(nullptr, nullptr, T_dev, ld > 0 ? ld : ncols, ncols, op->S.p, op->rows_pad,
+                                               op->ldb, op->escale.p, nrows);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   if (!oz::make_tmap_u8(&op->tm, op->S.p, OZ_NS * op->rows_pad, op->ldb, op->ldb, oz::BN))
@@ -138,26 +138,31 @@ int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op,
   return 0;
 }
 
-int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st) {
+int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st, int ns) {
+  if (ns <= 0) ns = OZ_NS;
   const long long ldb = ((long long)ncols + oz::BKB - 1) / oz::BKB * oz::BKB;
   const long long cap_pad = (cap + oz::BM - 1) / oz::BM * oz::BM;
-  if (cap_pad <= r->cap_pad && ldb == r->ldb && ncols == r->ncols) return 0;
+  if (cap_pad <= r->cap_pad && ldb == r->ldb && ncols == r->ncols && ns == r->ns) return 0;
   const long long cp = cap_pad > r->cap_pad ? cap_pad : r->cap_pad;
-  const size_t bytes = (size_t)OZ_NS * cp * ldb;
+  const size_t bytes = (size_t)ns * cp * ldb;
   NNMPC_TRY(r->S.ensure(bytes));
   NNMPC_TRY(r->fscale.ensure((size_t)cp));
   NNMPC_CUDA(cudaMemsetAsync(r->S.p, 0, bytes, st));      // the k-padding stays zero: the slicing kernel writes ncols bytes per row
   NNMPC_CUDA(cudaMemsetAsync(r->fscale.p, 0, (size_t)cp * sizeof(double), st));
-  if (!oz::make_tmap_u8(&r->tm, r->S.p, OZ_NS * cp, ldb, ldb, oz::BM))
+  if (!oz::make_tmap_u8(&r->tm, r->S.p, ns * cp, ldb, ldb, oz::BM))
     return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the sample digit planes");
-  r->cap_pad = cp; r->ldb = ldb; r->ncols = ncols;
+  r->cap_pad = cp; r->ldb = ldb; r->ncols = ncols; r->ns = ns;
   return 0;
 }
 
 static int oz_slice_rows(OzRows* r, const int* rows, const int* count, int max_rows, const double* src, long long ld_src,
                          cudaStream_t st) {
-  oz::k_oz_slice<OZ_NS><<<row_grid(max_rows), 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
-                                                  r->fscale.p);
+  if (r->ns == 4)
+    oz::k_oz_slice<4><<<row_grid(max_rows), 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
+                                                          r->fscale.p, max_rows);
+  else
+    oz::k_oz_slice<OZ_NS><<<row_grid(max_rows), 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
+                                                              r->fscale.p, max_rows);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -215,6 +220,47 @@ int oz_verify(const OzOperator* P, OzRows* r, const int* rows, const int* count,
   NNMPC_TRY(oz_slice_rows(r, rows, count, max_rows, Z, n, st));
   return oz_apply<OZ_LMAX, OzEpiVerify>(P, r, max_rows, count, OzEpiVerify::Params{Z, Ql, lb, ub, kres, G, rows, n, nu},
                                         device, st);
+}
+
+// ---- structured-network Dense layer (mlp.cu) ---------------------------------------------------------------------
+struct OzEpiDense {
+  struct Params {
+    double* out;
+    long long ldo;
+    const double* bias;   // nullable
+    int relu;
+  };
+  Params p;
+  long long pos;
+  __device__ explicit OzEpiDense(const Params& p_) : p(p_), pos(0) {}
+  __device__ void begin_row(int pos_, bool) { pos = pos_; }
+  __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+#pragma unroll
+    for (int k = 0; k < oz::CH; ++k) {
+      const int col = col0 + k;
+      if (col < N) {
+        double h = v[k] + (p.bias ? __ldg(p.bias + col) : 0.0);
+        if (p.relu) h = h > 0.0 ? h : 0.0;
+        p.out[pos * p.ldo + col] = h;
+      }
+    }
+  }
+  __device__ void end_row() {}
+};
+
+int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long long lda, const double* bias, int relu,
+                   double* out, long long ldo, int device, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (!W->ready) return set_error(NNMPC_ERR_BADARG, "oz_dense_layer: weights not sliced");
+  NNMPC_TRY(oz_rows_ensure(r, M, W->ncols, st, 4));
+  NNMPC_TRY(oz_slice_rows(r, nullptr, nullptr, M, A, lda, st));
+  const oz::OzShape g = oz_shape(W, r, M, nullptr);
+  cudaError_t e = oz::launch_oz_gemm2<0, 3, 128, OzEpiDense>(r->tm, W->tm128, oz::OzShape2{g, nullptr, 0, 0},
+                                                             OzEpiDense::Params{out, ldo, bias, relu},
+                                                             device_sm_count(device), st);
+  count_launch();
+  if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 }  // namespace nnmpc

@@ -24,6 +24,7 @@ struct OzRows {
   long long cap_pad = 0;    // rows per plane (multiple of 128)
   long long ldb = 0;
   int ncols = 0;
+  int ns = 0;               // digit planes kept (8 for the FP64-exact applies, 4 for the structured-network layers)
   DevBuf<int8_t> S;
   DevBuf<double> fscale;    // per position: 2^f
   DevBuf<double> partial;   // cap_pad x ncols: partial level sums between the two launches of the 128-column kernel
@@ -31,8 +32,14 @@ struct OzRows {
   void release() { S.release(); fscale.release(); partial.release(); cap_pad = 0; }
 };
 
-int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st);
-int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st);
+int oz_slice_operator(const double* T_dev, int nrows, int ncols, OzOperator* op, cudaStream_t st, long long ld = 0);
+int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st, int ns = 0);
+// One Dense layer of the structured network on the INT8 tensor cores: out[M x N] = act(A[M x K] W^T + bias), with A
+// (FP64, leading dimension lda) cut into 4 signed base-128 digit planes per row (28 bits below the row maximum) and
+// the 10 digit-plane products of levels 0..3 accumulated exactly in INT32 - no accumulation error, truncation
+// <= 4 K 2^-30 relative to (row max) x (weight-row max).  W: operator planes from oz_slice_operator (N x K).
+int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long long lda, const double* bias, int relu,
+                   double* out, long long ldo, int device, cudaStream_t st);
 // x = Top w - c for the listed rows (W, C, X are B x n with the sample row as physical row)
 int oz_anchor(const OzOperator* top, OzRows* r, const int* rows, const int* count, int max_rows, const double* W,
               const double* C, double* X, int n, int device, cudaStream_t st);

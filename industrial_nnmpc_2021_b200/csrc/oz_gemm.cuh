@@ -505,9 +505,11 @@ inline cudaError_t launch_oz_gemm2(const CUtensorMap& tmA, const CUtensorMap& tm
 template <int NS>
 __global__ void __launch_bounds__(256)
 k_oz_slice(const int* __restrict__ rows, const int* __restrict__ count, const double* __restrict__ src, long long ld_src,
-           int ncols, int8_t* __restrict__ dst, long long rows_pad, long long ldb, double* __restrict__ scale_out) {
-  // grid-stride over the listed rows (the grid is capped by the launcher, the list length lives on the device)
-  const long long total = count ? *count : (long long)gridDim.x;
+           int ncols, int8_t* __restrict__ dst, long long rows_pad, long long ldb, double* __restrict__ scale_out,
+           int max_rows) {
+  // grid-stride over the listed rows (the grid is capped by the launcher; the list length lives on the device, or
+  // every one of max_rows rows is taken)
+  const long long total = count ? (*count < max_rows ? *count : max_rows) : (long long)max_rows;
   __shared__ double red[8];
   for (long long p = blockIdx.x; p < total; p += gridDim.x) {
     const long long r = rows ? rows[p] : p;

@@ -808,7 +808,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   e.swap_old = h->lists.p + 7 * (long long)B; e.swap_new = h->lists.p + 8 * (long long)B;
   e.chunk = h->chunk.p; e.cold = h->cold.p; e.n_chunks = Btot;
   e.lp_list = h->lp_layout.p; e.lp_pos = h->lp_layout.p + 2 * (long long)B;
-  e.tail_rows = h->tail_rows >= 0 ? h->tail_rows : (B / 16 > 48 ? B / 16 : 48);
+  // automatic tail: below ~B/256 live rows skinny FP64 GEMMs beat a tensor-core pass (measured on B200, round 2c:
+  // B/16 spends 5.5 % of the step in the tail, B/64 2.3 %, B/256 1.5 %)
+  e.tail_rows = h->tail_rows >= 0 ? h->tail_rows : (B / 256 > 48 ? B / 256 : 48);
   const bool t2skip = mixed && h->t2_factor > 0.0;
   e.dlast = h->dlast.p; e.t2_thr = h->t2_factor * tol; e.need2 = t2skip ? h->need2.p : nullptr;
   if (t2skip) NNMPC_CUDA(cudaMemsetAsync(h->need2.p, 1, (size_t)((B + 127) / 128 + 2), st));   // first pass: both terms everywhere
@@ -1042,7 +1044,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
-  h->t2_factor = 1000.0;
+  h->t2_factor = 0.0;       // one-term tiles off: measured share of such tiles 0.4 - 6 % (rows restart inside late tiles), no gain
   h->tile_stat = nullptr;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = h->tot_qps_active = h->tot_active = 0;
   h->kappa0 = 0.25 * qp->p_norm_inf;
