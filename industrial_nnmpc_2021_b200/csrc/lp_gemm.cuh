@@ -54,8 +54,11 @@ struct EpiRowInfo {
   int pw;           // operand row written for it
   double inv_in, s_out, inv_out;
 };
+// leading dimension of the staging block: bank-conflict-free both for the writes (one column, 32 consecutive rows)
+// and for the epilogue's reads (lane = (row group, column pair), see EpiDelta)
+constexpr int STG_LD = CW == 16 ? 34 : 36;
 struct EpiWarpSmem {
-  float stg[CW * 33];
+  float stg[CW * STG_LD];
   EpiRowInfo info[32];
 };
 constexpr int EPI_SMEM_BYTES = EPI_WARPS * (int)sizeof(EpiWarpSmem);

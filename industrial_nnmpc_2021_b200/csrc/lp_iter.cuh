@@ -63,10 +63,12 @@ __device__ __forceinline__ __half quantise_dw_fast(double dw, double s, double i
 }
 
 // ---- epilogue of the tensor-core pass: the whole iteration on the accumulator registers ----------
-// Warp-collective (see lp_gemm.cuh): the warp owns 32 rows; TMEM hands lane l the 16 accumulators of row l, the
-// block is transposed through shared memory, and lane (rg = l / 4, cp = l % 4) then updates rows rg, rg + 8,
-// rg + 16, rg + 24 at columns {2cp, 2cp + 1} (and {8 + 2cp, 9 + 2cp} with 16-column steps): every global access of the FP64 state is a
-// 64-byte run per row, whole 32-byte sectors, all loads of a step in flight before the first use.
+// Warp-collective (see lp_gemm.cuh): the warp owns 32 rows; TMEM hands lane l the CW accumulators of row l, the
+// block is transposed through shared memory, and lane (rg = l / LPR, cp = l % LPR), LPR = CW / 2 lanes per row,
+// then updates the column pair {2cp, 2cp + 1} of rows rg, rg + RG, rg + 2 RG, ... (RG = 32 / LPR rows per
+// instruction).  With CW = 16 one warp instruction touches 4 rows x one full 128-byte line of FP64 state each (round
+// 1 touched 8 rows x 64 bytes: twice the L1 wavefronts per request - the LSU data pipe ran at 45 %), every access is
+// whole 32-byte sectors, and all loads of a step are in flight before the first use.
 struct EpiDelta {
   struct Params {
     double* X;
@@ -87,12 +89,15 @@ struct EpiDelta {
     double alpha;
     double inv_sT;       // 1 / operator scale
   };
+  static constexpr int LPR = lp::CW / 2;     // lanes per row
+  static constexpr int RG = 32 / LPR;        // rows per warp instruction
+  static constexpr int NI = 32 / RG;         // row iterations = column pairs per lane
   Params p;
   lp::EpiWarpSmem* sm;
   int lane, rg, cp;
-  double dmax[4];
+  double dmax[NI];
   __device__ EpiDelta(const Params& p_, lp::EpiWarpSmem* sm_, int lane_)
-      : p(p_), sm(sm_), lane(lane_), rg(lane_ >> 2), cp(lane_ & 3) {}
+      : p(p_), sm(sm_), lane(lane_), rg(lane_ / LPR), cp(lane_ % LPR) {}
   __device__ void begin_tile(int pos0, int M) {
     const int pos = pos0 + lane;
     lp::EpiRowInfo ri;
@@ -109,7 +114,8 @@ struct EpiDelta {
     }
     __syncwarp();            // the previous tile's last reads of info[] are done
     sm->info[lane] = ri;
-    dmax[0] = dmax[1] = dmax[2] = dmax[3] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) dmax[i] = 0.0;
     __syncwarp();
   }
   // one column pair of one row
@@ -130,79 +136,59 @@ struct EpiDelta {
     dm = (a <= dm) ? dm : a;
   }
   __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
-    constexpr int NP = lp::CW / 8;     // column pairs per row and lane
-    // transpose: stg[c][r] (stride 33: conflict-free writes)
+    // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
 #pragma unroll
-    for (int c = 0; c < lp::CW; ++c) sm->stg[c * 33 + lane] = __uint_as_float(acc[c]);
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
     __syncwarp();
-    // stage width a multiple of the chunk width: the chunk (col0 is a multiple of CW) lies inside one stage, so the
-    // bound index of the lane's first pair is taken once and the others are constant offsets
-    const bool fast = (p.nu % lp::CW) == 0;
-    const int cbase = col0 + 2 * cp;                           // this lane's first column; n is even: a pair is inside when its first column is
-    const int kbase = cbase % p.nu;
-    double2 x[4 * NP], v[4 * NP];
-    float2 e[4 * NP];
+    const int cbase = col0 + 2 * cp;       // this lane's column pair; n is even: the pair is inside when its first column is
+    const bool in = cbase < N;
+    // the chunk (col0 is a multiple of CW) lies inside one stage when the stage width is a multiple of CW
+    const int k0 = cbase % p.nu;
+    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;
+    double2 x[NI], v[NI];
+    float2 e[NI];
     // all state loads of the step first (streaming: read once per pass)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = sm->info[rg + 8 * i].row;
-      if (row >= 0) {
+    for (int i = 0; i < NI; ++i) {
+      const int row = sm->info[rg + RG * i].row;
+      if (row >= 0 && in) {
         const long long base = (long long)row * p.n + cbase;
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          if (cbase + 8 * j < N) {
-            x[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.X + base + 8 * j));
-            v[NP * i + j] = __ldcs(reinterpret_cast<const double2*>(p.V + base + 8 * j));
-            e[NP * i + j] = __ldcs(reinterpret_cast<const float2*>(p.E + base + 8 * j));
-          }
-        }
+        x[i] = __ldcs(reinterpret_cast<const double2*>(p.X + base));
+        v[i] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
+        e[i] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rg + 8 * i;
+    for (int i = 0; i < NI; ++i) {
+      const int r = rg + RG * i;
       const lp::EpiRowInfo ri = sm->info[r];
-      if (ri.row >= 0) {
+      if (ri.row >= 0 && in) {
         const long long base = (long long)ri.row * p.n + cbase;
         const double* lbr = p.lb + (long long)ri.row * p.nu;
         const double* ubr = p.ub + (long long)ri.row * p.nu;
-        __half* dn = p.Dn + (long long)ri.pw * p.ldd + cbase;
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          if (cbase + 8 * j < N) {
-            double2 l, u;
-            if (fast) {
-              l = *reinterpret_cast<const double2*>(lbr + kbase + 8 * j);
-              u = *reinterpret_cast<const double2*>(ubr + kbase + 8 * j);
-            } else {
-              const int k = (cbase + 8 * j) % p.nu;
-              const int k1 = (k + 1 == p.nu) ? 0 : k + 1;
-              l = make_double2(lbr[k], lbr[k1]);
-              u = make_double2(ubr[k], ubr[k1]);
-            }
-            __half2 q;
-            pair(x[NP * i + j], v[NP * i + j], e[NP * i + j], sm->stg[(8 * j + 2 * cp) * 33 + r],
-                 sm->stg[(8 * j + 2 * cp + 1) * 33 + r], l, u, ri, q, dmax[i]);
-            __stcs(reinterpret_cast<double2*>(p.X + base + 8 * j), x[NP * i + j]);
-            __stcs(reinterpret_cast<double2*>(p.V + base + 8 * j), v[NP * i + j]);
-            __stcs(reinterpret_cast<float2*>(p.E + base + 8 * j), e[NP * i + j]);
-            *reinterpret_cast<__half2*>(dn + 8 * j) = q;
-          }
-        }
+        const double2 l = make_double2(lbr[k0], lbr[k1]);      // k1 wraps to stage input 0 when nu is odd
+        const double2 u = make_double2(ubr[k0], ubr[k1]);
+        __half2 q;
+        pair(x[i], v[i], e[i], sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], l, u, ri, q, dmax[i]);
+        __stcs(reinterpret_cast<double2*>(p.X + base), x[i]);
+        __stcs(reinterpret_cast<double2*>(p.V + base), v[i]);
+        __stcs(reinterpret_cast<float2*>(p.E + base), e[i]);
+        *reinterpret_cast<__half2*>(p.Dn + (long long)ri.pw * p.ldd + cbase) = q;
       }
     }
     __syncwarp();            // stg is rewritten by the next step
   }
   __device__ void end_tile() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NI; ++i) {
       double m = dmax[i];
-      // the 4 lanes of a row group hold disjoint columns of the same rows; NaN must survive the reduction
-      double o = __shfl_xor_sync(0xffffffffu, m, 1);
-      m = (o <= m) ? m : o;
-      o = __shfl_xor_sync(0xffffffffu, m, 2);
-      m = (o <= m) ? m : o;
-      const int row = sm->info[rg + 8 * i].row;
+      // the LPR lanes of a row group hold disjoint columns of the same rows; NaN must survive the reduction
+#pragma unroll
+      for (int o = 1; o < LPR; o <<= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = (t <= m) ? m : t;
+      }
+      const int row = sm->info[rg + RG * i].row;
       if (cp == 0 && row >= 0) {
         if (!(m <= 1.7e308)) m = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
         atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(m));
