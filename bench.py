@@ -1042,10 +1042,13 @@ def main():
     ap.add_argument("--gain-norm", type=float, default=None,
                     help="conditioning study: steady-state gain-row norm of the synthetic plant (default plants/cdu.py: 0.7)")
     ap.add_argument("--r-weight", type=float, default=None, help="conditioning study: R = r I (reference tuning: 0.1)")
-    ap.add_argument("--max-iter", type=int, default=3000, help="per-QP iteration cap (a hit rejects the number)")
+    ap.add_argument("--max-iter", type=int, default=None,
+                    help="per-QP iteration cap (a hit rejects the number); default 3000 (CDU closed loop) / 20000 (cold CSTR QPs)")
     args = ap.parse_args()
     if args.traj is None:
         args.traj = 16384 if args.workload == "horizon_sweep" else 65536
+    if args.max_iter is None:
+        args.max_iter = 20000 if args.workload == "cstr_qp_1m" else 3000
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("cdu_closed_loop", "horizon_sweep"):

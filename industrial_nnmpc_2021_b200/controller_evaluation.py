@@ -220,8 +220,9 @@ class BatchedOnlineSimulation:
         iters = torch.zeros((S_, T), dtype=torch.int32, device=dev)
         kkt = torch.zeros((S_, T), **f64)
         d = lambda a: _lib.dptr(a, device=self._dev)
-        rc = L.nnmpc_online_run(self._handle, self.KINDS[self.kind], S_, T, d(x_io), d(xhat_io), d(up_io), d(t_(sp)),
-                                d(t_(ds)), d(t_(noise)), d(y), d(out["u"]), d(out["x"]), d(out["xhat"]), d(out["xs"]),
+        sp_d, ds_d, noise_d = t_(sp), t_(ds), t_(noise)       # named: the device copies must outlive the call
+        rc = L.nnmpc_online_run(self._handle, self.KINDS[self.kind], S_, T, d(x_io), d(xhat_io), d(up_io), d(sp_d),
+                                d(ds_d), d(noise_d), d(y), d(out["u"]), d(out["x"]), d(out["xhat"]), d(out["xs"]),
                                 d(out["us"]), d(out["average_stage_costs"]), _lib.dptr_i32(iters, self._dev), d(kkt),
                                 float(tol), int(max_iter), _lib.stream_ptr(self._dev))
         hit = _lib.check(rc, "nnmpc_online_run")

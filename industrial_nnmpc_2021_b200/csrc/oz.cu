@@ -255,9 +255,10 @@ int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long 
   NNMPC_TRY(oz_rows_ensure(r, M, W->ncols, st, 4));
   NNMPC_TRY(oz_slice_rows(r, nullptr, nullptr, M, A, lda, st));
   const oz::OzShape g = oz_shape(W, r, M, nullptr);
-  cudaError_t e = oz::launch_oz_gemm2<0, 3, 128, OzEpiDense>(r->tm, W->tm128, oz::OzShape2{g, nullptr, 0, 0},
-                                                             OzEpiDense::Params{out, ldo, bias, relu},
-                                                             device_sm_count(device), st);
+  // 64-column tiles: the 4-level window then fits TMEM twice and the accumulators are double buffered
+  cudaError_t e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDense>(r->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
+                                                            OzEpiDense::Params{out, ldo, bias, relu},
+                                                            device_sm_count(device), st);
   count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));
   return 0;

@@ -298,6 +298,10 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // (measured: 29 % tensor-pipe activity for window 0..3 against 54 % for window 4..7).
   constexpr int NSB = LHI + 1;                          // operator slices this window uses
   constexpr bool DB = 2 * NSB <= NS_MAX;
+  // A window that fits TMEM twice (e.g. levels 0..3 at 64 columns: 256 of 512) double buffers the accumulators, so
+  // the level-folding epilogue of a tile overlaps the products of the next one - what matters when the contraction
+  // is short (structured-network layers: K = 568 .. 1024, 5 - 8 k-blocks per tile).
+  constexpr int ACC = (2 * NL * BN <= TMEM_COLS) ? 2 : 1;
   auto b_slot = [](int j, uint32_t kbc) -> int { return DB ? (int)(kbc & 1u) * NSB + j : j; };
   auto b_par = [](uint32_t kbc) -> uint32_t { return DB ? (kbc >> 1) & 1u : kbc & 1u; };
   const OzShape& g = g2.s;
@@ -310,9 +314,9 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* a_empty = a_full + T::A_SLOTS;      // [A_SLOTS]
   uint64_t* b_full = a_empty + T::A_SLOTS;      // [NS_MAX]
   uint64_t* b_empty = b_full + NS_MAX;          // [NS_MAX]
-  uint64_t* acc_full = b_empty + NS_MAX;        // [1]
-  uint64_t* acc_empty = acc_full + 1;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* acc_full = b_empty + NS_MAX;        // [ACC]
+  uint64_t* acc_empty = acc_full + 2;           // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
@@ -331,8 +335,10 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       lp::mbar_init(b_full + s, 1);
       lp::mbar_init(b_empty + s, 1);
     }
-    lp::mbar_init(acc_full, 1);
-    lp::mbar_init(acc_empty, EPI_WARPS2);
+    for (int s = 0; s < ACC; ++s) {
+      lp::mbar_init(acc_full + s, 1);
+      lp::mbar_init(acc_empty + s, EPI_WARPS2);
+    }
     lp::fence_barrier_init();
   }
   if (warp == 1) lp::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -379,11 +385,13 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t idesc = make_idesc_i8(BM, BN);
     const bool issue = lane == 0;
     int as = 0;
-    uint32_t aph = 0, kbc = 0, tph = 0;
+    uint32_t aph = 0, kbc = 0, ti = 0;
     const uint64_t da_base = lp::make_sw128_kmajor_desc(lp::smem_u32(a_ring));
     const uint64_t db_base = lp::make_sw128_kmajor_desc(lp::smem_u32(b_slots));
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      lp::mbar_wait(acc_empty, tph ^ 1);
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++ti) {
+      const uint32_t acs = ACC == 2 ? (ti & 1u) : 0u;                       // accumulator stage of this tile
+      const uint32_t tph = ACC == 2 ? (ti >> 1) & 1u : ti & 1u;             // its phase
+      lp::mbar_wait(acc_empty + acs, tph ^ 1);
       lp::tc_fence_after();
       for (int kb = 0; kb < g.KB; ++kb, ++kbc) {
         const uint32_t first = kb ? 1u : 0u;
@@ -401,7 +409,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               lp::tc_fence_after();
             }
             const uint64_t db = db_base + (uint64_t)((sbase + j) * (T::B_TILE >> 4));
-            const uint32_t tacc = tmem_base + (uint32_t)((i + j - LLO) * BN);
+            const uint32_t tacc = tmem_base + (uint32_t)((acs * NL + (i + j - LLO)) * BN);
             if (issue) {
               // every level of the window is first written by sample slice 0, step 0 of the tile's first k-block
               umma_i8(tacc, da, db, idesc, i == 0 ? first : 1u);
@@ -418,9 +426,8 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++as == T::A_SLOTS) { as = 0; aph ^= 1; }
         }
       }
-      if (issue) lp::umma_commit(acc_full);
+      if (issue) lp::umma_commit(acc_full + acs);
       __syncwarp();
-      tph ^= 1;
     }
   } else {
     // ===== epilogue warps =====
@@ -428,19 +435,21 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int hsel = (warp - 2) >> 2;             // which half of the tile's column chunks it folds
     constexpr int CHUNKS = BN / CH / 2;
     Epi epi(ep);
-    uint32_t tph = 0;
+    uint32_t ti = 0;
     // 128^-(LLO+1) as a compile-time power of two
     const double lev0 = __longlong_as_double((long long)(1023 - 7 * (LLO + 1)) << 52);
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++ti) {
+      const uint32_t acs = ACC == 2 ? (ti & 1u) : 0u;
+      const uint32_t tph = ACC == 2 ? (ti >> 1) & 1u : ti & 1u;
       int bm, bn;
       oz_tile_coords(t, ntm, ntn, g.group_rows, bm, bn);
       const int pos = bm * BM + q * 32 + lane;
       const bool rok = pos < M;
       const double fs = rok ? g.fscale[pos] : 0.0;
       epi.begin_row(pos, rok);
-      lp::mbar_wait(acc_full, tph);
+      lp::mbar_wait(acc_full + acs, tph);
       lp::tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * NL * BN);
 #pragma unroll 1
       for (int c = hsel * CHUNKS; c < (hsel + 1) * CHUNKS; ++c) {
         double v[CH];
@@ -467,8 +476,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       epi.end_row();
       lp::tc_fence_before();
       __syncwarp();
-      if (lane == 0) lp::mbar_arrive(acc_empty);
-      tph ^= 1;
+      if (lane == 0) lp::mbar_arrive(acc_empty + acs);
     }
   }
 
