@@ -157,7 +157,10 @@ int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st, int ns)
 
 static int oz_slice_rows(OzRows* r, const int* rows, const int* count, int max_rows, const double* src, long long ld_src,
                          cudaStream_t st) {
-  if (r->ns == 4)
+  if (r->ns == 4 && !rows && !count && r->ncols <= 4096)      // dense list of short rows: one warp per row
+    oz::k_oz_slice_warp<4><<<row_grid((max_rows + 7) / 8), 256, 0, st>>>(src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
+                                                                         r->fscale.p, max_rows);
+  else if (r->ns == 4)
     oz::k_oz_slice<4><<<row_grid(max_rows), 256, 0, st>>>(rows, count, src, ld_src, r->ncols, r->S.p, r->cap_pad, r->ldb,
                                                           r->fscale.p, max_rows);
   else

@@ -453,21 +453,44 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int c = hsel * CHUNKS; c < (hsel + 1) * CHUNKS; ++c) {
         double v[CH];
+        if constexpr (NL <= 4) {
+          // Fold the levels in 64-bit INTEGER arithmetic (exact: |acc_L| < 2^31, three shifts by 7 bits stay below
+          // 2^53) and convert once: one I2F + one multiply per element on the FP64 pipe instead of a convert, an add
+          // and a multiply per LEVEL.  The FP64 ALU (64 FMA/clk/SM on B200) is what the epilogue of a short
+          // contraction is bound by.
+          long long sacc[CH];
 #pragma unroll
-        for (int k = 0; k < CH; ++k) v[k] = 0.0;
+          for (int k = 0; k < CH; ++k) sacc[k] = 0;
 #pragma unroll
-        for (int L = NL - 1; L >= 0; --L) {
-          uint32_t acc[CH];
-          lp::tmem_ld_32x16(trow + (uint32_t)(L * BN + c * CH), acc);
-          lp::tmem_ld_wait();
+          for (int L = 0; L < NL; ++L) {
+            uint32_t acc[CH];
+            lp::tmem_ld_32x16(trow + (uint32_t)(L * BN + c * CH), acc);
+            lp::tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < CH; ++k) v[k] = (v[k] + (double)(int)acc[k]) * 0.0078125;
+            for (int k = 0; k < CH; ++k) sacc[k] = sacc[k] * 128 + (long long)(int)acc[k];
+          }
+          // sum_L acc_L 128^(NL-1-L) x 128^-NL x 128^-(LLO+1) = sum_L acc_L 128^-(L+LLO+2)
+          const double wnl = __longlong_as_double((long long)(1023 - 7 * (NL + LLO + 1)) << 52);
+#pragma unroll
+          for (int k = 0; k < CH; ++k) v[k] = (double)sacc[k] * wnl;
+        } else {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) v[k] = 0.0;
+#pragma unroll
+          for (int L = NL - 1; L >= 0; --L) {
+            uint32_t acc[CH];
+            lp::tmem_ld_32x16(trow + (uint32_t)(L * BN + c * CH), acc);
+            lp::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < CH; ++k) v[k] = (v[k] + (double)(int)acc[k]) * 0.0078125;
+          }
+#pragma unroll
+          for (int k = 0; k < CH; ++k) v[k] *= lev0;                 // sum_L acc_L 128^-(L+2)
         }
         const int col0 = bn * BN + c * CH;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
           const int col = col0 + k;
-          v[k] *= lev0;                                              // sum_L acc_L 128^-(L+2)
           if (g2.partial_in && rok && col < g.N) v[k] += g2.partial_in[(long long)pos * g2.ldp + col];
           if (!g2.raw_out) v[k] *= fs * (col < g.N ? g.escale[col] : 0.0);
         }
@@ -553,6 +576,63 @@ k_oz_slice(const int* __restrict__ rows, const int* __restrict__ count, const do
     }
     if (threadIdx.x == 0)
       scale_out[p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
+  }
+}
+
+// Same for SHORT rows (structured-network activations, K ~ 10^3): one warp per row, 8 rows per CTA, no block-wide
+// synchronisation; every lane cuts 4 consecutive numbers per step and stores a char4 per digit plane.
+template <int NS>
+__global__ void __launch_bounds__(256)
+k_oz_slice_warp(const double* __restrict__ src, long long ld_src, int ncols, int8_t* __restrict__ dst, long long rows_pad,
+                long long ldb, double* __restrict__ scale_out, long long nrows) {
+  const int lane = threadIdx.x & 31;
+  const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < nrows; p += wpg) {
+    const double* a = src + p * ld_src;
+    double m = 0.0;
+    for (int k = lane; k < ncols; k += 32) {
+      const double b = fabs(a[k]);
+      m = (b <= m) ? m : b;            // NaN propagates
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double b = __shfl_xor_sync(0xffffffffu, m, o);
+      m = (b <= m) ? m : b;
+    }
+    const bool bad = !(m <= 1.7e308);
+    int ex = 0;
+    if (!bad && m > 0.0) frexp(m, &ex);
+    const double inv = bad ? 0.0 : ldexp(1.0, -(ex + 1));
+    const int n4 = ncols & ~3;
+    for (int k = 4 * lane; k < n4; k += 128) {
+      double t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t[e] = bad ? 0.0 : a[k + e] * inv;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        char4 d;
+        int8_t* dd = reinterpret_cast<int8_t*>(&d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          t[e] *= 128.0;
+          const double r = rint(t[e]);
+          t[e] -= r;
+          dd[e] = (int8_t)(int)r;
+        }
+        *reinterpret_cast<char4*>(dst + ((long long)s * rows_pad + p) * ldb + k) = d;
+      }
+    }
+    for (int k = n4 + lane; k < ncols; k += 32) {
+      double t = bad ? 0.0 : a[k] * inv;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        t *= 128.0;
+        const double r = rint(t);
+        t -= r;
+        dst[((long long)s * rows_pad + p) * ldb + k] = (int8_t)(int)r;
+      }
+    }
+    if (lane == 0) scale_out[p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
   }
 }
 
