@@ -163,30 +163,32 @@ __global__ void k_struct_out(const double* __restrict__ f, const double* __restr
   }
 }
 
-// INT8 tensor-core forward: every layer = slice the FP64 activations into digit planes + one exact-accumulation GEMM
+// INT8 tensor-core forward: the activations only ever exist as digit planes - the first-layer operand is cut from the
+// inputs (exact row maximum), every hidden layer's epilogue cuts relu(. + bias) into the planes the next layer reads
+// (scaled from a bound of the row), the last layer hands f of both passes to the output assembly
 static int mlp_forward_i8(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
                           const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
                           cudaStream_t st) {
   if (B <= 0) return 0;
+  const int nx = h->nx, nu = h->nu, L = h->L;
   long long chunk = (long long)(1ll << 28) / (2ll * h->maxw);
   chunk = chunk < 1024 ? 1024 : (chunk > (1 << 18) ? (1 << 18) : chunk);
   if (chunk > B) chunk = B;
-  NNMPC_TRY(h->act0.ensure((size_t)2 * chunk * h->maxw));
-  NNMPC_TRY(h->act1.ensure((size_t)2 * chunk * h->maxw));
-  NNMPC_TRY(h->fout.ensure((size_t)2 * chunk * h->nu));
-  const int nx = h->nx, nu = h->nu, L = h->L;
+  for (int l = 0; l < L; ++l) NNMPC_TRY(oz_rows_ensure(&h->ozA[l], 2 * chunk, h->dims[l], st, 4));
+  NNMPC_TRY(h->fout.ensure((size_t)2 * chunk * nu));
+  for (int b = 0; b < 2; ++b) NNMPC_TRY(h->tcamax[b].ensure((size_t)2 * chunk));
   for (long long b0 = 0; b0 < B; b0 += chunk) {
     const long long nb = B - b0 < chunk ? B - b0 : chunk;
-    k_pack_inputs<<<148 * 16, 256, 0, st>>>(x + b0 * nx, uprev ? uprev + b0 * nu : nullptr, xs + b0 * nx,
-                                            us + b0 * nu, xscale, h->act0.p, nb, nx, nu, h->with_uprev, h->ld[0]);
-    count_launch();
-    double* cur = h->act0.p;
-    double* nxt = h->act1.p;
+    const int M = (int)(2 * nb);
+    NNMPC_TRY(oz_pack_network_input(&h->ozA[0], nb, x + b0 * nx, uprev ? uprev + b0 * nu : nullptr, xs + b0 * nx, us + b0 * nu,
+                                    xscale, nx, nu, h->with_uprev, h->tcamax[0].p, st));
     for (int l = 0; l < L; ++l) {
       const bool last = l == L - 1;
-      NNMPC_TRY(oz_dense_layer(&h->ozW[l], &h->ozA[l], (int)(2 * nb), cur, h->ld[l], last ? nullptr : h->bias[l], last ? 0 : 1,
-                               last ? h->fout.p : nxt, last ? nu : h->ld[l + 1], h->device, st));
-      double* t = cur; cur = nxt; nxt = t;
+      const int in = l & 1, on = in ^ 1;
+      if (!last) NNMPC_CUDA(cudaMemsetAsync(h->tcamax[on].p, 0, (size_t)M * sizeof(float), st));
+      NNMPC_TRY(oz_dense_planes(&h->ozW[l], &h->ozA[l], M, last ? nullptr : h->bias[l], last ? nullptr : &h->ozA[l + 1],
+                                h->tcamax[in].p, last ? nullptr : h->tcamax[on].p, h->tcl[l].w1norm, h->tcl[l].bmax,
+                                last ? h->fout.p : nullptr, nu, h->device, st));
     }
     k_struct_out<<<148 * 4, 256, 0, st>>>(h->fout.p, us + b0 * nu, ulb, uub, out + b0 * nu, nb, nu);
     count_launch();

@@ -267,6 +267,167 @@ int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long 
   return 0;
 }
 
+// hidden layer writing the next layer's digit planes
+struct OzEpiDensePlanes {
+  struct Params {
+    int8_t* planes;        // 4 planes: [(s * rows_pad + pos) * ldb + col]
+    long long rows_pad, ldb;
+    const double* bias;
+    const float* amax_in;
+    float* amax_out;
+    double* fscale_out;
+    double w1norm, bmax;
+  };
+  Params p;
+  long long pos;
+  double inv;
+  float hmax;
+  __device__ explicit OzEpiDensePlanes(const Params& p_) : p(p_), pos(0), inv(0.0), hmax(0.f) {}
+  __device__ void begin_row(int pos_, bool ok) {
+    pos = pos_;
+    hmax = 0.f;
+    inv = 0.0;
+    if (ok) {
+      const double bound = (double)p.amax_in[pos] * p.w1norm + p.bmax;
+      int ex = 0;
+      if (bound > 0.0 && bound <= 1.7e308) frexp(bound, &ex);      // bound <= 2^ex = 2^(f-1)
+      inv = ldexp(1.0, -(ex + 1));
+      p.fscale_out[pos] = (bound <= 1.7e308) ? ldexp(1.0, ex + 1) : __longlong_as_double(0x7ff8000000000000ll);
+    }
+  }
+  __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+    double t[oz::CH];
+#pragma unroll
+    for (int k = 0; k < oz::CH; ++k) {
+      double h = 0.0;
+      if (col0 + k < N) {
+        h = v[k] + __ldg(p.bias + col0 + k);
+        h = h > 0.0 ? h : 0.0;
+        hmax = fmaxf(hmax, (float)h * 1.0000002f);
+      }
+      t[k] = h * inv;                                             // |t| <= 1/2
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      __align__(16) int8_t d[oz::CH];
+#pragma unroll
+      for (int k = 0; k < oz::CH; ++k) {
+        t[k] *= 128.0;
+        const double r = rint(t[k]);
+        t[k] -= r;
+        d[k] = (int8_t)(int)r;
+      }
+      *reinterpret_cast<uint4*>(p.planes + ((long long)s * p.rows_pad + pos) * p.ldb + col0) = *reinterpret_cast<const uint4*>(d);
+    }
+  }
+  __device__ void end_row() {
+    atomicMax(reinterpret_cast<unsigned int*>(p.amax_out + pos), __float_as_uint(hmax));
+  }
+};
+
+int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias, OzRows* rout, const float* amax_in,
+                    float* amax_out, double w1norm, double bmax, double* out, long long ldo, int device, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (!W->ready || rin->ns != 4 || rin->ncols != W->ncols || M > rin->cap_pad)
+    return set_error(NNMPC_ERR_BADARG, "oz_dense_planes: operands not prepared");
+  const oz::OzShape g = oz_shape(W, rin, M, nullptr);
+  cudaError_t e;
+  if (out) {
+    e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDense>(rin->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
+                                                  OzEpiDense::Params{out, ldo, bias, 0}, device_sm_count(device), st);
+  } else {
+    if (rout->ns != 4 || rout->ncols != W->nrows || M > rout->cap_pad)
+      return set_error(NNMPC_ERR_BADARG, "oz_dense_planes: output planes not prepared");
+    e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDensePlanes>(
+        rin->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
+        OzEpiDensePlanes::Params{rout->S.p, rout->cap_pad, rout->ldb, bias, amax_in, amax_out, rout->fscale.p, w1norm, bmax},
+        device_sm_count(device), st);
+  }
+  count_launch();
+  if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_oz_pack_network_input(const double* __restrict__ x, const double* __restrict__ uprev, const double* __restrict__ xs,
+                        const double* __restrict__ us, const double* __restrict__ xscale, int8_t* __restrict__ dst,
+                        long long rows_pad, long long ldb, double* __restrict__ fscale, float* __restrict__ amax, long long B,
+                        int nx, int nu, int with_uprev) {
+  const int lane = threadIdx.x & 31;
+  const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
+  const int o1 = nx, o2 = nx + (with_uprev ? nu : 0), o3 = o2 + nx, o4 = o3 + nu;
+  for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += wpg) {
+    auto value = [&](int c, double& v1, double& v2) {
+      if (c < o1) {
+        v1 = x[b * nx + c];
+        v2 = xs[b * nx + c];
+        if (xscale) { v1 /= xscale[c]; v2 /= xscale[c]; }
+      } else if (c < o2) {
+        v1 = uprev[b * nu + (c - o1)];
+        v2 = us[b * nu + (c - o1)];
+      } else if (c < o3) {
+        v1 = xs[b * nx + (c - o2)];
+        if (xscale) v1 /= xscale[c - o2];
+        v2 = v1;
+      } else {
+        v1 = v2 = us[b * nu + (c - o3)];
+      }
+    };
+    double m1 = 0.0, m2 = 0.0;
+    for (int c = lane; c < o4; c += 32) {
+      double v1, v2;
+      value(c, v1, v2);
+      const double a1 = fabs(v1), a2 = fabs(v2);
+      m1 = (a1 <= m1) ? m1 : a1;       // NaN propagates
+      m2 = (a2 <= m2) ? m2 : a2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a1 = __shfl_xor_sync(0xffffffffu, m1, o), a2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      m1 = (a1 <= m1) ? m1 : a1;
+      m2 = (a2 <= m2) ? m2 : a2;
+    }
+    double inv[2], fs[2];
+    const double mm[2] = {m1, m2};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const bool bad = !(mm[r] <= 1.7e308);
+      int ex = 0;
+      if (!bad && mm[r] > 0.0) frexp(mm[r], &ex);
+      inv[r] = bad ? 0.0 : ldexp(1.0, -(ex + 1));
+      fs[r] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
+    }
+    for (int c = lane; c < o4; c += 32) {
+      double v1, v2;
+      value(c, v1, v2);
+      double t1 = v1 * inv[0], t2 = v2 * inv[1];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        t1 *= 128.0; t2 *= 128.0;
+        const double r1 = rint(t1), r2 = rint(t2);
+        t1 -= r1; t2 -= r2;
+        dst[((long long)s * rows_pad + 2 * b) * ldb + c] = (int8_t)(int)r1;
+        dst[((long long)s * rows_pad + 2 * b + 1) * ldb + c] = (int8_t)(int)r2;
+      }
+    }
+    if (lane == 0) {
+      fscale[2 * b] = fs[0]; fscale[2 * b + 1] = fs[1];
+      amax[2 * b] = (float)m1 * 1.0000002f; amax[2 * b + 1] = (float)m2 * 1.0000002f;
+    }
+  }
+}
+
+int oz_pack_network_input(OzRows* r, long long B, const double* x, const double* uprev, const double* xs, const double* us,
+                          const double* xscale, int nx, int nu, int with_uprev, float* amax, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (r->ns != 4 || 2 * B > r->cap_pad) return set_error(NNMPC_ERR_BADARG, "oz_pack_network_input: planes not prepared");
+  k_oz_pack_network_input<<<row_grid((B + 7) / 8), 256, 0, st>>>(x, uprev, xs, us, xscale, r->S.p, r->cap_pad, r->ldb, r->fscale.p,
+                                                                 amax, B, nx, nu, with_uprev);
+  count_launch();
+  NNMPC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace nnmpc
 
 using namespace nnmpc;
