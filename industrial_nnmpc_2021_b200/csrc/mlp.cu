@@ -36,6 +36,7 @@ struct nnmpc_mlp {
   nnmpc::OzOperator ozW[16];        // weight digit planes per layer
   nnmpc::OzRows ozA[16];            // activation digit planes per layer (distinct contraction lengths)
   nnmpc::DevBuf<double> fout;       // last layer: f of both passes, 2 B x nu
+  nnmpc::DevBuf<float> hf32;        // hidden activation between a layer's epilogue and the slicing of the next operand
   // split-fp16 tcgen05 mode
   int tc_mode;                      // 1: INT8 tcgen05 layers, 2: split-fp16 tcgen05 layers, 0: FP64 DMMA
   nnmpc::MlpTcLayer tcl[16];
@@ -163,9 +164,9 @@ __global__ void k_struct_out(const double* __restrict__ f, const double* __restr
   }
 }
 
-// INT8 tensor-core forward: the activations only ever exist as digit planes - the first-layer operand is cut from the
-// inputs (exact row maximum), every hidden layer's epilogue cuts relu(. + bias) into the planes the next layer reads
-// (scaled from a bound of the row), the last layer hands f of both passes to the output assembly
+// INT8 tensor-core forward: the first-layer operand is cut into digit planes straight from the inputs, every hidden
+// layer's epilogue writes relu(. + bias) as fp32 with the exact row maximum and one slicing pass cuts the planes the next
+// layer reads, the last layer hands f of both passes to the output assembly.  No FP64 activations in memory.
 static int mlp_forward_i8(nnmpc_mlp* h, long long B, const double* x, const double* uprev, const double* xs,
                           const double* us, const double* xscale, const double* ulb, const double* uub, double* out,
                           cudaStream_t st) {
@@ -177,6 +178,8 @@ static int mlp_forward_i8(nnmpc_mlp* h, long long B, const double* x, const doub
   for (int l = 0; l < L; ++l) NNMPC_TRY(oz_rows_ensure(&h->ozA[l], 2 * chunk, h->dims[l], st, 4));
   NNMPC_TRY(h->fout.ensure((size_t)2 * chunk * nu));
   for (int b = 0; b < 2; ++b) NNMPC_TRY(h->tcamax[b].ensure((size_t)2 * chunk));
+  const long long ldh = ((long long)h->maxw + 63) / 64 * 64;      // fp32 scratch of one hidden activation
+  NNMPC_TRY(h->hf32.ensure((size_t)2 * chunk * ldh));
   for (long long b0 = 0; b0 < B; b0 += chunk) {
     const long long nb = B - b0 < chunk ? B - b0 : chunk;
     const int M = (int)(2 * nb);
@@ -184,11 +187,9 @@ static int mlp_forward_i8(nnmpc_mlp* h, long long B, const double* x, const doub
                                     xscale, nx, nu, h->with_uprev, h->tcamax[0].p, st));
     for (int l = 0; l < L; ++l) {
       const bool last = l == L - 1;
-      const int in = l & 1, on = in ^ 1;
-      if (!last) NNMPC_CUDA(cudaMemsetAsync(h->tcamax[on].p, 0, (size_t)M * sizeof(float), st));
+      if (!last) NNMPC_CUDA(cudaMemsetAsync(h->tcamax[1].p, 0, (size_t)M * sizeof(float), st));
       NNMPC_TRY(oz_dense_planes(&h->ozW[l], &h->ozA[l], M, last ? nullptr : h->bias[l], last ? nullptr : &h->ozA[l + 1],
-                                h->tcamax[in].p, last ? nullptr : h->tcamax[on].p, h->tcl[l].w1norm, h->tcl[l].bmax,
-                                last ? h->fout.p : nullptr, nu, h->device, st));
+                                h->hf32.p, ldh, h->tcamax[1].p, last ? h->fout.p : nullptr, nu, h->device, st));
     }
     k_struct_out<<<148 * 4, 256, 0, st>>>(h->fout.p, us + b0 * nu, ulb, uub, out + b0 * nu, nb, nu);
     count_launch();
@@ -399,6 +400,7 @@ int nnmpc_mlp_destroy(nnmpc_mlp_t* h) {
     h->ozA[l].release();
   }
   h->fout.release();
+  h->hf32.release();
   for (int b = 0; b < 2; ++b) { h->tcA[b].release(); h->tcsc[b].release(); h->tcamax[b].release(); }
   h->act0.release(); h->act1.release();
   h->hx.release(); h->hup.release(); h->hxs.release(); h->hus.release(); h->hout.release();

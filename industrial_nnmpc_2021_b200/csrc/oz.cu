@@ -267,66 +267,83 @@ int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long 
   return 0;
 }
 
-// hidden layer writing the next layer's digit planes
-struct OzEpiDensePlanes {
+// hidden layer: relu(. + bias) as fp32 plus the exact row maximum; k_oz_slice_f32 then cuts the digit planes of the next
+// layer's operand with the EXACT power-of-two scale of each row.  (Cutting the planes right in this epilogue needs the
+// scale before the row is complete, i.e. an a-priori bound max|a| ||W||_1 + max|b|; measured on B200: that bound is
+// ~25x loose on the CDU network, the level-truncation error of the next GEMM scales with it, and the outputs drift to
+// 4.6e-6 of the float64 layer instead of 1.3e-7 - too close to the 1e-5 tolerance.)
+struct OzEpiDenseF32 {
   struct Params {
-    int8_t* planes;        // 4 planes: [(s * rows_pad + pos) * ldb + col]
-    long long rows_pad, ldb;
+    float* H;
+    long long ldh;
     const double* bias;
-    const float* amax_in;
-    float* amax_out;
-    double* fscale_out;
-    double w1norm, bmax;
+    float* amax_out;       // per row: max entry written (atomicMax on the bit pattern; entries are >= 0)
   };
   Params p;
   long long pos;
-  double inv;
   float hmax;
-  __device__ explicit OzEpiDensePlanes(const Params& p_) : p(p_), pos(0), inv(0.0), hmax(0.f) {}
-  __device__ void begin_row(int pos_, bool ok) {
+  __device__ explicit OzEpiDenseF32(const Params& p_) : p(p_), pos(0), hmax(0.f) {}
+  __device__ void begin_row(int pos_, bool) {
     pos = pos_;
     hmax = 0.f;
-    inv = 0.0;
-    if (ok) {
-      const double bound = (double)p.amax_in[pos] * p.w1norm + p.bmax;
-      int ex = 0;
-      if (bound > 0.0 && bound <= 1.7e308) frexp(bound, &ex);      // bound <= 2^ex = 2^(f-1)
-      inv = ldexp(1.0, -(ex + 1));
-      p.fscale_out[pos] = (bound <= 1.7e308) ? ldexp(1.0, ex + 1) : __longlong_as_double(0x7ff8000000000000ll);
-    }
   }
   __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
-    double t[oz::CH];
+    __align__(16) float h[oz::CH];
 #pragma unroll
     for (int k = 0; k < oz::CH; ++k) {
-      double h = 0.0;
+      double t = 0.0;
       if (col0 + k < N) {
-        h = v[k] + __ldg(p.bias + col0 + k);
-        h = h > 0.0 ? h : 0.0;
-        hmax = fmaxf(hmax, (float)h * 1.0000002f);
+        t = v[k] + __ldg(p.bias + col0 + k);
+        t = t > 0.0 ? t : 0.0;
       }
-      t[k] = h * inv;                                             // |t| <= 1/2
+      h[k] = (float)t;
+      hmax = fmaxf(hmax, h[k]);
     }
+    float4* dst = reinterpret_cast<float4*>(p.H + pos * p.ldh + col0);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      __align__(16) int8_t d[oz::CH];
-#pragma unroll
-      for (int k = 0; k < oz::CH; ++k) {
-        t[k] *= 128.0;
-        const double r = rint(t[k]);
-        t[k] -= r;
-        d[k] = (int8_t)(int)r;
-      }
-      *reinterpret_cast<uint4*>(p.planes + ((long long)s * p.rows_pad + pos) * p.ldb + col0) = *reinterpret_cast<const uint4*>(d);
-    }
+    for (int q = 0; q < oz::CH / 4; ++q) dst[q] = reinterpret_cast<const float4*>(h)[q];
   }
   __device__ void end_row() {
     atomicMax(reinterpret_cast<unsigned int*>(p.amax_out + pos), __float_as_uint(hmax));
   }
 };
 
-int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias, OzRows* rout, const float* amax_in,
-                    float* amax_out, double w1norm, double bmax, double* out, long long ldo, int device, cudaStream_t st) {
+// fp32 rows with KNOWN maxima -> 4 digit planes (one warp per row, one pass)
+__global__ void __launch_bounds__(256)
+k_oz_slice_f32(const float* __restrict__ H, long long ldh, int ncols, const float* __restrict__ amax, int8_t* __restrict__ dst,
+               long long rows_pad, long long ldb, double* __restrict__ fscale, long long nrows) {
+  const int lane = threadIdx.x & 31;
+  const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < nrows; p += wpg) {
+    const float* a = H + p * ldh;
+    const double m = (double)amax[p];
+    const bool bad = !(m <= 1.7e308);
+    int ex = 0;
+    if (!bad && m > 0.0) frexp(m, &ex);
+    const double inv = bad ? 0.0 : ldexp(1.0, -(ex + 1));
+    for (int k = 4 * lane; k < ncols; k += 128) {          // ldh and the plane pitch are multiples of 4: whole float4 / char4
+      const float4 f = *reinterpret_cast<const float4*>(a + k);
+      double t[4] = {f.x * inv, f.y * inv, f.z * inv, f.w * inv};
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        char4 d;
+        int8_t* dd = reinterpret_cast<int8_t*>(&d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          t[e] *= 128.0;
+          const double r = rint(t[e]);
+          t[e] -= r;
+          dd[e] = (k + e < ncols) ? (int8_t)(int)r : (int8_t)0;
+        }
+        *reinterpret_cast<char4*>(dst + ((long long)s * rows_pad + p) * ldb + k) = d;
+      }
+    }
+    if (lane == 0) fscale[p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex + 1);
+  }
+}
+
+int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias, OzRows* rout, float* hbuf, long long ldh,
+                    float* amax_out, double* out, long long ldo, int device, cudaStream_t st) {
   if (M <= 0) return 0;
   if (!W->ready || rin->ns != 4 || rin->ncols != W->ncols || M > rin->cap_pad)
     return set_error(NNMPC_ERR_BADARG, "oz_dense_planes: operands not prepared");
@@ -335,15 +352,19 @@ int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias,
   if (out) {
     e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDense>(rin->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
                                                   OzEpiDense::Params{out, ldo, bias, 0}, device_sm_count(device), st);
+    count_launch();
   } else {
-    if (rout->ns != 4 || rout->ncols != W->nrows || M > rout->cap_pad)
-      return set_error(NNMPC_ERR_BADARG, "oz_dense_planes: output planes not prepared");
-    e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDensePlanes>(
-        rin->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
-        OzEpiDensePlanes::Params{rout->S.p, rout->cap_pad, rout->ldb, bias, amax_in, amax_out, rout->fscale.p, w1norm, bmax},
-        device_sm_count(device), st);
+    if (rout->ns != 4 || rout->ncols != W->nrows || M > rout->cap_pad || (ldh & 3) || ldh < ((W->nrows + 63) / 64) * 64)
+      return set_error(NNMPC_ERR_BADARG, "oz_dense_planes: output planes / fp32 scratch not prepared");
+    e = oz::launch_oz_gemm2<0, 3, 64, OzEpiDenseF32>(rin->tm, W->tm, oz::OzShape2{g, nullptr, 0, 0},
+                                                     OzEpiDenseF32::Params{hbuf, ldh, bias, amax_out}, device_sm_count(device), st);
+    if (e == cudaSuccess) {
+      k_oz_slice_f32<<<row_grid((M + 7) / 8), 256, 0, st>>>(hbuf, ldh, W->nrows, amax_out, rout->S.p, rout->cap_pad, rout->ldb,
+                                                            rout->fscale.p, M);
+      e = cudaGetLastError();
+    }
+    count_launch(2);
   }
-  count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));
   return 0;
 }

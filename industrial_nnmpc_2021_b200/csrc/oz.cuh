@@ -40,13 +40,12 @@ int oz_rows_ensure(OzRows* r, long long cap, int ncols, cudaStream_t st, int ns 
 // <= 4 K 2^-30 relative to (row max) x (weight-row max).  W: operator planes from oz_slice_operator (N x K).
 int oz_dense_layer(const OzOperator* W, OzRows* r, int M, const double* A, long long lda, const double* bias, int relu,
                    double* out, long long ldo, int device, cudaStream_t st);
-// The same layer between DIGIT-PLANE operands: reads the planes already in `rin` (scales in rin->fscale), writes
-// relu(. + bias) straight into the planes of `rout` - no FP64 activations in memory.  The row that is written is scaled
-// from an upper bound of its entries, amax_in[row] * w1norm + bmax (amax_in = measured max |entry| of the row that was
-// read, w1norm = max_j sum_i |W_ij|); the measured maximum of what is written goes to amax_out (atomicMax, zeroed by
-// the caller).  out != NULL (last layer): plain FP64 result instead of planes.
-int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias, OzRows* rout, const float* amax_in,
-                    float* amax_out, double w1norm, double bmax, double* out, long long ldo, int device, cudaStream_t st);
+// The same layer between DIGIT-PLANE operands: reads the planes already in `rin` (scales in rin->fscale); the epilogue
+// writes relu(. + bias) as fp32 into hbuf (row pitch ldh floats, a multiple of 4 and >= the width rounded up to 64) and
+// the exact row maxima into amax_out (atomicMax, zeroed by the caller), then one slicing pass cuts the planes of `rout`
+// with exact scales - no FP64 activations in memory.  out != NULL (last layer, no bias / ReLU): plain FP64 result.
+int oz_dense_planes(const OzOperator* W, OzRows* rin, int M, const double* bias, OzRows* rout, float* hbuf, long long ldh,
+                    float* amax_out, double* out, long long ldo, int device, cudaStream_t st);
 // first-layer operand of the structured network straight into digit planes: rows 2b / 2b+1 = [x/s, (uprev), xs/s, us] /
 // [xs/s, (us), xs/s, us] (controller_evaluation.py:863-866), one warp per sample
 int oz_pack_network_input(OzRows* r, long long B, const double* x, const double* uprev, const double* xs, const double* us,
