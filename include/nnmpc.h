@@ -205,6 +205,17 @@ int nnmpc_mlp_destroy(nnmpc_mlp_t* h);
  * output assembly: ~1e-7 of the float64 layer, steady-state identity u = us exact; 0 = FP64 DMMA GEMMs (~1e-13);
  * 2 = split-fp16 tcgen05 GEMMs with fp32 TMEM accumulation (~2e-5: outside the 1e-5 tolerance, comparison only). */
 int nnmpc_mlp_set_precision(nnmpc_mlp_t* h, int mode);
+/* One training step of the structured network as cdu_train.py:24-62 / cstrs_train.py:24-61 fit it with Keras
+ * (optimizer='adam', loss='mean_squared_error'): FP64 forward, loss = mean over B x nu of (us + f(x,..) - f(xs,..) - u)^2,
+ * backward through both network passes, Adam update (Keras: lr_t = lr sqrt(1-beta2^t)/(1-beta1^t),
+ * w -= lr_t m / (sqrt(v) + eps); defaults lr 1e-3, beta 0.9 / 0.999, eps 1e-7) with t = step (1-based).  apply = 0:
+ * forward and loss only (validation).  All pointers device memory, B <= 262144; loss_host (nullable) receives the loss
+ * of THIS batch before the update.  The inference operators are rebuilt lazily before the next forward. */
+int nnmpc_mlp_train_step(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev, const double* xs,
+                         const double* us, const double* u_target, double lr, double beta1, double beta2, double eps,
+                         long long step, int apply, double* loss_host, void* stream);
+/* current weights in Keras get_weights() layout: weights_host[l] (in_l x out_l), biases_host[l] (out_l; NULL for the last) */
+int nnmpc_mlp_get_weights(nnmpc_mlp_t* h, double* const* weights_host, double* const* biases_host);
 /* x,xs dev B x nx; uprev,us dev B x nu (uprev ignored when !with_uprev); out dev B x nu.
  * xscale dev nx or NULL (x/xscale, xs/xscale, :863-866); ulb/uub dev nu or NULL (clip, :888-892). */
 int nnmpc_mlp_forward(nnmpc_mlp_t* h, long long B, const double* x, const double* uprev,

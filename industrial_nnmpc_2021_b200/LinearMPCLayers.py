@@ -62,6 +62,7 @@ class _StructuredRegulatorLayer:
         self._install(ws)
 
     def get_weights(self):
+        self._sync_weights()
         return [w.copy() for w in (self._weights or [])]
 
     def set_weights(self, weights):
@@ -102,6 +103,7 @@ class _StructuredRegulatorLayer:
         _lib.check(L.nnmpc_mlp_set_precision(hnd, self._MODES[self.precision]), "nnmpc_mlp_set_precision")
         self._handle, self._dev = hnd, dev
         self._weights = [np.array(w, dtype=np.float64) for w in weights]
+        self._weights_stale, self._train_steps = False, 0      # a new handle starts with fresh Adam moments
 
     def _free(self):
         if getattr(self, "_handle", None):
@@ -157,6 +159,65 @@ class _StructuredRegulatorLayer:
     def get_config(self):
         return dict(layer_dims=list(self.layer_dims), trainable=self.trainable, name=self.name)
 
+    # -- training (cdu_train.py:24-62: compile(optimizer='adam', loss='mean_squared_error') + fit) ------------------
+    def _train_call(self, inputs, u, step, apply, lr, beta_1, beta_2, epsilon):
+        import torch
+        L = _lib.lib()
+        if self._with_uprev:
+            x, uprev, xs, us = inputs
+        else:
+            (x, xs, us), uprev = inputs, None
+        if self._handle is None:
+            self.build(int(np.shape(x)[1]), int(np.shape(us)[1]))
+        dev = torch.device("cuda", self._dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        t = lambda a: None if a is None else torch.as_tensor(a, **f64).contiguous()
+        xt, upt, xst, ust, ut = t(x), t(uprev), t(xs), t(us), t(u)
+        Bn = xt.shape[0]
+        if tuple(ut.shape) != (Bn, self._nu) or tuple(ust.shape) != (Bn, self._nu) or tuple(xst.shape) != tuple(xt.shape):
+            raise ValueError("x, xs must be (B, Nx); us, u (B, Nu)")
+        loss = C.c_double()
+        dv = self._dev
+        rc = L.nnmpc_mlp_train_step(self._handle, Bn, _lib.dptr(xt, device=dv), _lib.dptr(upt, device=dv),
+                                    _lib.dptr(xst, device=dv), _lib.dptr(ust, device=dv), _lib.dptr(ut, device=dv),
+                                    float(lr), float(beta_1), float(beta_2), float(epsilon), int(step), int(apply),
+                                    C.byref(loss), _lib.stream_ptr(dv))
+        _lib.check(rc, "nnmpc_mlp_train_step")
+        if apply:
+            self._weights_stale = True
+        return loss.value
+
+    def train_on_batch(self, inputs, u, *, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        """One Adam step on the mean-squared error against the MPC inputs ``u`` (Keras defaults).  Returns the loss
+        of the batch before the update, like ``keras.Model.train_on_batch``."""
+        self._train_steps = getattr(self, "_train_steps", 0) + 1
+        return self._train_call(inputs, u, self._train_steps, 1, lr, beta_1, beta_2, epsilon)
+
+    def evaluate(self, inputs, u, batch_size=8192):
+        """Mean-squared error over the whole set (float64 forward)."""
+        n = np.shape(u)[0]
+        tot = 0.0
+        for i in range(0, n, batch_size):
+            sl = slice(i, min(n, i + batch_size))
+            tot += self._train_call([a[sl] for a in inputs], u[sl], 1, 0, 0.0, 0.9, 0.999, 1e-7) * (sl.stop - sl.start)
+        return tot / n
+
+    def _sync_weights(self):
+        """Trained kernels / biases back from the device (Keras get_weights() order)."""
+        if not getattr(self, "_weights_stale", False):
+            return
+        nl = len(self.layer_dims)
+        ws = [np.empty_like(self._weights[2 * i]) for i in range(nl - 1)] + [np.empty_like(self._weights[-1])]
+        bs = [np.empty_like(self._weights[2 * i + 1]) for i in range(nl - 1)]
+        warr = (C.c_void_p * nl)(*[w.ctypes.data for w in ws])
+        barr = (C.c_void_p * nl)(*([b.ctypes.data for b in bs] + [None]))
+        _lib.check(_lib.lib().nnmpc_mlp_get_weights(self._handle, warr, barr), "nnmpc_mlp_get_weights")
+        out = []
+        for i in range(nl - 1):
+            out += [ws[i], bs[i]]
+        self._weights = out + [ws[-1]]
+        self._weights_stale = False
+
 
 class RegulatorLayerWithUprev(_StructuredRegulatorLayer):
     """inputs = [x, uprev, xs, us]  (LinearMPCLayers.py:40-61)."""
@@ -201,3 +262,51 @@ class RegulatorModel:
 
     def set_weights(self, weights):
         self.regulator.set_weights(weights)
+
+    # -- Keras-style training surface used by cdu_train.py / cstrs_train.py (:33-35, :52-57) -----------------------
+    def compile(self, optimizer="adam", loss="mean_squared_error"):
+        if optimizer != "adam" or loss not in ("mean_squared_error", "mse"):
+            raise NotImplementedError("only optimizer='adam', loss='mean_squared_error' (what the reference compiles)")
+        self._compiled = True
+
+    def train_on_batch(self, x, y, **adam):
+        return self.regulator.train_on_batch(x, y[0] if isinstance(y, (list, tuple)) else y, **adam)
+
+    def evaluate(self, x, y, batch_size=8192):
+        return self.regulator.evaluate(x, y[0] if isinstance(y, (list, tuple)) else y, batch_size=batch_size)
+
+    def fit(self, x, y, epochs=1, batch_size=32, validation_split=0.0, shuffle=True, seed=0, restore_best=True,
+            verbose=0):
+        """Minimal ``keras.Model.fit``: the LAST ``validation_split`` fraction of the samples is held out (Keras
+        takes it before shuffling), mini-batches are reshuffled every epoch, and - the reference's ModelCheckpoint
+        with monitor='val_loss', save_best_only=True followed by load_weights (cdu_train.py:44-49, :98) - the
+        weights of the epoch with the best validation loss are restored at the end.  Returns
+        ``{"loss": [...], "val_loss": [...]}``."""
+        y = y[0] if isinstance(y, (list, tuple)) else y
+        x = [np.asarray(a, dtype=np.float64) for a in x]
+        y = np.asarray(y, dtype=np.float64)
+        n = y.shape[0]
+        nval = int(n * validation_split)
+        ntr = n - nval
+        xv, yv = [a[ntr:] for a in x], y[ntr:]
+        rng = np.random.default_rng(seed)
+        hist = {"loss": [], "val_loss": []}
+        best, best_w = np.inf, None
+        for ep in range(epochs):
+            order = rng.permutation(ntr) if shuffle else np.arange(ntr)
+            tot = 0.0
+            for i in range(0, ntr, batch_size):
+                idx = order[i:i + batch_size]
+                tot += self.train_on_batch([a[idx] for a in x], y[idx]) * len(idx)
+            hist["loss"].append(tot / ntr)
+            if nval:
+                vl = self.evaluate(xv, yv)
+                hist["val_loss"].append(vl)
+                if restore_best and vl < best:
+                    best, best_w = vl, self.get_weights()
+            if verbose:
+                print(f"Epoch {ep + 1}/{epochs} - loss: {hist['loss'][-1]:.6e}" +
+                      (f" - val_loss: {hist['val_loss'][-1]:.6e}" if nval else ""))
+        if restore_best and best_w is not None:
+            self.set_weights(best_w)
+        return hist

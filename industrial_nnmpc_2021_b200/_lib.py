@@ -62,6 +62,9 @@ SIGNATURES = {
                                    C.POINTER(vp), C.c_int]),
     "nnmpc_mlp_destroy": (C.c_int, [vp]),
     "nnmpc_mlp_set_precision": (C.c_int, [vp, C.c_int]),
+    "nnmpc_mlp_train_step": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.c_longlong, C.c_int, c_double_p, vp]),
+    "nnmpc_mlp_get_weights": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "nnmpc_mlp_forward": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_mlp_forward_host": (C.c_int, [vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nnmpc_online_create": (C.c_int, [C.POINTER(vp), vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
