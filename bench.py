@@ -598,15 +598,15 @@ def run_cdu(args):
         mma_factor = (t1 + 2.0 * t2) / max(t1 + t2, 1) if (t1 + t2) else 2.0
         # DRAM bytes per launch: a MODEL, not a per-run measurement - two fp16 operator terms read once per pass
         # (2 x 2 n^2 B) plus the per-row state, with the per-row constant taken from the one `ncu --set full` capture of
-        # this kernel (profiles/r01af_ncu_full_lp_gemm.txt: 238.4 kB per row at n = 4480 vs 42 B x n = 188.2 kB
-        # algorithmic), scaled linearly in n
+        # this kernel (profiles/r02h_ncu_full_lp_gemm.txt: 3.72 GB per launch at 16 384 rows, n = 4480 -> 222 kB per row
+        # vs 42 B x n = 188.2 kB algorithmic), scaled linearly in n
         op_bytes = mma_factor * 2.0 * n * n
         r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
                                              "increments x two-term fp16 operator split, fp32 TMEM accumulators, FP64 state)",
                 "achieved": achieved, "executed_mma": mma_factor * achieved, "peak": lp_peak, "unit": "TFLOP/s",
                 "one_term_tile_share": t1 / max(t1 + t2, 1),
                 "frac": achieved / lp_peak, "frac_executed": mma_factor * achieved / lp_peak,
-                "traffic": op_bytes + 238.4e3 * (n / 4480.0) * rows_per_launch,
+                "traffic": op_bytes + 222.0e3 * (n / 4480.0) * rows_per_launch,
                 "traffic_kind": "model scaled from one ncu capture (see bench.py), not measured in this run",
                 "traffic_algorithmic": op_bytes + 42.0 * n * rows_per_launch,
                 "rows_per_launch": rows_per_launch,

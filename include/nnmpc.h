@@ -260,6 +260,9 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
  * operands, exact INT32 accumulation, 36 INT8 products), C[M x N] = A[M x K] Bt[N x K]^T; dense row-major FP64
  * device matrices, K <= 32768. */
 int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, double* C, void* stream);
+/* nnmpc_lp_pass_probe (tools/probes/lp_pass_split.py): one tensor-core pass over B x n synthetic state with the production
+ * epilogue (ms[0]) and with an epilogue that only drains TMEM (ms[1]), averaged over reps launches. */
+int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms);
 /* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,
                   long long ldb, double* C, long long ldc, const int* rows, void* stream);

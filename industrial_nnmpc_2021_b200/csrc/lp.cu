@@ -219,4 +219,104 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
   return rc;
 }
 
+// Probe (tools/probes/lp_pass_split.py, not on the product path): what the tensor-core pass costs with and without its
+// FP64 epilogue.  B rows x n columns of synthetic state, `reps` passes each of
+//   ms[0]  the production kernel (EpiDelta: the whole Douglas-Rachford update on the accumulators)
+//   ms[1]  the same TMA + tcgen05 main loop with an epilogue that only drains TMEM (no state traffic, no FP64)
+// so ms[1] is what the operand supply and the MMA issue can sustain and ms[0] - ms[1] what the epilogue exposes.
+struct EpiLpDrain {
+  struct Params { float* sink; };
+  Params p;
+  float acc;
+  __device__ EpiLpDrain(const Params& p_, lp::EpiWarpSmem*, int) : p(p_), acc(0.f) {}
+  __device__ void begin_tile(int, int) {}
+  __device__ void chunk(int, const uint32_t (&a)[lp::CW], int) {
+#pragma unroll
+    for (int j = 0; j < lp::CW; ++j) acc += __uint_as_float(a[j]);
+  }
+  __device__ void end_tile() {
+    if (acc == 123456.789f) *p.sink = acc;     // keeps the TMEM loads alive
+  }
+};
+
+__global__ void k_probe_fill(double* V, double* X, float* E, __half* D, long long ldd, double* sc, int* state, long long B, int n) {
+  const long long total = B * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    const int c = (int)(i - r * n);
+    const double t = (double)((i * 2654435761ull) % 2001) / 1000.0 - 1.0;
+    V[i] = 0.7 * t; X[i] = 0.6 * t; E[i] = 0.f;
+    D[r * ldd + c] = __double2half(8.0 * t);
+    if (c == 0) { sc[r] = 1024.0; state[r] = 1; }
+  }
+}
+
+int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
+  if (B <= 0 || n <= 0 || (n & 1) || n > B || reps <= 0 || !ms)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_lp_pass_probe: need even n <= B, reps > 0");
+  cudaStream_t st = 0;
+  int dev = 0;
+  NNMPC_CUDA(cudaGetDevice(&dev));
+  DevBuf<double> Top, V, lb, ub, sc;
+  DevBuf<int> state;
+  DevBuf<unsigned long long> dres;
+  DevBuf<float> sink;
+  LpState lps;
+  LpOperator op;
+  int rc = Top.ensure((size_t)n * n);
+  if (rc == 0) rc = V.ensure((size_t)B * n);
+  if (rc == 0) rc = lb.ensure((size_t)B * 32);
+  if (rc == 0) rc = ub.ensure((size_t)B * 32);
+  if (rc == 0) rc = sc.ensure((size_t)B);
+  if (rc == 0) rc = state.ensure((size_t)B);
+  if (rc == 0) rc = dres.ensure((size_t)B);
+  if (rc == 0) rc = sink.ensure(1);
+  if (rc == 0) rc = lp_state_ensure(&lps, B, n, st);
+  if (rc == 0) {
+    k_probe_fill<<<148 * 8, 256, 0, st>>>(Top.p, Top.p, lps.E.p, lps.D[0].p, lps.ldd, sc.p, state.p, n, n);   // any bounded operator
+    k_probe_fill<<<148 * 8, 256, 0, st>>>(V.p, lps.X.p, lps.E.p, lps.D[0].p, lps.ldd, sc.p, state.p, B, n);
+    cudaMemsetAsync(lb.p, 0xc0, (size_t)B * 32 * 8, st);     // -2.0...
+    cudaMemsetAsync(ub.p, 0x40, (size_t)B * 32 * 8, st);     // +2.0...
+    cudaMemsetAsync(dres.p, 0, (size_t)B * 8, st);
+    cudaMemcpyAsync(lps.sc_in.p, sc.p, (size_t)B * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(lps.sc_out.p, sc.p, (size_t)B * 8, cudaMemcpyDeviceToDevice, st);
+    rc = lp_split_operator(Top.p, n, 1.0, &op, st);
+  }
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  if (rc == 0) {
+    const double tile_mb = 2.0 * LpTileN128::BN * (double)op.ldh * 2.0 / 1048576.0;
+    int group_cols = (int)(24.0 / tile_mb);
+    if (group_cols < 1) group_cols = 1;
+    lp::LpShape g{B, n, n, nullptr, group_cols, nullptr, nullptr, 0, 0};
+    EpiDelta::Params ep{};
+    ep.X = lps.X.p; ep.V = V.p; ep.E = lps.E.p; ep.Dn = lps.D[1].p; ep.ldd = lps.ldd; ep.lb = lb.p; ep.ub = ub.p;
+    ep.state = state.p; ep.iter_state = 1; ep.list_r = nullptr; ep.pos_w = nullptr; ep.sc_in = lps.sc_in.p; ep.sc_out = lps.sc_out.p;
+    ep.dres = dres.p; ep.n = n; ep.nu = 32; ep.alpha = 1.8; ep.inv_sT = 1.0 / op.scale;
+    const int sms = device_sm_count(dev);
+    for (int w = 0; w < 2; ++w) {
+      lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g, ep, sms, st);
+      lp::launch_lp_gemm<LpTileN128, EpiLpDrain>(lps.tmD[0], op.tm1, op.tm2, g, EpiLpDrain::Params{sink.p}, sms, st);
+    }
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; ++i) lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g, ep, sms, st);
+    cudaEventRecord(e1, st);
+    for (int i = 0; i < reps; ++i)
+      lp::launch_lp_gemm<LpTileN128, EpiLpDrain>(lps.tmD[0], op.tm1, op.tm2, g, EpiLpDrain::Params{sink.p}, sms, st);
+    cudaEventRecord(e2, st);
+    if (cudaEventSynchronize(e2) != cudaSuccess)
+      rc = set_error(NNMPC_ERR_CUDA, "lp pass probe failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == 0) {
+      cudaEventElapsedTime(&ms[0], e0, e1);
+      cudaEventElapsedTime(&ms[1], e1, e2);
+      ms[0] /= reps; ms[1] /= reps;
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaStreamSynchronize(st);
+  for (DevBuf<double>* b : {&Top, &V, &lb, &ub, &sc}) b->release();
+  state.release(); dres.release(); sink.release(); lps.release(); op.release();
+  return rc;
+}
+
 }  // extern "C"
