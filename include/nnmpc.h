@@ -261,7 +261,8 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
  * device matrices, K <= 32768. */
 int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, double* C, void* stream);
 /* nnmpc_lp_pass_probe (tools/probes/lp_pass_split.py): one tensor-core pass over B x n synthetic state with the production
- * epilogue (ms[0]) and with an epilogue that only drains TMEM (ms[1]), averaged over reps launches. */
+ * epilogue (ms[0]), with an epilogue that only drains TMEM (ms[1]) and with the production epilogue but no TMA loads / MMAs
+ * (ms[2]: the epilogue alone), each averaged over reps launches; ms has room for 3 floats. */
 int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms);
 /* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,

@@ -282,13 +282,15 @@ int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
     cudaMemcpyAsync(lps.sc_out.p, sc.p, (size_t)B * 8, cudaMemcpyDeviceToDevice, st);
     rc = lp_split_operator(Top.p, n, 1.0, &op, st);
   }
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
   if (rc == 0) {
     const double tile_mb = 2.0 * LpTileN128::BN * (double)op.ldh * 2.0 / 1048576.0;
     int group_cols = (int)(24.0 / tile_mb);
     if (group_cols < 1) group_cols = 1;
-    lp::LpShape g{B, n, n, nullptr, group_cols, nullptr, nullptr, 0, 0};
+    lp::LpShape g{B, n, n, nullptr, group_cols, nullptr, nullptr, 0, 0, 0};
+    lp::LpShape g_epi = g;
+    g_epi.skip_mma = 1;
     EpiDelta::Params ep{};
     ep.X = lps.X.p; ep.V = V.p; ep.E = lps.E.p; ep.Dn = lps.D[1].p; ep.ldd = lps.ldd; ep.lb = lb.p; ep.ub = ub.p;
     ep.state = state.p; ep.iter_state = 1; ep.list_r = nullptr; ep.pos_w = nullptr; ep.sc_in = lps.sc_in.p; ep.sc_out = lps.sc_out.p;
@@ -298,21 +300,29 @@ int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
       lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g, ep, sms, st);
       lp::launch_lp_gemm<LpTileN128, EpiLpDrain>(lps.tmD[0], op.tm1, op.tm2, g, EpiLpDrain::Params{sink.p}, sms, st);
     }
+    // NNMPC_PROBE_ONLY = 0 / 1 / 2 runs one of the three phases alone (clock and power sampling from outside)
+    const char* only_s = getenv("NNMPC_PROBE_ONLY");
+    const int only = only_s ? atoi(only_s) : -1;
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; ++i) lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g, ep, sms, st);
+    for (int i = 0; i < reps && (only < 0 || only == 0); ++i)
+      lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g, ep, sms, st);
     cudaEventRecord(e1, st);
-    for (int i = 0; i < reps; ++i)
+    for (int i = 0; i < reps && (only < 0 || only == 1); ++i)
       lp::launch_lp_gemm<LpTileN128, EpiLpDrain>(lps.tmD[0], op.tm1, op.tm2, g, EpiLpDrain::Params{sink.p}, sms, st);
     cudaEventRecord(e2, st);
-    if (cudaEventSynchronize(e2) != cudaSuccess)
+    for (int i = 0; i < reps && (only < 0 || only == 2); ++i)
+      lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g_epi, ep, sms, st);
+    cudaEventRecord(e3, st);
+    if (cudaEventSynchronize(e3) != cudaSuccess)
       rc = set_error(NNMPC_ERR_CUDA, "lp pass probe failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc == 0) {
       cudaEventElapsedTime(&ms[0], e0, e1);
       cudaEventElapsedTime(&ms[1], e1, e2);
-      ms[0] /= reps; ms[1] /= reps;
+      cudaEventElapsedTime(&ms[2], e2, e3);
+      ms[0] /= reps; ms[1] /= reps; ms[2] /= reps;
     }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   cudaStreamSynchronize(st);
   for (DevBuf<double>* b : {&Top, &V, &lb, &ub, &sc}) b->release();
   state.release(); dres.release(); sink.release(); lps.release(); op.release();

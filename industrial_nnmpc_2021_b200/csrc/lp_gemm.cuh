@@ -227,6 +227,9 @@ struct LpShape {
   //     acc = A_hi B1' + A_hi B2' + A_lo B1'      (the 2^-22 term A_lo B2' is never formed).
   int kb2;
   int b_wrap;
+  // Probe only (tools/probes/lp_pass_split.py): 1 = no TMA loads and no MMAs, the accumulators are handed to the
+  // epilogue as they are - the time of the epilogue alone.
+  int skip_mma;
 };
 
 // Tile order of the persistent CTAs.  The operator (2 x n x n fp16, 80 MB at n = 4480) does not fit the part of
@@ -258,13 +261,23 @@ __device__ __forceinline__ void tile_coords(int t, int ntm, int ntn, int group_c
 //     __device__ void chunk(int col0, const uint32_t (&acc)[CW] /*fp32 bit patterns*/, int N);   // CW columns
 //     __device__ void end_tile();
 //   };
+// optional epilogue hook: prefetch(col0, N) - the state the epilogue will read for the chunk at col0 (after begin_tile)
+template <class E>
+__device__ __forceinline__ auto epi_prefetch(E& e, int col0, int N, int) -> decltype(e.prefetch(col0, N), void()) {
+  e.prefetch(col0, N);
+}
+template <class E>
+__device__ __forceinline__ void epi_prefetch(E&, int, int, long) {}
+
 template <class T, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmB2, LpShape g, typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (128B-swizzle atoms span 8 rows x 128 B)
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on smem_raw, not an integer round trip: the compiler must keep seeing SHARED addresses, or
+  //  every access of the epilogue's staging block becomes a generic LD/ST that may alias its global stores)
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + T::STAGES * T::STAGE_BYTES);
   uint64_t* full = bars;                               // [STAGES]      TMA -> MMA
   uint64_t* empty = bars + T::STAGES;                  // [STAGES]      MMA -> TMA
@@ -313,7 +326,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < tiles && !g.skip_mma; t += gridDim.x) {
         int bm, bn;
         tile_coords(t, ntm, ntn, g.group_cols, bm, bn);
         const bool two = tile_two(bm);
@@ -347,7 +360,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(acc_empty + as, aph ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * T::MR * T::BN);
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < (g.skip_mma ? 0 : KB); ++kb) {
           mbar_wait(full + s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + s * T::STAGE_BYTES);
@@ -386,6 +399,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int r = 0; r < T::MR; ++r) {
         epi.begin_tile(bm * T::TILE_M + r * BM + q * 32, M);
+        epi_prefetch(epi, bn * T::BN + hsel * CW, g.N, 0);
         if (r == 0) {
           mbar_wait(acc_full + as, aph);
           tc_fence_after();
@@ -395,6 +409,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = 0; cc < T::BN / 32; ++cc) {
           uint32_t acc[CW];
           tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
+          if (cc + 1 < T::BN / 32) epi_prefetch(epi, bn * T::BN + (cc + 1) * 32 + hsel * CW, g.N, 0);
           tmem_ld_wait();
           epi.chunk(bn * T::BN + cc * 32 + hsel * CW, acc, g.N);
         }
@@ -486,7 +501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmB2, LpShape g, typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES2 * STAGE2_BYTES);
   uint64_t* full = bars;                          // [STAGES2]  leader's copy is used: both CTAs' TMA bytes + 2 arrivals
   uint64_t* empty = bars + STAGES2;               // [STAGES2]  per CTA, released by the leader's multicast commit

@@ -18,6 +18,19 @@
 
 namespace nnmpc {
 
+#ifndef NNMPC_EPI_PHASED
+#define NNMPC_EPI_PHASED 1
+#endif
+// probe variants (tools/probes/lp_pass_split.py): drop the state loads / the state stores of the epilogue
+#ifndef NNMPC_EPI_PREFETCH
+#define NNMPC_EPI_PREFETCH 1
+#endif
+#ifndef NNMPC_PROBE_NOLOAD
+#define NNMPC_PROBE_NOLOAD 0
+#endif
+#ifndef NNMPC_PROBE_NOSTORE
+#define NNMPC_PROBE_NOSTORE 0
+#endif
 using LpTileN128 = lp::LpTile<128, 4>;
 using LpTileM256 = lp::LpTile<128, 3, 2>;     // 256 x 128 outputs per CTA tile: operator bytes per flop halved
 
@@ -95,7 +108,7 @@ struct EpiDelta {
   Params p;
   lp::EpiWarpSmem* sm;
   int lane, rg, cp;
-  double dmax[NI];
+  float dmax[NI];          // per row: max |d| (fp32 is plenty for a trigger; NaN survives)
   __device__ EpiDelta(const Params& p_, lp::EpiWarpSmem* sm_, int lane_)
       : p(p_), sm(sm_), lane(lane_), rg(lane_ / LPR), cp(lane_ % LPR) {}
   __device__ void begin_tile(int pos0, int M) {
@@ -115,12 +128,12 @@ struct EpiDelta {
     __syncwarp();            // the previous tile's last reads of info[] are done
     sm->info[lane] = ri;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) dmax[i] = 0.0;
+    for (int i = 0; i < NI; ++i) dmax[i] = 0.f;
     __syncwarp();
   }
   // one column pair of one row
   __device__ __forceinline__ void pair(double2& x, double2& v, float2& e, float a0, float a1, double2 l, double2 u,
-                                       const lp::EpiRowInfo& ri, __half2& q, double& dm) {
+                                       const lp::EpiRowInfo& ri, __half2& q, float& dm, bool valid = true) {
     x.x += (double)a0 * ri.inv_in;
     x.y += (double)a1 * ri.inv_in;
     const double z00 = clip_sel(v.x, l.x, u.x), z01 = clip_sel(v.y, l.y, u.y);
@@ -132,9 +145,108 @@ struct EpiDelta {
     const __half q0 = quantise_dw_fast(dw0, ri.s_out, ri.inv_out, e.x);
     const __half q1 = quantise_dw_fast(dw1, ri.s_out, ri.inv_out, e.y);
     q = __halves2half2(q0, q1);
-    const double a = (d0 <= d1) ? d1 : d0;       // NaN propagates
-    dm = (a <= dm) ? dm : a;
+    const float a = (float)((d0 <= d1) ? d1 : d0);       // NaN propagates
+    dm = (!valid || a <= dm) ? dm : a;                   // lanes that ran on a stand-in row must not touch the residual
   }
+#if NNMPC_EPI_PHASED
+  // Bounds of one half of the chunk's rows (H = NI / 2 row iterations): issued together, ahead of their use.
+  // lb / ub rows are 16-byte aligned pairs when nu is even (vec); an odd nu wraps k1 to stage input 0.
+  static constexpr int H = NI / 2;
+  template <class RowOf>
+  __device__ __forceinline__ void load_bounds(int h, const RowOf& row_of, int k0, int k1, bool vec, double2 (&l)[H],
+                                              double2 (&u)[H]) const {
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const int r = row_of(h * H + j);
+      const double* lbr = p.lb + (long long)(r >= 0 ? r : 0) * p.nu;
+      const double* ubr = p.ub + (long long)(r >= 0 ? r : 0) * p.nu;
+      if (vec) {
+        l[j] = __ldg(reinterpret_cast<const double2*>(lbr + k0));
+        u[j] = __ldg(reinterpret_cast<const double2*>(ubr + k0));
+      } else {
+        l[j] = make_double2(__ldg(lbr + k0), __ldg(lbr + k1));
+        u[j] = make_double2(__ldg(ubr + k0), __ldg(ubr + k1));
+      }
+    }
+  }
+  // The chunk is written as explicit phases, in the order the hardware should see them, because the compiler cannot
+  // move a global load across the global stores of an earlier row (they may alias): round 2h's per-row loop loaded the
+  // bounds of row i only after the stores of row i - 1, i.e. paid one exposed L1/L2 round trip per row iteration
+  // (profiles/r02h_ncu_full_lp_gemm.txt: 39 % of the warp samples on the first use of those loads, per-warp IPC 0.1).
+  //   1. all state loads of the chunk + the bounds of the first half   2. update first half (8 independent chains)
+  //   3. bounds of the second half (before the first half's stores)    4. stores first half
+  //   5. update second half                                            6. stores second half
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
+    // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
+#pragma unroll
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
+    __syncwarp();
+    const int cbase = col0 + 2 * cp;       // this lane's column pair; n is even: the pair is inside when its first column is
+    const bool in = cbase < N;
+    // the chunk (col0 is a multiple of CW) lies inside one stage when the stage width is a multiple of CW
+    const int k0 = (in ? cbase : 0) % p.nu;
+    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;
+    const bool vec = (p.nu & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.lb) | reinterpret_cast<uintptr_t>(p.ub)) & 15) == 0;
+    double2 x[NI], v[NI];
+    float2 e[NI];
+    // row of iteration i (re-read from shared memory where needed: registers are the scarce resource here)
+    auto row_of = [&](int i) -> int { return in ? sm->info[rg + RG * i].row : -1; };
+    // 1. all state loads (streaming: read once per pass).  Unconditional: a row that does not take part reads row 0
+    //    (always there) and its results are dropped - a conditional load makes the compiler convert the loaded value
+    //    inside the conditional block, i.e. wait for every row's loads before issuing the next row's (measured:
+    //    profiles/r02l_*: eight serialised round trips per chunk).
+    const int cb_ld = in ? cbase : 0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int row = row_of(i);
+      const long long base = (long long)(row >= 0 ? row : 0) * p.n + cb_ld;
+#if NNMPC_PROBE_NOLOAD
+      x[i] = make_double2(0.0, (double)base * 1e-300);
+      v[i] = make_double2(0.0, 0.0);
+      e[i] = make_float2(0.f, 0.f);
+#else
+      x[i] = __ldcs(reinterpret_cast<const double2*>(p.X + base));
+      v[i] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
+      e[i] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
+#endif
+    }
+    double2 l0[H], u0[H], l1[H], u1[H];
+    load_bounds(0, row_of, k0, k1, vec, l0, u0);
+    // 2. first half
+#pragma unroll
+    for (int j = 0; j < H; ++j) update_row(j, cbase, row_of(j), x[j], v[j], e[j], l0[j], u0[j]);
+    // 3. bounds of the second half are in flight while the first half is stored
+    load_bounds(1, row_of, k0, k1, vec, l1, u1);
+    // 4.
+#pragma unroll
+    for (int j = 0; j < H; ++j) store_row(row_of(j), cbase, x[j], v[j], e[j]);
+    // 5. second half
+#pragma unroll
+    for (int j = 0; j < H; ++j) update_row(H + j, cbase, row_of(H + j), x[H + j], v[H + j], e[H + j], l1[j], u1[j]);
+    // 6.
+#pragma unroll
+    for (int j = 0; j < H; ++j) store_row(row_of(H + j), cbase, x[H + j], v[H + j], e[H + j]);
+    __syncwarp();            // stg is rewritten by the next step
+  }
+  // rows that do not take part run on zeros (no branch around the arithmetic: the H rows of a half interleave); the
+  // fp16 increment goes straight to the operand the next pass reads
+  __device__ __forceinline__ void update_row(int i, int cbase, int row, double2& x, double2& v, float2& e, const double2& l,
+                                             const double2& u) {
+    const int r = rg + RG * i;
+    const lp::EpiRowInfo ri = sm->info[r];
+    __half2 q;
+    pair(x, v, e, sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], l, u, ri, q, dmax[i], row >= 0);
+    if (row >= 0) *reinterpret_cast<__half2*>(p.Dn + (long long)ri.pw * p.ldd + cbase) = q;
+  }
+  __device__ __forceinline__ void store_row(int row, int cbase, const double2& x, const double2& v, const float2& e) const {
+    if (row < 0 || (NNMPC_PROBE_NOSTORE && x.x != 123.456)) return;
+    const long long base = (long long)row * p.n + cbase;
+    __stcs(reinterpret_cast<double2*>(p.X + base), x);
+    __stcs(reinterpret_cast<double2*>(p.V + base), v);
+    __stcs(reinterpret_cast<float2*>(p.E + base), e);
+  }
+#else
+  // round-2h form (one row iteration at a time), kept for A/B runs of the probe
   __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
     // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
 #pragma unroll
@@ -178,20 +290,43 @@ struct EpiDelta {
     }
     __syncwarp();            // stg is rewritten by the next step
   }
+#endif
+  // L2 prefetch of the state of the NEXT chunk of this warp (lane = row): the loads of a chunk are one exposed DRAM round
+  // trip per chunk and warp, and with two warps per scheduler nothing else covers it.  No registers held.
+  __device__ __forceinline__ void prefetch(int col0, int N) const {
+#if NNMPC_EPI_PREFETCH
+    const int row = sm->info[lane].row;
+    if (row < 0 || col0 >= N) return;
+    const long long base = (long long)row * p.n + col0;
+    const int last = (col0 + lp::CW <= N ? lp::CW : N - col0) - 1;
+    const char* px = reinterpret_cast<const char*>(p.X + base);
+    const char* pv = reinterpret_cast<const char*>(p.V + base);
+    const char* pe = reinterpret_cast<const char*>(p.E + base);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
+    if ((reinterpret_cast<uintptr_t>(px) & 127) + 8 * last >= 128) {       // rows that are not 128-byte aligned straddle lines
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 8 * last));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + 8 * last));
+    }
+    if ((reinterpret_cast<uintptr_t>(pe) & 127) + 4 * last >= 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 4 * last));
+#endif
+  }
   __device__ void end_tile() {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      double m = dmax[i];
+      float m = dmax[i];
       // the LPR lanes of a row group hold disjoint columns of the same rows; NaN must survive the reduction
 #pragma unroll
       for (int o = 1; o < LPR; o <<= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, m, o);
+        const float t = __shfl_xor_sync(0xffffffffu, m, o);
         m = (t <= m) ? m : t;
       }
       const int row = sm->info[rg + RG * i].row;
       if (cp == 0 && row >= 0) {
-        if (!(m <= 1.7e308)) m = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
-        atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(m));
+        double md = (double)m;
+        if (!(m <= 3.0e38f)) md = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
+        atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(md));
       }
     }
   }

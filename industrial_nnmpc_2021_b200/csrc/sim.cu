@@ -202,17 +202,22 @@ __device__ int block_excl_scan(int c, int& total_out) {
 //  mode run every `cadence`-th loop - so the list grows instead of starting over).
 // Four consecutive list entries per thread and round: the dependent loads of a row (list -> state -> residual)
 // overlap across the four, and the candidate list keeps the order of the live list.
-__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int append, int full,
+// Several 1024-thread blocks share the live list (it is the one kernel between two tensor-core passes, so its latency
+// is exposed): every block scans its slices and reserves a range of the candidate list with one atomicAdd per slice,
+// hence the ORDER of the candidate list - not its content - varies from run to run; nothing downstream depends on
+// it.  N_CAND is reset by the host-side launcher when a new list starts.  With one-term tiles enabled (need2) the
+// kernel runs as a single block, because the tile flags are cleared before they are raised.
+__global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int max_iter, int full,
                                                  const int* __restrict__ pos_next, int S) {
   constexpr int RPT = 4;
   const int na = e.counts[N_ACTIVE];
-  int base = append ? e.counts[N_CAND] : 0;
   int iterated = 0;
   // tile flags of the NEXT pass start from "one term is enough"; rows that are not in their late phase raise them
   if (e.need2)
     for (int i = threadIdx.x; i < (S + 127) / 128 + 1; i += 1024) e.need2[i] = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < na; i0 += 1024 * RPT) {
+  __shared__ int s_base;
+  for (int i0 = blockIdx.x * 1024 * RPT; i0 < na; i0 += gridDim.x * 1024 * RPT) {
     int s[RPT];
     bool live[RPT], cand[RPT];
 #pragma unroll
@@ -252,20 +257,24 @@ __global__ void __launch_bounds__(1024) k_select(EngineArrays e, double tol, int
       }
     }
     int total;
-    int off = base + block_excl_scan(nc, total);
+    const int excl = block_excl_scan(nc, total);
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(e.counts + N_CAND, total) : 0;
+    __syncthreads();
+    int off = s_base + excl;
 #pragma unroll
     for (int r = 0; r < RPT; ++r)
       if (cand[r]) e.l_cand[off++] = s[r];
-    base += total;
+    __syncthreads();
   }
   // block-wide count of the rows that iterated
   int tot_it;
   block_excl_scan(iterated, tot_it);
   if (threadIdx.x == 0) {
-    e.counts[N_CAND] = base;
-    *e.rowiters += (unsigned long long)tot_it;
-    if (e.mixed && e.counts[E_TAIL] > 0) e.rowiters[1] += (unsigned long long)tot_it;   // of which: FP64 tail iterations
-    if (e.mixed && full) e.stats[0] += (unsigned long long)e.counts[E_ANCHOR];   // anchors served at the top of this loop
+    if (tot_it) {
+      atomicAdd(e.rowiters, (unsigned long long)tot_it);
+      if (e.mixed && e.counts[E_TAIL] > 0) atomicAdd(e.rowiters + 1, (unsigned long long)tot_it);   // of which: FP64 tail iterations
+    }
+    if (blockIdx.x == 0 && e.mixed && full) e.stats[0] += (unsigned long long)e.counts[E_ANCHOR];   // anchors served at the top of this loop
   }
 }
 
@@ -819,6 +828,10 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   k_engine_init<<<(B + 255) / 256, 256, 0, st>>>(e, B, cont ? 1 : 0, h->kappa0, cont ? 0 : 1);
   count_launch();
 
+  const size_t adv_smem = (size_t)ADV_ROWS * h->kin_ld * sizeof(double);
+  if (adv_smem > 200 * 1024) return set_error(NNMPC_ERR_UNSUPPORTED, "plant step: nx + nu + nd = %d does not fit the staging buffer", h->kin_ld);
+  if (adv_smem > 48 * 1024)
+    NNMPC_CUDA(cudaFuncSetAttribute(k_advance_plant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adv_smem));
   double* Wc = q->W0.p;   // operand the next iteration reads
   double* Wn = q->W1.p;
   int lay = 0;            // mixed mode: operand layout buffer the next tensor-core pass reads
@@ -927,7 +940,13 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       double* t = Wc; Wc = Wn; Wn = t;
     }
     // 2-4. candidates -> exact KKT check -> done list
-    k_select<<<1, 1024, 0, st>>>(e, tol, max_iter, (cad > 1 && (loop % cad) != 1 % cad) ? 1 : 0, full ? 1 : 0, pos_next, B);
+    if (!(cad > 1 && (loop % cad) != 1 % cad))      // a new candidate list starts (otherwise this pass appends to it)
+      NNMPC_CUDA(cudaMemsetAsync(e.counts + N_CAND, 0, sizeof(int), st));
+    {
+      int sel_blocks = e.need2 ? 1 : (B + 4095) / 4096;
+      if (sel_blocks > 16) sel_blocks = 16;
+      k_select<<<sel_blocks, 1024, 0, st>>>(e, tol, max_iter, full ? 1 : 0, pos_next, B);
+    }
     if (!full) {
       count_launch();
       continue;
@@ -961,7 +980,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       k_qp_store<<<row_grid(B), 256, 0, st>>>(e.l_done, e.counts + N_DONE, e.chunk, *qb, h->Z.p, gbuf, q->Ql.p, h->lb.p, h->ub.p,
                                               h->stats, n, nu);
     else
-      k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, (size_t)ADV_ROWS * h->kin_ld * sizeof(double), st>>>(
+      k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, adv_smem, st>>>(
           e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou, h->upcur.p, h->ABd, n, nx, nu, nd,
           h->kin_ld, gbuf, q->Ql.p, h->cap_useq, h->cap_cost, h->lb.p, h->ub.p, h->stats);
     count_launch(2);
