@@ -508,6 +508,8 @@ def run_cdu(args):
                               "lp_tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
                               "exact_tflops_fp64eq": f64_flops / (f64_ms * 1e-3) / 1e12 if f64_ms > 0 else None,
                               "one_term_tile_share": t1 / max(t1 + t2, 1),
+                              "mma_products_per_iteration": (t1 + 2.0 * t2 + sp1.get("tiles_second_term_delivery", 0)
+                                                             - sp0.get("tiles_second_term_delivery", 0)) / max(t1 + t2, 1),
                               "work_per_qp": {k: (sp1[k] - sp0[k]) / nq for k in ("row_iterations", "anchors", "exact_checks")},
                               "shares": {"lp": gemm_ms / ms_prof, "exact": f64_ms / ms_prof, "tail": tail_ms / ms_prof,
                                          "rest": rest_ms / ms_prof}, "clocks": clocks,
@@ -595,14 +597,17 @@ def run_cdu(args):
         rows_per_launch = (gemm_flops / (2.0 * n * n)) / max(gemm_launches, 1)
         # tiles of late-phase rows run with one operator term (LpShape::need2): executed MMA work per algorithmic flop
         t1, t2 = sp1["tiles_one_term"] - sp0["tiles_one_term"], sp1["tiles_two_terms"] - sp0["tiles_two_terms"]
-        mma_factor = (t1 + 2.0 * t2) / max(t1 + t2, 1) if (t1 + t2) else 2.0
+        tc = sp1.get("tiles_second_term_delivery", 0) - sp0.get("tiles_second_term_delivery", 0)
+        mma_factor = (t1 + 2.0 * t2 + tc) / max(t1 + t2, 1) if (t1 + t2) else 2.0
         # DRAM bytes per launch: a MODEL, not a per-run measurement - two fp16 operator terms read once per pass
         # (2 x 2 n^2 B) plus the per-row state, with the per-row constant taken from the one `ncu --set full` capture of
         # this kernel (profiles/r02h_ncu_full_lp_gemm.txt: 3.72 GB per launch at 16 384 rows, n = 4480 -> 222 kB per row
         # vs 42 B x n = 188.2 kB algorithmic), scaled linearly in n
         op_bytes = mma_factor * 2.0 * n * n
-        r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
-                                             "increments x two-term fp16 operator split, fp32 TMEM accumulators, FP64 state)",
+        r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (+ <EpiAddX> every 4th pass) (regulator-QP iteration: tcgen05 kind::f16, fp16 "
+                                             "increments x two-term fp16 operator split - second term deferred, fp32 TMEM "
+                                             "accumulators, FP64 state)",
+                "mma_products_per_iteration": mma_factor,
                 "achieved": achieved, "executed_mma": mma_factor * achieved, "peak": lp_peak, "unit": "TFLOP/s",
                 "one_term_tile_share": t1 / max(t1 + t2, 1),
                 "frac": achieved / lp_peak, "frac_executed": mma_factor * achieved / lp_peak,

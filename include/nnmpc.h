@@ -161,8 +161,15 @@ int nnmpc_sim_set_exact_gemm(nnmpc_sim_t* h, int mode);
  * 0.4 - 6 % of the tiles qualify (trajectories restart inside late tiles between re-layouts) and a row's arithmetic would
  * depend on its neighbours; factors up to 1e4 left iterations and exact checks per QP unchanged. */
 int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor);
-/* cumulative since create: out2 = {128x128 tensor-core tiles run with one operator term, with both terms} */
-int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2);
+/* cumulative since create: out3 = {128x128 tensor-core tiles of the iteration passes run with one operator term, with
+ * both terms, tiles of the second-term delivery passes} */
+int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out3);
+/* Mixed mode only: the tensor-core pass multiplies the first fp16 operator term alone, and the second term (a 2^-11
+ * relative correction, linear in the increments) is delivered every `every`-th pass for all increments since the last
+ * delivery at once, by a one-term GEMM over the pending sums (rounded up to a multiple of the cadence; default 8;
+ * 0 = both terms in every pass, the round-1 form).  MMA work per iteration falls from 2 to 1 + 1/every products;
+ * fixed points and the exact KKT certification of every returned point are unchanged. */
+int nnmpc_sim_set_second_term_cadence(nnmpc_sim_t* h, int every);
 /* Optional per-QP sinks for the following nnmpc_sim_run calls (device pointers, either may be NULL; NULL, NULL
  * switches the capture off): useq [B][T][n] = the whole optimal input sequence of every regulator QP with the
  * target added back per stage - what get_control_sequence returns (lib/linearMPC.py:689) and DenseQPRegulator
@@ -262,7 +269,8 @@ int nnmpc_lp_gemm_test(int M, int N, int K, const double* A, const double* Bt, d
 int nnmpc_oz_gemm_test(int M, int N, int K, const double* A, const double* Bt, double* C, void* stream);
 /* nnmpc_lp_pass_probe (tools/probes/lp_pass_split.py): one tensor-core pass over B x n synthetic state with the production
  * epilogue (ms[0]), with an epilogue that only drains TMEM (ms[1]) and with the production epilogue but no TMA loads / MMAs
- * (ms[2]: the epilogue alone), each averaged over reps launches; ms has room for 3 floats. */
+ * (ms[2]: the epilogue alone); then the deferred-second-term form: the one-term pass (ms[3]) and the second-term delivery
+ * GEMM (ms[4]); each averaged over reps launches; ms has room for 5 floats. */
 int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms);
 /* C = A * Bt^T through the FP64 GEMM kernel */
 int nnmpc_gemm_tn(int M, int N, int K, const double* A, long long lda, const double* Bt,

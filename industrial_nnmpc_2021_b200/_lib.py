@@ -51,6 +51,7 @@ SIGNATURES = {
     "nnmpc_sim_set_capture": (C.c_int, [vp, vp, vp]),
     "nnmpc_sim_set_one_term_threshold": (C.c_int, [vp, C.c_double]),
     "nnmpc_sim_tile_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
+    "nnmpc_sim_set_second_term_cadence": (C.c_int, [vp, C.c_int]),
     "nnmpc_sim_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_active_stats": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "nnmpc_sim_run": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double,

@@ -44,8 +44,19 @@ int device_sm_count(int device) {
   return cache[device & 63];
 }
 
+// 0 = 128 x 128 tiles, 1 = 256 x 128 tiles for the ONE-term passes of the deferred-second-term form (NNMPC_LP1_TILE=m256):
+// with one product per staged operand pair the L2->SM bytes per flop double, which the 256-row tile halves again.
+static int lp1_tile_m256() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNMPC_LP1_TILE");
+    v = (e && strcmp(e, "m256") == 0) ? 1 : 0;
+  }
+  return v;
+}
+
 int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st) {
-  if (B <= s->cap && n == s->n) return 0;
+  if (B <= s->cap && n == s->n && (!s->defer2 || s->S[0].p)) return 0;
   const long long cap = B > s->cap ? B : s->cap;
   s->n = n;
   s->ldd = ((long long)n + 63) / 64 * 64;
@@ -62,6 +73,17 @@ int lp_state_ensure(LpState* s, long long B, int n, cudaStream_t st) {
     if (!lp::make_tmap_f16(&s->tmD[b], s->D[b].p, cap_pad, s->ldd, s->ldd, lp::BM) ||
         !lp::make_tmap_f16(&s->tmD256[b], s->D[b].p, cap_pad, s->ldd, s->ldd, 2 * lp::BM))
       return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the increment buffers");
+    if (s->defer2) {
+      NNMPC_TRY(s->S[b].ensure((size_t)cap_pad * s->ldd));
+      NNMPC_CUDA(cudaMemsetAsync(s->S[b].p, 0, (size_t)cap_pad * s->ldd * sizeof(__half), st));
+      if (!lp::make_tmap_f16(&s->tmS[b], s->S[b].p, cap_pad, s->ldd, s->ldd, lp::BM) ||
+          !lp::make_tmap_f16(&s->tmS256[b], s->S[b].p, cap_pad, s->ldd, s->ldd, 2 * lp::BM))
+        return set_error(NNMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for the pending-sum buffers");
+    }
+  }
+  if (s->defer2) {
+    NNMPC_TRY(s->sS.ensure((size_t)cap));
+    NNMPC_CUDA(cudaMemsetAsync(s->sS.p, 0, (size_t)cap * sizeof(double), st));
   }
   s->cap = cap;
   s->cur = 0;
@@ -90,7 +112,8 @@ int lp_dr_first(const int* rows, const int* count, int max_rows, LpState* s, dou
                 cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
   k_dr_first<<<row_grid(max_rows), 256, 0, st>>>(rows, count, s->X.p, V, W, s->E.p, s->D[s->cur].p, s->ldd, lb, ub, s->sc_in.p,
-                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r, need2);
+                                       s->sc_out.p, state, it, iter_state, s->n, nu, alpha, pos_r, need2,
+                                       s->defer2 ? s->S[s->cur].p : nullptr, s->defer2 ? s->sS.p : nullptr);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -110,7 +133,8 @@ int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emi
             const int* pos_r, cudaStream_t st, unsigned char* need2) {
   if (max_rows <= 0) return 0;
   k_lp_emit<<<row_grid(max_rows), 256, 0, st>>>(rows, count, state, emit_state, iter_state, V, s->Wl.p, s->E.p, s->D[s->cur].p,
-                                      s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r, need2);
+                                      s->ldd, lb, ub, s->sc_in.p, s->sc_out.p, dtrig, s->n, nu, alpha, pos_r, need2,
+                                      s->defer2 ? s->S[s->cur].p : nullptr, s->defer2 ? s->sS.p : nullptr);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
   return 0;
@@ -118,9 +142,13 @@ int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emi
 
 int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
                const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
-               double alpha, int device, cudaStream_t st, const unsigned char* need2, unsigned long long* tile_stat) {
+               double alpha, int device, cudaStream_t st, const unsigned char* need2, unsigned long long* tile_stat,
+               int s_mode) {
   if (B <= 0) return 0;
+  if (s_mode && !s->defer2) return set_error(NNMPC_ERR_BADARG, "lp_iterate: pending-sum buffers were not allocated");
   EpiDelta::Params ep{};
+  ep.s_mode = s_mode;
+  if (s_mode) { ep.Sc = s->S[s->cur].p; ep.Sn = s->S[s->cur ^ 1].p; ep.sS = s->sS.p; }
   ep.X = s->X.p; ep.V = V; ep.E = s->E.p; ep.Dn = s->D[s->cur ^ 1].p; ep.ldd = s->ldd; ep.lb = lb; ep.ub = ub;
   ep.state = state; ep.iter_state = iter_state; ep.list_r = list_r; ep.pos_w = pos_w; ep.sc_in = s->sc_in.p; ep.sc_out = s->sc_out.p; ep.dres = dres;
   ep.n = s->n; ep.nu = nu; ep.alpha = alpha; ep.inv_sT = 1.0 / op->scale;
@@ -130,6 +158,17 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   int group_cols = (int)(24.0 / tile_mb);
   if (group_cols < 1) group_cols = 1;
   lp::LpShape g{B, s->n, s->n, len_r, group_cols, need2, tile_stat, 0, 0};
+  if (s_mode) {      // one-term pass (the kernel never touches the second operator map)
+    g.need2 = nullptr;
+    g.group_cols = 2 * group_cols;        // one term: the same bytes of operator cover twice the column tiles
+    cudaError_t e1 = lp1_tile_m256()
+                         ? lp::launch_lp_gemm<LpTile1M256, EpiDelta>(s->tmD256[s->cur], op->tm1, op->tm1, g, ep, device_sm_count(device), st)
+                         : lp::launch_lp_gemm<LpTile1N128, EpiDelta>(s->tmD[s->cur], op->tm1, op->tm1, g, ep, device_sm_count(device), st);
+    count_launch();
+    if (e1 != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e1));
+    s->cur ^= 1;
+    return 0;
+  }
   cudaError_t e = lp_use_pair()
                       ? lp::launch_lp_gemm_pair<EpiDelta>(s->tmD[s->cur], op->tm1, op->tm2, g, ep, device_sm_count(device), st)
                   : lp_tile_m256()
@@ -138,6 +177,23 @@ int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const
   count_launch();
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm launch failed: %s", cudaGetErrorString(e));
   s->cur ^= 1;
+  return 0;
+}
+
+int lp_correct(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* state,
+               int iter_state, int device, cudaStream_t st, unsigned long long* tile_stat) {
+  if (B <= 0) return 0;
+  if (!s->defer2) return set_error(NNMPC_ERR_BADARG, "lp_correct: pending-sum buffers were not allocated");
+  EpiAddX::Params ep{s->X.p, state, iter_state, list_r, s->sS.p, s->n, 1.0 / op->scale};
+  const double tile_mb = LpTile1N128::BN * (double)op->ldh * 2.0 / 1048576.0;
+  int group_cols = (int)(24.0 / tile_mb);
+  if (group_cols < 1) group_cols = 1;
+  lp::LpShape g{B, s->n, s->n, len_r, group_cols, nullptr, tile_stat, 0, 0};
+  cudaError_t e = lp1_tile_m256()
+                      ? lp::launch_lp_gemm<LpTile1M256, EpiAddX>(s->tmS256[s->cur], op->tm2, op->tm2, g, ep, device_sm_count(device), st)
+                      : lp::launch_lp_gemm<LpTile1N128, EpiAddX>(s->tmS[s->cur], op->tm2, op->tm2, g, ep, device_sm_count(device), st);
+  count_launch();
+  if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "lp_gemm (second-term delivery) launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -271,6 +327,7 @@ int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
   if (rc == 0) rc = state.ensure((size_t)B);
   if (rc == 0) rc = dres.ensure((size_t)B);
   if (rc == 0) rc = sink.ensure(1);
+  lps.defer2 = true;
   if (rc == 0) rc = lp_state_ensure(&lps, B, n, st);
   if (rc == 0) {
     k_probe_fill<<<148 * 8, 256, 0, st>>>(Top.p, Top.p, lps.E.p, lps.D[0].p, lps.ldd, sc.p, state.p, n, n);   // any bounded operator
@@ -282,8 +339,8 @@ int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
     cudaMemcpyAsync(lps.sc_out.p, sc.p, (size_t)B * 8, cudaMemcpyDeviceToDevice, st);
     rc = lp_split_operator(Top.p, n, 1.0, &op, st);
   }
-  cudaEvent_t e0, e1, e2, e3;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+  cudaEvent_t e0, e1, e2, e3, e4, e5, e6;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); cudaEventCreate(&e4); cudaEventCreate(&e5); cudaEventCreate(&e6);
   if (rc == 0) {
     const double tile_mb = 2.0 * LpTileN128::BN * (double)op.ldh * 2.0 / 1048576.0;
     int group_cols = (int)(24.0 / tile_mb);
@@ -313,16 +370,41 @@ int nnmpc_lp_pass_probe(int B, int n, int reps, float* ms) {
     for (int i = 0; i < reps && (only < 0 || only == 2); ++i)
       lp::launch_lp_gemm<LpTileN128, EpiDelta>(lps.tmD[0], op.tm1, op.tm2, g_epi, ep, sms, st);
     cudaEventRecord(e3, st);
-    if (cudaEventSynchronize(e3) != cudaSuccess)
+    // deferred second term: the one-term pass (increment added to the pending sum) and the delivery GEMM
+    cudaMemcpyAsync(lps.sS.p, sc.p, (size_t)B * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(lps.S[0].p, lps.D[0].p, (size_t)B * lps.ldd * sizeof(__half), cudaMemcpyDeviceToDevice, st);
+    EpiDelta::Params ep1 = ep;
+    ep1.s_mode = 1; ep1.Sc = lps.S[0].p; ep1.Sn = lps.S[1].p; ep1.sS = lps.sS.p;
+    lp::LpShape g1 = g;
+    g1.group_cols = 2 * group_cols;
+    EpiAddX::Params epx{lps.X.p, state.p, 1, nullptr, lps.sS.p, n, 1.0 / op.scale};
+    const bool m256 = getenv("NNMPC_LP1_TILE") && strcmp(getenv("NNMPC_LP1_TILE"), "m256") == 0;
+    auto pass1 = [&]() {
+      if (m256) lp::launch_lp_gemm<LpTile1M256, EpiDelta>(lps.tmD256[0], op.tm1, op.tm1, g1, ep1, sms, st);
+      else lp::launch_lp_gemm<LpTile1N128, EpiDelta>(lps.tmD[0], op.tm1, op.tm1, g1, ep1, sms, st);
+    };
+    auto corr = [&]() {
+      if (m256) lp::launch_lp_gemm<LpTile1M256, EpiAddX>(lps.tmS256[0], op.tm2, op.tm2, g1, epx, sms, st);
+      else lp::launch_lp_gemm<LpTile1N128, EpiAddX>(lps.tmS[0], op.tm2, op.tm2, g1, epx, sms, st);
+    };
+    pass1(); corr();
+    cudaEventRecord(e6, st);
+    for (int i = 0; i < reps && (only < 0 || only == 3); ++i) pass1();
+    cudaEventRecord(e4, st);
+    for (int i = 0; i < reps && (only < 0 || only == 4); ++i) corr();
+    cudaEventRecord(e5, st);
+    if (cudaEventSynchronize(e5) != cudaSuccess)
       rc = set_error(NNMPC_ERR_CUDA, "lp pass probe failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc == 0) {
       cudaEventElapsedTime(&ms[0], e0, e1);
       cudaEventElapsedTime(&ms[1], e1, e2);
       cudaEventElapsedTime(&ms[2], e2, e3);
-      ms[0] /= reps; ms[1] /= reps; ms[2] /= reps;
+      cudaEventElapsedTime(&ms[3], e6, e4);
+      cudaEventElapsedTime(&ms[4], e4, e5);
+      ms[0] /= reps; ms[1] /= reps; ms[2] /= reps; ms[3] /= reps; ms[4] /= reps;
     }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4); cudaEventDestroy(e5); cudaEventDestroy(e6);
   cudaStreamSynchronize(st);
   for (DevBuf<double>* b : {&Top, &V, &lb, &ub, &sc}) b->release();
   state.release(); dres.release(); sink.release(); lps.release(); op.release();

@@ -18,8 +18,18 @@ struct LpState {
   DevBuf<__half> D[2];               // double buffered: the TMA reads D[cur], the epilogue writes D[cur ^ 1]
   CUtensorMap tmD[2];
   CUtensorMap tmD256[2];             // the same buffers with 256-row boxes (LpTile<.,.,2>)
+  // deferred second operator term (lp_iter.cuh): pending sums of the increments, laid out and flipped like D, and the
+  // per-row scale of each sum.  Allocated when defer2 is set before lp_state_ensure.
+  bool defer2 = false;
+  DevBuf<__half> S[2];
+  DevBuf<double> sS;
+  CUtensorMap tmS[2];
+  CUtensorMap tmS256[2];
   int cur = 0;
-  void release() { Wl.release(); X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release(); cap = 0; }
+  void release() {
+    Wl.release(); X.release(); sc_in.release(); sc_out.release(); E.release(); D[0].release(); D[1].release();
+    S[0].release(); S[1].release(); sS.release(); cap = 0;
+  }
 };
 
 #ifdef __CUDACC__
@@ -63,7 +73,13 @@ int lp_emit(const int* rows, const int* count, int max_rows, int* state, int emi
 int lp_iterate(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* pos_w, double* V,
                const double* lb, const double* ub, const int* state, int iter_state, unsigned long long* dres, int nu,
                double alpha, int device, cudaStream_t st, const unsigned char* need2 = nullptr,
-               unsigned long long* tile_stat = nullptr);
+               unsigned long long* tile_stat = nullptr, int s_mode = 0);
+// Deferred second operator term: x += T2 S / (s_T sS) over the operand rows the NEXT lp_iterate will read (same
+// list / state predicate); that pass must then run with s_mode = 2 (a new pending sum starts).  s_mode of
+// lp_iterate: 0 = two-term pass (no pending sums), 1 = one-term pass, increment added to the pending sum, 2 = one-term
+// pass, pending sum restarted.
+int lp_correct(const LpOperator* op, LpState* s, int B, const int* list_r, const int* len_r, const int* state,
+               int iter_state, int device, cudaStream_t st, unsigned long long* tile_stat = nullptr);   // tile_stat[0] += tiles
 
 
 }  // namespace nnmpc

@@ -53,6 +53,8 @@ struct EpiRowInfo {
   int row;          // sample row (-1: not taking part)
   int pw;           // operand row written for it
   double inv_in, s_out, inv_out;
+  float g;          // deferred second term: scale of the pending-sum operand relative to the operand written now
+  int pad;
 };
 // leading dimension of the staging block: bank-conflict-free both for the writes (one column, 32 consecutive rows)
 // and for the epilogue's reads (lane = (row group, column pair), see EpiDelta)
@@ -70,12 +72,16 @@ constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 // MR_ = 128-row blocks per CTA tile (1 or 2).  With MR = 2 a CTA owns 256 x BN outputs: one staged operator tile
 // (B1, B2) feeds the MMAs of both row blocks, so the operator bytes pulled from L2 per flop halve - the pass is
 // bound by L2->SM throughput (ncu: 7.5 kB/clk chip-wide at 48 % tensor-pipe activity with MR = 1).
-template <int BN_, int STAGES_, int MR_ = 1>
+// TERMS_ = operator terms per pass: 2 = A x (B1 + B2) (both products share the staged A tile and the accumulator);
+// 1 = A x B1 only (a stage holds A and B1: deeper ring for the same shared memory) - the form of the regulator pass when
+// the second operator term is delivered every m-th pass by its own GEMM (lp_iter.cuh, "deferred second term").
+template <int BN_, int STAGES_, int MR_ = 1, int TERMS_ = 2>
 struct LpTile {
-  static constexpr int BN = BN_, STAGES = STAGES_, MR = MR_;
+  static constexpr int BN = BN_, STAGES = STAGES_, MR = MR_, TERMS = TERMS_;
   static constexpr int TILE_M = MR * BM;
   static constexpr int A_BYTES = TILE_M * BK * 2, B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + TERMS * B_BYTES;
+  static_assert(TERMS == 1 || TERMS == 2, "operator terms");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*1 KB alignment slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
   static constexpr int TMEM_COLS = ACC_STAGES * MR * BN;
   static_assert(MR == 1 || MR == 2, "row blocks per tile");
@@ -294,6 +300,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int KB = (g.K + BK - 1) / BK;
   // does row tile bm need the second operator term?  (flags are per 128 rows)
   auto tile_two = [&](int bm) -> bool {
+    if (T::TERMS == 1) return false;
     if (!g.need2) return true;
     bool two = false;
 #pragma unroll
@@ -338,7 +345,8 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(full + s, two_kb ? T::STAGE_BYTES : T::A_BYTES + T::B_BYTES);
           tma_load_2d(st, &tmA, full + s, kb * BK, bm * T::TILE_M);      // the A map's box is TILE_M rows
           tma_load_2d_hint(st + T::A_BYTES, &tmB1, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
-          if (two_kb) tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
+          if (T::TERMS == 2 && two_kb)
+            tma_load_2d_hint(st + T::A_BYTES + T::B_BYTES, &tmB2, full + s, kbb * BK, bn * T::BN, L2_EVICT_LAST);
           if (++s == T::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -374,7 +382,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes (2 x 16 B units) per K = 16 step inside the swizzle span
               umma_f16(tr, da + 2 * k, db1 + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            if (two_kb) {
+            if (T::TERMS == 2 && two_kb) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tr, da + 2 * k, db2 + 2 * k, idesc, 1u);
             }

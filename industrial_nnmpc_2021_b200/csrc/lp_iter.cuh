@@ -7,6 +7,12 @@
 //   D     fp16: scaled increment s_row (w_lp+ - w_lp) = the A operand of the next tensor-core pass
 // One pass:  x += (T1 + T2) dq / (s_T s_row);  d = x - clip(v);  v += alpha d;
 //            dw = (2 clip(v) - v) - w_lp;  dq = fp16(s_row' dw);  w_lp += dq / s_row'
+// Deferred second operator term (s_mode != 0): the pass multiplies T1 only, and the 2^-11-relative correction T2 dq is
+// delivered every m-th pass for all increments since the last delivery at once - T2 is linear, so nothing is lost,
+// only delayed (like E): S (fp16, laid out like D, own per-row power-of-two scale sS) holds the pending sum
+// sum_j dq_j, a one-term GEMM  x += T2 S / (s_T sS)  (EpiAddX) delivers it, and the next pass starts a new sum.
+// MMA work per pass falls from 2 to 1 + 1/m products; the board is power capped in this kernel
+// (profiles/r02n_pass_energy_diagnosis.md), so joules are what the pass time is made of.
 // Fixed points are exactly those of the FP64 iteration in qp.cu (E -> 0, dq -> 0).  What the fp16
 // operator split and the fp32 accumulation lose is proportional to |w_lp - w_anchor|; an FP64
 // anchor GEMM (x = Top w - c with w_lp := w, E := 0) resets it, and every returned point is
@@ -18,9 +24,6 @@
 
 namespace nnmpc {
 
-#ifndef NNMPC_EPI_PHASED
-#define NNMPC_EPI_PHASED 1
-#endif
 // probe variants (tools/probes/lp_pass_split.py): drop the state loads / the state stores of the epilogue
 #ifndef NNMPC_EPI_PREFETCH
 #define NNMPC_EPI_PREFETCH 1
@@ -33,6 +36,9 @@ namespace nnmpc {
 #endif
 using LpTileN128 = lp::LpTile<128, 4>;
 using LpTileM256 = lp::LpTile<128, 3, 2>;     // 256 x 128 outputs per CTA tile: operator bytes per flop halved
+// one operator term per pass (deferred second term): a stage is A + B1
+using LpTile1N128 = lp::LpTile<128, 6, 1, 1>;
+using LpTile1M256 = lp::LpTile<128, 4, 2, 1>;
 
 // one element of the Douglas-Rachford delta update (shared by the tensor-core epilogue and k_dr_first)
 __device__ __forceinline__ void dr_delta_one(double& x, double& v, double wl, double l, double u, double alpha,
@@ -98,6 +104,11 @@ struct EpiDelta {
     const double* sc_in;   // scale the current operand row was quantised with
     const double* sc_out;  // scale for the operand written now
     unsigned long long* dres;  // per row: max |d| (bit pattern of a non-negative double)
+    // deferred second term (s_mode: 0 = off, 1 = add this pass's increment to the pending sum, 2 = start a new sum)
+    const __half* Sc;    // pending sums, laid out like the operand the TMA reads
+    __half* Sn;          // ... like the operand written now
+    double* sS;          // per sample row: scale of its pending sum
+    int s_mode;
     int n, nu;
     double alpha;
     double inv_sT;       // 1 / operator scale
@@ -108,13 +119,15 @@ struct EpiDelta {
   Params p;
   lp::EpiWarpSmem* sm;
   int lane, rg, cp;
+  int pos0;                // operand position of the warp's first row in this tile
   float dmax[NI];          // per row: max |d| (fp32 is plenty for a trigger; NaN survives)
   __device__ EpiDelta(const Params& p_, lp::EpiWarpSmem* sm_, int lane_)
       : p(p_), sm(sm_), lane(lane_), rg(lane_ / LPR), cp(lane_ % LPR) {}
-  __device__ void begin_tile(int pos0, int M) {
+  __device__ void begin_tile(int pos0_, int M) {
+    pos0 = pos0_;
     const int pos = pos0 + lane;
     lp::EpiRowInfo ri;
-    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0;
+    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.pad = 0;
     if (pos < M) {
       const int row = p.list_r ? p.list_r[pos] : pos;
       if (p.state[row] == p.iter_state) {
@@ -123,6 +136,9 @@ struct EpiDelta {
         ri.inv_in = p.inv_sT / p.sc_in[row];
         ri.s_out = p.sc_out[row];
         ri.inv_out = 1.0 / ri.s_out;
+        // a new sum is kept at 1/8 of the operand scale: head room for the increments that follow
+        if (p.s_mode == 2) ri.g = 0.125f;
+        else if (p.s_mode == 1) ri.g = (float)(p.sS[row] * ri.inv_out);
       }
     }
     __syncwarp();            // the previous tile's last reads of info[] are done
@@ -148,7 +164,6 @@ struct EpiDelta {
     const float a = (float)((d0 <= d1) ? d1 : d0);       // NaN propagates
     dm = (!valid || a <= dm) ? dm : a;                   // lanes that ran on a stand-in row must not touch the residual
   }
-#if NNMPC_EPI_PHASED
   // Bounds of one half of the chunk's rows (H = NI / 2 row iterations): issued together, ahead of their use.
   // lb / ub rows are 16-byte aligned pairs when nu is even (vec); an odd nu wraps k1 to stage input 0.
   static constexpr int H = NI / 2;
@@ -189,6 +204,7 @@ struct EpiDelta {
     const bool vec = (p.nu & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.lb) | reinterpret_cast<uintptr_t>(p.ub)) & 15) == 0;
     double2 x[NI], v[NI];
     float2 e[NI];
+    __half2 sold[NI];
     // row of iteration i (re-read from shared memory where needed: registers are the scarce resource here)
     auto row_of = [&](int i) -> int { return in ? sm->info[rg + RG * i].row : -1; };
     // 1. all state loads (streaming: read once per pass).  Unconditional: a row that does not take part reads row 0
@@ -209,12 +225,15 @@ struct EpiDelta {
       v[i] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
       e[i] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
 #endif
+      // pending sum of this row and column pair (operand position = tile row; the buffers are padded to whole tiles)
+      sold[i] = __float2half2_rn(0.f);
+      if (p.s_mode == 1) sold[i] = *reinterpret_cast<const __half2*>(p.Sc + (long long)(pos0 + rg + RG * i) * p.ldd + cb_ld);
     }
     double2 l0[H], u0[H], l1[H], u1[H];
     load_bounds(0, row_of, k0, k1, vec, l0, u0);
     // 2. first half
 #pragma unroll
-    for (int j = 0; j < H; ++j) update_row(j, cbase, row_of(j), x[j], v[j], e[j], l0[j], u0[j]);
+    for (int j = 0; j < H; ++j) update_row(j, cbase, row_of(j), x[j], v[j], e[j], l0[j], u0[j], sold[j]);
     // 3. bounds of the second half are in flight while the first half is stored
     load_bounds(1, row_of, k0, k1, vec, l1, u1);
     // 4.
@@ -222,7 +241,7 @@ struct EpiDelta {
     for (int j = 0; j < H; ++j) store_row(row_of(j), cbase, x[j], v[j], e[j]);
     // 5. second half
 #pragma unroll
-    for (int j = 0; j < H; ++j) update_row(H + j, cbase, row_of(H + j), x[H + j], v[H + j], e[H + j], l1[j], u1[j]);
+    for (int j = 0; j < H; ++j) update_row(H + j, cbase, row_of(H + j), x[H + j], v[H + j], e[H + j], l1[j], u1[j], sold[H + j]);
     // 6.
 #pragma unroll
     for (int j = 0; j < H; ++j) store_row(row_of(H + j), cbase, x[H + j], v[H + j], e[H + j]);
@@ -231,12 +250,22 @@ struct EpiDelta {
   // rows that do not take part run on zeros (no branch around the arithmetic: the H rows of a half interleave); the
   // fp16 increment goes straight to the operand the next pass reads
   __device__ __forceinline__ void update_row(int i, int cbase, int row, double2& x, double2& v, float2& e, const double2& l,
-                                             const double2& u) {
+                                             const double2& u, const __half2& sold) {
     const int r = rg + RG * i;
     const lp::EpiRowInfo ri = sm->info[r];
     __half2 q;
     pair(x, v, e, sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], l, u, ri, q, dmax[i], row >= 0);
-    if (row >= 0) *reinterpret_cast<__half2*>(p.Dn + (long long)ri.pw * p.ldd + cbase) = q;
+    if (row >= 0) {
+      const long long o = (long long)ri.pw * p.ldd + cbase;
+      *reinterpret_cast<__half2*>(p.Dn + o) = q;
+      if (p.s_mode) {      // pending sum of the second operator term: S+ = S + g dq, saturating (what saturates is lost to
+                           // the fp16 path only: the exact check certifies every returned point)
+        const float2 so = __half22float2(sold), qf = __half22float2(q);
+        const float s0 = fminf(fmaxf(fmaf(qf.x, ri.g, so.x), -65504.f), 65504.f);
+        const float s1 = fminf(fmaxf(fmaf(qf.y, ri.g, so.y), -65504.f), 65504.f);
+        *reinterpret_cast<__half2*>(p.Sn + o) = __floats2half2_rn(s0, s1);
+      }
+    }
   }
   __device__ __forceinline__ void store_row(int row, int cbase, const double2& x, const double2& v, const float2& e) const {
     if (row < 0 || (NNMPC_PROBE_NOSTORE && x.x != 123.456)) return;
@@ -245,52 +274,6 @@ struct EpiDelta {
     __stcs(reinterpret_cast<double2*>(p.V + base), v);
     __stcs(reinterpret_cast<float2*>(p.E + base), e);
   }
-#else
-  // round-2h form (one row iteration at a time), kept for A/B runs of the probe
-  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
-    // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
-#pragma unroll
-    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
-    __syncwarp();
-    const int cbase = col0 + 2 * cp;       // this lane's column pair; n is even: the pair is inside when its first column is
-    const bool in = cbase < N;
-    // the chunk (col0 is a multiple of CW) lies inside one stage when the stage width is a multiple of CW
-    const int k0 = cbase % p.nu;
-    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;
-    double2 x[NI], v[NI];
-    float2 e[NI];
-    // all state loads of the step first (streaming: read once per pass)
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int row = sm->info[rg + RG * i].row;
-      if (row >= 0 && in) {
-        const long long base = (long long)row * p.n + cbase;
-        x[i] = __ldcs(reinterpret_cast<const double2*>(p.X + base));
-        v[i] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
-        e[i] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int r = rg + RG * i;
-      const lp::EpiRowInfo ri = sm->info[r];
-      if (ri.row >= 0 && in) {
-        const long long base = (long long)ri.row * p.n + cbase;
-        const double* lbr = p.lb + (long long)ri.row * p.nu;
-        const double* ubr = p.ub + (long long)ri.row * p.nu;
-        const double2 l = make_double2(lbr[k0], lbr[k1]);      // k1 wraps to stage input 0 when nu is odd
-        const double2 u = make_double2(ubr[k0], ubr[k1]);
-        __half2 q;
-        pair(x[i], v[i], e[i], sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], l, u, ri, q, dmax[i]);
-        __stcs(reinterpret_cast<double2*>(p.X + base), x[i]);
-        __stcs(reinterpret_cast<double2*>(p.V + base), v[i]);
-        __stcs(reinterpret_cast<float2*>(p.E + base), e[i]);
-        *reinterpret_cast<__half2*>(p.Dn + (long long)ri.pw * p.ldd + cbase) = q;
-      }
-    }
-    __syncwarp();            // stg is rewritten by the next step
-  }
-#endif
   // L2 prefetch of the state of the NEXT chunk of this warp (lane = row): the loads of a chunk are one exposed DRAM round
   // trip per chunk and warp, and with two warps per scheduler nothing else covers it.  No registers held.
   __device__ __forceinline__ void prefetch(int col0, int N) const {
@@ -324,12 +307,73 @@ struct EpiDelta {
       }
       const int row = sm->info[rg + RG * i].row;
       if (cp == 0 && row >= 0) {
+        // (every column tile of the row writes the same value)
+        if (p.s_mode == 2) p.sS[row] = 0.125 * sm->info[rg + RG * i].s_out;
         double md = (double)m;
         if (!(m <= 3.0e38f)) md = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
         atomicMax(p.dres + row, (unsigned long long)__double_as_longlong(md));
       }
     }
   }
+};
+
+// ---- delivery of the deferred second operator term:  x += T2 S / (s_T sS)  for the iterating rows ----------------
+// Same warp-collective shape as EpiDelta (transpose through shared memory, one warp instruction = 4 rows x 128 bytes).
+struct EpiAddX {
+  struct Params {
+    double* X;
+    const int* state;
+    int iter_state;
+    const int* list_r;   // operand position -> sample row; null = identity
+    const double* sS;    // per sample row: scale of its pending sum
+    int n;
+    double inv_sT;
+  };
+  static constexpr int LPR = lp::CW / 2, RG = 32 / LPR, NI = 32 / RG;
+  Params p;
+  lp::EpiWarpSmem* sm;
+  int lane, rg, cp;
+  __device__ EpiAddX(const Params& p_, lp::EpiWarpSmem* sm_, int lane_)
+      : p(p_), sm(sm_), lane(lane_), rg(lane_ / LPR), cp(lane_ % LPR) {}
+  __device__ void begin_tile(int pos0, int M) {
+    const int pos = pos0 + lane;
+    lp::EpiRowInfo ri;
+    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.pad = 0;
+    if (pos < M) {
+      const int row = p.list_r ? p.list_r[pos] : pos;
+      if (p.state[row] == p.iter_state) {
+        ri.row = row;
+        ri.inv_in = p.inv_sT / p.sS[row];
+      }
+    }
+    __syncwarp();
+    sm->info[lane] = ri;
+    __syncwarp();
+  }
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
+#pragma unroll
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
+    __syncwarp();
+    const int cbase = col0 + 2 * cp;
+    const bool in = cbase < N;
+    double2 x[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int row = in ? sm->info[rg + RG * i].row : -1;
+      x[i] = *reinterpret_cast<const double2*>(p.X + (long long)(row >= 0 ? row : 0) * p.n + (in ? cbase : 0));
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int r = rg + RG * i;
+      const int row = in ? sm->info[r].row : -1;
+      const double inv = sm->info[r].inv_in;
+      x[i].x += (double)sm->stg[(2 * cp) * lp::STG_LD + r] * inv;
+      x[i].y += (double)sm->stg[(2 * cp + 1) * lp::STG_LD + r] * inv;
+      if (row >= 0) *reinterpret_cast<double2*>(p.X + (long long)row * p.n + cbase) = x[i];
+    }
+    __syncwarp();
+  }
+  __device__ void end_tile() {}
 };
 
 // plain store (self test): C = scale * acc
@@ -418,7 +462,8 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
            double* __restrict__ W, float* __restrict__ E, __half* __restrict__ D, long long ldd,
            const double* __restrict__ lb, const double* __restrict__ ub, double* __restrict__ sc_in,
            double* __restrict__ sc_out, int* __restrict__ state, int* __restrict__ it, int iter_state, int n, int nu,
-           double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
+           double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2, __half* __restrict__ S,
+           double* __restrict__ sS) {
   __shared__ double red[2][8];
   const int cnt = *count;
   for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
@@ -456,10 +501,13 @@ k_dr_first(const int* __restrict__ rows, const int* __restrict__ count, double* 
   const long long dpos = pos_r ? pos_r[s] : s;      // row of the operand buffer the next pass reads for this sample
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     float e;
-    D[dpos * ldd + j] = quantise_dw(W[s * n + j], sq, inv, e);
+    const __half q = quantise_dw(W[s * n + j], sq, inv, e);
+    D[dpos * ldd + j] = q;
+    if (S) S[dpos * ldd + j] = __float2half_rn(0.125f * __half2float(q));    // deferred second term: the pending sum starts
     E[s * n + j] = e;
   }
   if (threadIdx.x == 0) {
+    if (sS) sS[s] = 0.125 * sq;
     sc_in[s] = sq;
     sc_out[s] = pow2_scale(3.0 * alpha * dmax);
     state[s] = iter_state;
@@ -500,7 +548,8 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
           int iter_state, const double* __restrict__ V, double* __restrict__ WL, float* __restrict__ E,
           __half* __restrict__ D, long long ldd, const double* __restrict__ lb, const double* __restrict__ ub,
           double* __restrict__ sc_in, double* __restrict__ sc_out, const double* __restrict__ dtrig, int n, int nu,
-          double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2) {
+          double alpha, const int* __restrict__ pos_r, unsigned char* __restrict__ need2, __half* __restrict__ S,
+          double* __restrict__ sS) {
   __shared__ double red[8];
   const int cnt = *count;
   for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
@@ -531,9 +580,11 @@ k_lp_emit(const int* __restrict__ rows, const int* __restrict__ count, int* __re
     float e;
     const __half q = quantise_dw(WL[s * n + j], sq, inv, e);
     if (dpos >= 0) D[dpos * ldd + j] = q;
+    if (S && dpos >= 0) S[dpos * ldd + j] = __float2half_rn(0.125f * __half2float(q));
     E[s * n + j] = e;
   }
   if (threadIdx.x == 0) {
+    if (sS) sS[s] = 0.125 * sq;
     sc_in[s] = sq;
     sc_out[s] = pow2_scale(3.0 * alpha * (dtrig[s] + wmax));
     state[s] = iter_state;

@@ -68,7 +68,8 @@ struct nnmpc_sim {
   nnmpc::DevBuf<double> dlast;      // last ||d|| per slot
   nnmpc::DevBuf<unsigned char> need2;   // per 128-row operand tile: both operator terms needed in the next pass
   double t2_factor;                 // a row is "late" when ||d|| <= t2_factor * tol (0: never skip the second term)
-  unsigned long long* tile_stat;    // device: tensor-core tiles run with [0] one, [1] both operator terms (cumulative)
+  int t2_every;                     // mixed mode: second fp16 operator term delivered every t2_every-th pass (0: every pass, fused)
+  unsigned long long* tile_stat;    // device: tensor-core tiles run with [0] one, [1] both operator terms, [2] second-term delivery tiles (cumulative)
   unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks, [2] QPs whose optimum has active bounds, [3] active bounds in total
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps, tot_qps_active, tot_active;   // since create (host)
   nnmpc::DevBuf<unsigned long long> dres, kres;
@@ -356,6 +357,7 @@ k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, con
                 unsigned long long* __restrict__ stats) {
   extern __shared__ double adv_in[];          // ADV_ROWS x kin_ld
   __shared__ double red[8];
+  __shared__ int row_act[ADV_ROWS];
   const int cnt = *count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int g0 = blockIdx.x * ADV_ROWS; g0 < cnt; g0 += gridDim.x * ADV_ROWS) {
@@ -379,21 +381,33 @@ k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, con
       }
       adv_in[idx] = v;
     }
-    for (int r = 0; r < nr; ++r) {
+    {  // workload statistics: how constrained the optimum is (z = clip(v) sits exactly on an active bound).  One flat
+       // loop over the group's rows x n elements: independent, coalesced loads (a per-row loop with a block-wide vote
+       // per row serialised 8 x 18 dependent load rounds and was most of this kernel's time)
+      if (threadIdx.x < ADV_ROWS) row_act[threadIdx.x] = 0;
+      __syncthreads();
+      int na = 0;
+      const int total = nr * n;
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int r = idx / n, j = idx - r * n;
+        const long long s = rows[g0 + r];
+        const double z = Z[s * n + j];
+        const bool act = z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)];
+        if (act) { ++na; row_act[r] = 1; }
+      }
+      na = __reduce_add_sync(0xffffffffu, na);
+      if (lane == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int nrow = 0;
+        for (int r = 0; r < nr; ++r) nrow += row_act[r];
+        if (nrow) atomicAdd(stats + 2, (unsigned long long)nrow);
+      }
+    }
+    for (int r = 0; r < nr && (cap_useq || cap_cost); ++r) {
       const long long s = rows[g0 + r];
       const long long o = (long long)chunk[s] * T + tcur[s];
-      {  // workload statistics: how constrained the optimum is (z = clip(v) sits exactly on an active bound)
-        int na = 0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-          const double z = Z[s * n + j];
-          na += (z <= lb[s * nu + (j % nu)] || z >= ub[s * nu + (j % nu)]) ? 1 : 0;
-        }
-        if (__syncthreads_or(na > 0)) {
-          na = __reduce_add_sync(0xffffffffu, na);
-          if (lane == 0 && na > 0) atomicAdd(stats + 3, (unsigned long long)na);
-          if (threadIdx.x == 0) atomicAdd(stats + 2, 1ull);
-        }
-      }
       if (cap_useq)
         for (int j = threadIdx.x; j < n; j += blockDim.x) cap_useq[o * n + j] = Z[s * n + j] + us[o * nu + (j % nu)];
       if (cap_cost) {
@@ -789,6 +803,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     if (!q->rinv)
       return set_error(NNMPC_ERR_BADARG, "mixed precision needs the ADMM penalty vector: call nnmpc_qp_set_penalty first");
     if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
+    h->lps.defer2 = h->t2_every > 0 && !(h->t2_factor > 0.0);      // (one-term tiles by row phase are the other, older scheme)
     NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n, st));
     if (h->exact_oz) {
       if (!q->ozP.ready) NNMPC_TRY(oz_slice_operator(q->P, n, n, &q->ozP, st));
@@ -881,6 +896,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
   // over the rows that accumulated meanwhile - those rows sit out at most cad-1 tensor-core passes, and the FP64
   // GEMMs and the small kernels around them see cad times longer row lists
   const int cad = mixed ? (h->cadence > 1 ? h->cadence : 1) : 1;
+  // deferred second operator term: delivery passes fall on full loops (right after the anchors of new QPs, whose first
+  // - largest - increment is then corrected in the same loop), every m2-th loop
+  const int m2 = (mixed && h->lps.defer2) ? (h->t2_every + cad - 1) / cad * cad : 0;
   long long polls = 0;
   const long long max_loops = ((long long)T * ((long long)max_iter + 2) * ((Btot + B - 1) / B) + 8) * cad;
   int rc_warn = 0;
@@ -912,8 +930,16 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       // 1b. tensor-core pass (tcgen05, fp16 increments of the operand, state in FP64) over every live row
       ProfSpan span;
       const bool prof = prof_begin(&span, st);
+      int s_mode = 0;
+      if (m2) {
+        s_mode = 1;
+        if (loop % m2 == 0) {
+          NNMPC_TRY(lp_correct(&q->lpop, &h->lps, B, list_r, e.counts + E_LP, e.state, SLOT_ITER, h->device, st, h->tile_stat + 2));
+          s_mode = 2;
+        }
+      }
       NNMPC_TRY(lp_iterate(&q->lpop, &h->lps, B, list_r, e.counts + E_LP, pos_w, h->V.p, h->lb.p, h->ub.p, e.state,
-                           SLOT_ITER, e.dres, nu, q->alpha, h->device, st, e.need2, h->tile_stat));
+                           SLOT_ITER, e.dres, nu, q->alpha, h->device, st, e.need2, h->tile_stat, s_mode));
       pos_next = pos_w;
       if (prof) prof_end(span, st, 0.0, 1);
       // 1c. tail: with few live rows left the same update runs as skinny FP64 GEMMs (counts[E_TAIL] rows, else 0)
@@ -1063,6 +1089,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
+  h->t2_every = 8;          // measured (profiles/r02o/p): 4 -> +12 %, 8 -> +16 %, 12 -> +17 %, 16 -> +11 % sim-steps/s over the fused form;
+                            // iterations and exact checks per QP are unchanged up to 8 and start to grow at 12
   h->t2_factor = 0.0;       // one-term tiles off: measured share of such tiles 0.4 - 6 % (rows restart inside late tiles), no gain
   h->tile_stat = nullptr;
   h->tot_rowiters = h->tot_anchors = h->tot_verifies = h->tot_qps = h->tot_qps_active = h->tot_active = 0;
@@ -1090,8 +1118,8 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   if (rc == 0) cu(cudaMalloc((void**)&h->rowiters, 2 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMalloc((void**)&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc");
   if (rc == 0) cu(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
-  if (rc == 0) cu(cudaMalloc((void**)&h->tile_stat, 2 * sizeof(unsigned long long)), "cudaMalloc");
-  if (rc == 0) cu(cudaMemset(h->tile_stat, 0, 2 * sizeof(unsigned long long)), "cudaMemset");
+  if (rc == 0) cu(cudaMalloc((void**)&h->tile_stat, 4 * sizeof(unsigned long long)), "cudaMalloc");
+  if (rc == 0) cu(cudaMemset(h->tile_stat, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
   if (rc == 0) cu(cudaMallocHost((void**)&h->pin, POLL_RING * N_COUNTERS * sizeof(int) + 8 * sizeof(unsigned long long)), "cudaMallocHost");
   for (int i = 0; i < POLL_RING && rc == 0; ++i) cu(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming), "cudaEventCreate");
   if (rc < 0) {          // a half-built handle is released, not leaked
@@ -1182,12 +1210,20 @@ int nnmpc_sim_set_one_term_threshold(nnmpc_sim_t* h, double factor) {
   return 0;
 }
 
-int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out2) {
-  if (!h || !out2) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_tile_stats: null argument");
+int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out3) {
+  if (!h || !out3) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_tile_stats: null argument");
   DeviceGuard dg(h->device);
-  unsigned long long t[2] = {0, 0};
+  unsigned long long t[3] = {0, 0, 0};
   NNMPC_CUDA(cudaMemcpy(t, h->tile_stat, sizeof(t), cudaMemcpyDeviceToHost));
-  out2[0] = (long long)t[0]; out2[1] = (long long)t[1];
+  out3[0] = (long long)t[0]; out3[1] = (long long)t[1]; out3[2] = (long long)t[2];
+  return 0;
+}
+
+int nnmpc_sim_set_second_term_cadence(nnmpc_sim_t* h, int every) {
+  if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_second_term_cadence: null handle");
+  if (every < 0 || every > 64) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_second_term_cadence: need 0 <= every <= 64");
+  h->t2_every = every;
+  h->warm_B = 0;        // the next run starts from cold operand buffers (pending sums are allocated on demand)
   return 0;
 }
 

@@ -726,12 +726,20 @@ class ClosedLoopEngine:
         if os.environ.get("NNMPC_EXACT_GEMM"):      # "dmma" = FP64 tensor cores, "int8" (default) = sliced INT8 tcgen05
             mode = {"dmma": 0, "int8": 1}[os.environ["NNMPC_EXACT_GEMM"]]
             _lib.check(L.nnmpc_sim_set_exact_gemm(self._handle, mode), "nnmpc_sim_set_exact_gemm")
+        if os.environ.get("NNMPC_T2_EVERY"):        # second fp16 operator term every k-th pass (0 = fused into every pass)
+            _lib.check(L.nnmpc_sim_set_second_term_cadence(self._handle, int(os.environ["NNMPC_T2_EVERY"])),
+                       "nnmpc_sim_set_second_term_cadence")
         if os.environ.get("NNMPC_T2_FACTOR"):       # late-phase threshold of the one-term tensor-core tiles (0 = off)
             _lib.check(L.nnmpc_sim_set_one_term_threshold(self._handle, float(os.environ["NNMPC_T2_FACTOR"])),
                        "nnmpc_sim_set_one_term_threshold")
         tail_rows = os.environ.get("NNMPC_TAIL_ROWS") if tail_rows is None else tail_rows
         if tail_rows is not None:     # mixed mode: live rows at or below which a call finishes in FP64 (-1 = automatic)
             _lib.check(L.nnmpc_sim_set_tail_rows(self._handle, int(tail_rows)), "nnmpc_sim_set_tail_rows")
+
+    def set_second_term_cadence(self, every):
+        """Mixed precision: the second fp16 operator term is delivered every ``every``-th tensor-core pass (default 8);
+        0 = both terms in every pass."""
+        _lib.check(_lib.lib().nnmpc_sim_set_second_term_cadence(self._handle, int(every)), "nnmpc_sim_set_second_term_cadence")
 
     def set_slots(self, slots):
         """Most trajectories advanced concurrently; a run with more chunks queues the rest (continuous batching)."""
@@ -751,10 +759,11 @@ class ClosedLoopEngine:
         _lib.check(_lib.lib().nnmpc_sim_stats(self._handle, out), "nnmpc_sim_stats")
         act = (C.c_longlong * 2)()
         _lib.check(_lib.lib().nnmpc_sim_active_stats(self._handle, act), "nnmpc_sim_active_stats")
-        til = (C.c_longlong * 2)()
+        til = (C.c_longlong * 3)()
         _lib.check(_lib.lib().nnmpc_sim_tile_stats(self._handle, til), "nnmpc_sim_tile_stats")
         return dict(row_iterations=out[0], anchors=out[1], exact_checks=out[2], qps=out[3],
-                    qps_with_active_bounds=act[0], active_bounds=act[1], tiles_one_term=til[0], tiles_two_terms=til[1])
+                    qps_with_active_bounds=act[0], active_bounds=act[1], tiles_one_term=til[0], tiles_two_terms=til[1],
+                    tiles_second_term_delivery=til[2])
 
     def __del__(self):
         try:

@@ -112,11 +112,13 @@ def cdu_full(torch_cuda):
     return p, sim, sp.reshape(len(STARTS), T_STEPS, -1), ds.reshape(len(STARTS), T_STEPS, -1), datas
 
 
-@pytest.mark.parametrize("precision", ["mixed-notail", "mixed-tail3", "mixed", "f64"])
+@pytest.mark.parametrize("precision", ["mixed-notail", "mixed-fused-notail", "mixed-every4-notail", "mixed-tail3", "mixed", "f64"])
 def test_full_cdu_closed_loop_matches_oracle(cdu_full, precision):
     """n = 4480, Nu = 32, against BoxQP / the (xs, us)-space target selector:
-    "mixed-notail"  every iteration on lp_gemm_kernel<EpiDelta> (tcgen05 fp16, 35 column tiles), anchors and KKT
+    "mixed-notail"  every iteration on lp_gemm_kernel<EpiDelta> (tcgen05 fp16, 35 column tiles; one operator term per
+                    pass, the second delivered every 8th pass by lp_gemm_kernel<EpiAddX>), anchors and KKT
                     checks on oz_gemm2_kernel (INT8 tcgen05), to the last live row;
+    "mixed-fused-notail" / "mixed-every4-notail"  the same with both terms in every pass / delivery every 4th pass;
     "mixed-tail3"   the same until three trajectories are left, then the FP64 tail (the hand-over the bench runs);
     "mixed"         default tail rule: six trajectories are below it, so the FP64 tail kernels do all iterations
                     and only the KKT checks run on the INT8 tier;
@@ -127,10 +129,20 @@ def test_full_cdu_closed_loop_matches_oracle(cdu_full, precision):
     eng = sim.engine
     eng.set_precision("f64" if precision == "f64" else "mixed")
     from industrial_nnmpc_2021_b200 import _lib
-    tail = {"mixed-notail": 0, "mixed-tail3": 3}.get(precision, -1)
+    tail = {"mixed-notail": 0, "mixed-fused-notail": 0, "mixed-every4-notail": 0, "mixed-tail3": 3}.get(precision, -1)
     _lib.check(_lib.lib().nnmpc_sim_set_tail_rows(eng._handle, tail), "nnmpc_sim_set_tail_rows")
+    eng.set_second_term_cadence({"mixed-fused-notail": 0, "mixed-every4-notail": 4}.get(precision, 8))
+    st0 = eng.stats()
     res = eng.run(p.xprior, p.uprev, sp, ds, capture=True)
     assert not res["maxiter_hit"]
+    st1 = eng.stats()
+    if precision.endswith("notail"):      # the tensor-core passes did run, in the form asked for
+        d1, d2, dc = (st1[k] - st0[k] for k in ("tiles_one_term", "tiles_two_terms", "tiles_second_term_delivery"))
+        if precision == "mixed-fused-notail":
+            assert d2 > 0 and d1 == 0 and dc == 0, (d1, d2, dc)
+        else:
+            assert d1 > 0 and d2 == 0 and 0 < dc <= d1, (d1, d2, dc)
+    eng.set_second_term_cadence(8)
     worst = _check_against_oracle(p, sim.regulator, res, datas, precision)
     print(f"\nfull CDU ({precision}): n_active per QP {nact}; worst rel. err u0 {worst['u0']:.2e}, useq "
           f"{worst['useq']:.2e}, cost {worst['cost']:.2e}, xs {worst['xs']:.2e}, us {worst['us']:.2e}; "

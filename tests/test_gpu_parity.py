@@ -268,19 +268,23 @@ def test_oz_int8_gemm_is_fp64_accurate(torch_cuda, M, N, K):
 
 
 # ------------------------------------------------------------------------------------ closed loop
-@pytest.fixture(params=["f64", "mixed", "mixed-notail", "mixed-oneterm"])
+@pytest.fixture(params=["f64", "mixed", "mixed-notail", "mixed-fused", "mixed-oneterm"])
 def precision(request, monkeypatch):
     """Arithmetic of the closed-loop iteration: FP64 DMMA, or tcgen05 fp16 increments + FP64 anchors - with the
-    automatic switch to skinny FP64 GEMMs for the last few live rows ("mixed"), or tensor-core passes to the end
-    with both fp16 operator terms on every tile ("mixed-notail": a row's arithmetic is then independent of its
-    neighbours) or with one-term tiles for late-phase rows at an aggressive threshold ("mixed-oneterm")."""
+    automatic switch to skinny FP64 GEMMs for the last few live rows ("mixed"), or tensor-core passes to the end:
+    "mixed-notail"  the default form: one fp16 operator term per pass, the second delivered every 8th pass from the
+                    pending sums (lp_iter.cuh, deferred second term) - a row's arithmetic is independent of its neighbours;
+    "mixed-fused"   both operator terms in every pass (the round-1 form, NNMPC_T2_EVERY=0);
+    "mixed-oneterm" both terms, except one-term tiles for late-phase rows at an aggressive threshold."""
     monkeypatch.setenv("NNMPC_PRECISION", request.param.split("-")[0])
-    if request.param in ("mixed-notail", "mixed-oneterm"):
+    for k in ("NNMPC_TAIL_ROWS", "NNMPC_T2_FACTOR", "NNMPC_T2_EVERY"):
+        monkeypatch.delenv(k, raising=False)
+    if request.param in ("mixed-notail", "mixed-fused", "mixed-oneterm"):
         monkeypatch.setenv("NNMPC_TAIL_ROWS", "0")
-        monkeypatch.setenv("NNMPC_T2_FACTOR", "0" if request.param == "mixed-notail" else "10000")
-    else:
-        monkeypatch.delenv("NNMPC_TAIL_ROWS", raising=False)
-        monkeypatch.delenv("NNMPC_T2_FACTOR", raising=False)
+    if request.param == "mixed-oneterm":
+        monkeypatch.setenv("NNMPC_T2_FACTOR", "10000")
+    if request.param == "mixed-fused":
+        monkeypatch.setenv("NNMPC_T2_EVERY", "0")
     return request.param
 
 

@@ -31,9 +31,10 @@ def sampler():
 
 th = threading.Thread(target=sampler, daemon=True)
 th.start()
-ms = (C.c_float * 4)()
+ms = (C.c_float * 8)()
 _lib.check(L.nnmpc_lp_pass_probe(B, n, 5, ms), "warm-up")
-for only, name, reps in ((0, "full pass", 1200), (1, "main loop only", 1800), (2, "epilogue only", 2000), (0, "full pass", 1200)):
+for only, name, reps in ((0, "full pass (two terms)", 1200), (1, "main loop only (two terms)", 1800), (2, "epilogue only", 2000),
+                         (3, "one-term pass", 1500), (4, "second-term delivery GEMM", 2500), (0, "full pass (two terms)", 1200)):
     os.environ["NNMPC_PROBE_ONLY"] = str(only)
     time.sleep(1.0)
     t0 = time.time()

@@ -16,9 +16,11 @@ sizes = ((16384, 4480), (8192, 4480), (16384, 8960), (16384, 540))
 if len(sys.argv) > 1:
     sizes = tuple(tuple(int(v) for v in a.split("x")) for a in sys.argv[1:])
 for B, n in sizes:
-    ms = (C.c_float * 4)()
+    ms = (C.c_float * 8)()
     _lib.check(L.nnmpc_lp_pass_probe(B, n, 10, ms), "nnmpc_lp_pass_probe")
     fl = 2.0 * n * n * B
     print(f"B={B} n={n}: full pass {ms[0]:.3f} ms ({fl / ms[0] / 1e9:.0f} TFLOP/s algorithmic), main loop only {ms[1]:.3f} ms "
           f"({fl / ms[1] / 1e9:.0f} TFLOP/s; executed MMA {2 * fl / ms[1] / 1e9:.0f} TFLOP/s), epilogue only {ms[2]:.3f} ms "
-          f"({42.0 * B * n / ms[2] / 1e9:.2f} TB/s of state) -> the epilogue exposes {100 * (ms[0] - ms[1]) / ms[0]:.0f} % of the pass")
+          f"({42.0 * B * n / ms[2] / 1e9:.2f} TB/s of state) -> the epilogue exposes {100 * (ms[0] - ms[1]) / ms[0]:.0f} % of the pass; "
+          f"deferred second term: one-term pass {ms[3]:.3f} ms + delivery GEMM {ms[4]:.3f} ms every 4th pass = "
+          f"{ms[3] + ms[4] / 4:.3f} ms per iteration ({fl / (ms[3] + ms[4] / 4) / 1e9:.0f} TFLOP/s algorithmic)")
