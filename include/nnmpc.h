@@ -167,7 +167,8 @@ int nnmpc_sim_tile_stats(nnmpc_sim_t* h, long long* out3);
 /* Mixed mode only: the tensor-core pass multiplies the first fp16 operator term alone, and the second term (a 2^-11
  * relative correction, linear in the increments) is delivered every `every`-th pass for all increments since the last
  * delivery at once, by a one-term GEMM over the pending sums (rounded up to a multiple of the cadence; default 8;
- * 0 = both terms in every pass, the round-1 form).  MMA work per iteration falls from 2 to 1 + 1/every products;
+ * 0 = both terms in every pass, the round-1 form; a handle this is never called on defers only for n >= 1536, below
+ * which the MMAs are a small part of the pass).  MMA work per iteration falls from 2 to 1 + 1/every products;
  * fixed points and the exact KKT certification of every returned point are unchanged. */
 int nnmpc_sim_set_second_term_cadence(nnmpc_sim_t* h, int every);
 /* Optional per-QP sinks for the following nnmpc_sim_run calls (device pointers, either may be NULL; NULL, NULL

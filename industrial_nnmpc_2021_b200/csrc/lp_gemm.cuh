@@ -54,7 +54,9 @@ struct EpiRowInfo {
   int pw;           // operand row written for it
   double inv_in, s_out, inv_out;
   float g;          // deferred second term: scale of the pending-sum operand relative to the operand written now
-  int pad;
+  int boff;         // row * nu: element offset of the row's bounds (row 0 for a row that does not take part)
+  long long xoff;   // row * n: element offset of the row's state (row 0 for a row that does not take part)
+  long long doff;   // pw * ldd: element offset of the operand row written for it
 };
 // leading dimension of the staging block: bank-conflict-free both for the writes (one column, 32 consecutive rows)
 // and for the epilogue's reads (lane = (row group, column pair), see EpiDelta)
@@ -275,6 +277,25 @@ __device__ __forceinline__ auto epi_prefetch(E& e, int col0, int N, int) -> decl
 template <class E>
 __device__ __forceinline__ void epi_prefetch(E&, int, int, long) {}
 
+// optional epilogue forms: prime(col0, N) after begin_tile (start the loads of the tile's first chunk), and
+// chunk(col0, acc, N, next_col0) (next_col0 < 0: last chunk of the row block) for epilogues that pipeline their
+// loads across chunks
+template <class E>
+__device__ __forceinline__ auto epi_prime(E& e, int col0, int N, int) -> decltype(e.prime(col0, N), void()) {
+  e.prime(col0, N);
+}
+template <class E>
+__device__ __forceinline__ void epi_prime(E&, int, int, long) {}
+template <class E>
+__device__ __forceinline__ auto epi_chunk(E& e, int col0, const uint32_t (&acc)[CW], int N, int next_col0, int)
+    -> decltype(e.chunk(col0, acc, N, next_col0), void()) {
+  e.chunk(col0, acc, N, next_col0);
+}
+template <class E>
+__device__ __forceinline__ void epi_chunk(E& e, int col0, const uint32_t (&acc)[CW], int N, int, long) {
+  e.chunk(col0, acc, N);
+}
+
 template <class T, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
@@ -408,6 +429,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int r = 0; r < T::MR; ++r) {
         epi.begin_tile(bm * T::TILE_M + r * BM + q * 32, M);
         epi_prefetch(epi, bn * T::BN + hsel * CW, g.N, 0);
+        epi_prime(epi, bn * T::BN + hsel * CW, g.N, 0);
         if (r == 0) {
           mbar_wait(acc_full + as, aph);
           tc_fence_after();
@@ -419,7 +441,8 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
           if (cc + 1 < T::BN / 32) epi_prefetch(epi, bn * T::BN + (cc + 1) * 32 + hsel * CW, g.N, 0);
           tmem_ld_wait();
-          epi.chunk(bn * T::BN + cc * 32 + hsel * CW, acc, g.N);
+          epi_chunk(epi, bn * T::BN + cc * 32 + hsel * CW, acc, g.N,
+                    cc + 1 < T::BN / 32 ? bn * T::BN + (cc + 1) * 32 + hsel * CW : -1, 0);
         }
         epi.end_tile();
       }
@@ -619,6 +642,7 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int as = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
       epi.begin_tile(bm * 2 * BM + (int)rank * BM + q * 32, M);
+      epi_prime(epi, bn * BN2 + hsel * CW, g.N, 0);
       mbar_wait(acc_full + as, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2);
@@ -627,7 +651,7 @@ lp_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t acc[CW];
         tmem_ld_cw(tacc + (uint32_t)(cc * 32 + hsel * CW), acc);
         tmem_ld_wait();
-        epi.chunk(bn * BN2 + cc * 32 + hsel * CW, acc, g.N);
+        epi_chunk(epi, bn * BN2 + cc * 32 + hsel * CW, acc, g.N, cc + 1 < BN2 / 32 ? bn * BN2 + (cc + 1) * 32 + hsel * CW : -1, 0);
       }
       epi.end_tile();
       tc_fence_before();

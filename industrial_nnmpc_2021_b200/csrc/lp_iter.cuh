@@ -127,7 +127,7 @@ struct EpiDelta {
     pos0 = pos0_;
     const int pos = pos0 + lane;
     lp::EpiRowInfo ri;
-    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.pad = 0;
+    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.boff = 0; ri.xoff = 0; ri.doff = 0;
     if (pos < M) {
       const int row = p.list_r ? p.list_r[pos] : pos;
       if (p.state[row] == p.iter_state) {
@@ -139,6 +139,9 @@ struct EpiDelta {
         // a new sum is kept at 1/8 of the operand scale: head room for the increments that follow
         if (p.s_mode == 2) ri.g = 0.125f;
         else if (p.s_mode == 1) ri.g = (float)(p.sS[row] * ri.inv_out);
+        ri.boff = row * p.nu;
+        ri.xoff = (long long)row * p.n;
+        ri.doff = (long long)ri.pw * p.ldd;
       }
     }
     __syncwarp();            // the previous tile's last reads of info[] are done
@@ -164,115 +167,107 @@ struct EpiDelta {
     const float a = (float)((d0 <= d1) ? d1 : d0);       // NaN propagates
     dm = (!valid || a <= dm) ? dm : a;                   // lanes that ran on a stand-in row must not touch the residual
   }
-  // Bounds of one half of the chunk's rows (H = NI / 2 row iterations): issued together, ahead of their use.
-  // lb / ub rows are 16-byte aligned pairs when nu is even (vec); an odd nu wraps k1 to stage input 0.
-  static constexpr int H = NI / 2;
-  template <class RowOf>
-  __device__ __forceinline__ void load_bounds(int h, const RowOf& row_of, int k0, int k1, bool vec, double2 (&l)[H],
-                                              double2 (&u)[H]) const {
+
+  // ---- the chunk as a software pipeline over QUARTERS (QR = NI / 4 row iterations = 2 rows x 2 columns per lane) ----
+  // The loads of a quarter (state, pending sum, bounds: 38 registers) are issued one quarter ahead of their use, across
+  // chunk boundaries, so every DRAM / L2 round trip is covered by the arithmetic of the quarter before it; an L2
+  // prefetch runs one chunk ahead of that.  History (profiles/r02n_pass_energy_diagnosis.md, r02p_*): the per-row loop
+  // of round 2h paid one exposed bounds round trip per row; loads under `if (row >= 0)` were serialised by the
+  // compiler's placement of the conversions; with everything loaded at the top of the chunk the pass was still one
+  // exposed round trip per chunk and warp (epilogue alone 0.88 ms against 0.47 ms without its loads).
+  // Rows that do not take part (and lanes beyond N) read row 0 / column 0 and are dropped at the stores.
+  static constexpr int QR = NI / 4;
+  struct QLoad {
+    double2 x[QR], v[QR], l[QR], u[QR];
+    float2 e[QR];
+    __half2 so[QR];
+  };
+  QLoad qa;                // the quarter in flight between two chunk() calls
+  template <int QI>
+  __device__ __forceinline__ void issue(int col0, int N, QLoad& q) const {
+    const int cbase = col0 + 2 * cp;       // n is even: the pair is inside when its first column is
+    const int cb = cbase < N ? cbase : 0;
+    // the chunk (col0 is a multiple of CW) lies inside one stage when the stage width is a multiple of CW
+    const int k0 = cb % p.nu;
+    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;          // wraps to stage input 0 when nu is odd
+    const bool vec = (p.nu & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.lb) | reinterpret_cast<uintptr_t>(p.ub)) & 15) == 0;
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-      const int r = row_of(h * H + j);
-      const double* lbr = p.lb + (long long)(r >= 0 ? r : 0) * p.nu;
-      const double* ubr = p.ub + (long long)(r >= 0 ? r : 0) * p.nu;
+    for (int j = 0; j < QR; ++j) {
+      const int r = rg + RG * (QI * QR + j);
+      const long long base = sm->info[r].xoff + cb;
+#if NNMPC_PROBE_NOLOAD
+      q.x[j] = make_double2(0.0, (double)base * 1e-300);
+      q.v[j] = make_double2(0.0, 0.0);
+      q.e[j] = make_float2(0.f, 0.f);
+#else
+      q.x[j] = __ldcs(reinterpret_cast<const double2*>(p.X + base));
+      q.v[j] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
+      q.e[j] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
+#endif
+      // pending sum of this row and column pair (operand position = tile row; the buffers are padded to whole tiles)
+      q.so[j] = __float2half2_rn(0.f);
+      if (p.s_mode == 1) q.so[j] = *reinterpret_cast<const __half2*>(p.Sc + (long long)(pos0 + r) * p.ldd + cb);
+      const double* lbr = p.lb + sm->info[r].boff;
+      const double* ubr = p.ub + sm->info[r].boff;
       if (vec) {
-        l[j] = __ldg(reinterpret_cast<const double2*>(lbr + k0));
-        u[j] = __ldg(reinterpret_cast<const double2*>(ubr + k0));
+        q.l[j] = __ldg(reinterpret_cast<const double2*>(lbr + k0));
+        q.u[j] = __ldg(reinterpret_cast<const double2*>(ubr + k0));
       } else {
-        l[j] = make_double2(__ldg(lbr + k0), __ldg(lbr + k1));
-        u[j] = make_double2(__ldg(ubr + k0), __ldg(ubr + k1));
+        q.l[j] = make_double2(__ldg(lbr + k0), __ldg(lbr + k1));
+        q.u[j] = make_double2(__ldg(ubr + k0), __ldg(ubr + k1));
       }
     }
   }
-  // The chunk is written as explicit phases, in the order the hardware should see them, because the compiler cannot
-  // move a global load across the global stores of an earlier row (they may alias): round 2h's per-row loop loaded the
-  // bounds of row i only after the stores of row i - 1, i.e. paid one exposed L1/L2 round trip per row iteration
-  // (profiles/r02h_ncu_full_lp_gemm.txt: 39 % of the warp samples on the first use of those loads, per-warp IPC 0.1).
-  //   1. all state loads of the chunk + the bounds of the first half   2. update first half (8 independent chains)
-  //   3. bounds of the second half (before the first half's stores)    4. stores first half
-  //   5. update second half                                            6. stores second half
-  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N) {
-    // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
-#pragma unroll
-    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
-    __syncwarp();
-    const int cbase = col0 + 2 * cp;       // this lane's column pair; n is even: the pair is inside when its first column is
+  template <int QI>
+  __device__ __forceinline__ void update_store(int col0, int N, QLoad& q) {
+    const int cbase = col0 + 2 * cp;
     const bool in = cbase < N;
-    // the chunk (col0 is a multiple of CW) lies inside one stage when the stage width is a multiple of CW
-    const int k0 = (in ? cbase : 0) % p.nu;
-    const int k1 = (k0 + 1 == p.nu) ? 0 : k0 + 1;
-    const bool vec = (p.nu & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.lb) | reinterpret_cast<uintptr_t>(p.ub)) & 15) == 0;
-    double2 x[NI], v[NI];
-    float2 e[NI];
-    __half2 sold[NI];
-    // row of iteration i (re-read from shared memory where needed: registers are the scarce resource here)
-    auto row_of = [&](int i) -> int { return in ? sm->info[rg + RG * i].row : -1; };
-    // 1. all state loads (streaming: read once per pass).  Unconditional: a row that does not take part reads row 0
-    //    (always there) and its results are dropped - a conditional load makes the compiler convert the loaded value
-    //    inside the conditional block, i.e. wait for every row's loads before issuing the next row's (measured:
-    //    profiles/r02l_*: eight serialised round trips per chunk).
-    const int cb_ld = in ? cbase : 0;
+    __half2 qh[QR];
+    // no branch around the arithmetic: the rows of a quarter interleave
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int row = row_of(i);
-      const long long base = (long long)(row >= 0 ? row : 0) * p.n + cb_ld;
-#if NNMPC_PROBE_NOLOAD
-      x[i] = make_double2(0.0, (double)base * 1e-300);
-      v[i] = make_double2(0.0, 0.0);
-      e[i] = make_float2(0.f, 0.f);
-#else
-      x[i] = __ldcs(reinterpret_cast<const double2*>(p.X + base));
-      v[i] = __ldcs(reinterpret_cast<const double2*>(p.V + base));
-      e[i] = __ldcs(reinterpret_cast<const float2*>(p.E + base));
-#endif
-      // pending sum of this row and column pair (operand position = tile row; the buffers are padded to whole tiles)
-      sold[i] = __float2half2_rn(0.f);
-      if (p.s_mode == 1) sold[i] = *reinterpret_cast<const __half2*>(p.Sc + (long long)(pos0 + rg + RG * i) * p.ldd + cb_ld);
+    for (int j = 0; j < QR; ++j) {
+      const int r = rg + RG * (QI * QR + j);
+      const lp::EpiRowInfo ri = sm->info[r];
+      pair(q.x[j], q.v[j], q.e[j], sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], q.l[j], q.u[j],
+           ri, qh[j], dmax[QI * QR + j], in && ri.row >= 0);
     }
-    double2 l0[H], u0[H], l1[H], u1[H];
-    load_bounds(0, row_of, k0, k1, vec, l0, u0);
-    // 2. first half
 #pragma unroll
-    for (int j = 0; j < H; ++j) update_row(j, cbase, row_of(j), x[j], v[j], e[j], l0[j], u0[j], sold[j]);
-    // 3. bounds of the second half are in flight while the first half is stored
-    load_bounds(1, row_of, k0, k1, vec, l1, u1);
-    // 4.
-#pragma unroll
-    for (int j = 0; j < H; ++j) store_row(row_of(j), cbase, x[j], v[j], e[j]);
-    // 5. second half
-#pragma unroll
-    for (int j = 0; j < H; ++j) update_row(H + j, cbase, row_of(H + j), x[H + j], v[H + j], e[H + j], l1[j], u1[j], sold[H + j]);
-    // 6.
-#pragma unroll
-    for (int j = 0; j < H; ++j) store_row(row_of(H + j), cbase, x[H + j], v[H + j], e[H + j]);
-    __syncwarp();            // stg is rewritten by the next step
-  }
-  // rows that do not take part run on zeros (no branch around the arithmetic: the H rows of a half interleave); the
-  // fp16 increment goes straight to the operand the next pass reads
-  __device__ __forceinline__ void update_row(int i, int cbase, int row, double2& x, double2& v, float2& e, const double2& l,
-                                             const double2& u, const __half2& sold) {
-    const int r = rg + RG * i;
-    const lp::EpiRowInfo ri = sm->info[r];
-    __half2 q;
-    pair(x, v, e, sm->stg[(2 * cp) * lp::STG_LD + r], sm->stg[(2 * cp + 1) * lp::STG_LD + r], l, u, ri, q, dmax[i], row >= 0);
-    if (row >= 0) {
-      const long long o = (long long)ri.pw * p.ldd + cbase;
-      *reinterpret_cast<__half2*>(p.Dn + o) = q;
+    for (int j = 0; j < QR; ++j) {
+      const int r = rg + RG * (QI * QR + j);
+      if (!in || sm->info[r].row < 0 || (NNMPC_PROBE_NOSTORE && q.x[j].x != 123.456)) continue;
+      const long long base = sm->info[r].xoff + cbase;
+      __stcs(reinterpret_cast<double2*>(p.X + base), q.x[j]);
+      __stcs(reinterpret_cast<double2*>(p.V + base), q.v[j]);
+      __stcs(reinterpret_cast<float2*>(p.E + base), q.e[j]);
+      const long long o = sm->info[r].doff + cbase;
+      *reinterpret_cast<__half2*>(p.Dn + o) = qh[j];       // the fp16 increment goes straight to the operand the next pass reads
       if (p.s_mode) {      // pending sum of the second operator term: S+ = S + g dq, saturating (what saturates is lost to
                            // the fp16 path only: the exact check certifies every returned point)
-        const float2 so = __half22float2(sold), qf = __half22float2(q);
-        const float s0 = fminf(fmaxf(fmaf(qf.x, ri.g, so.x), -65504.f), 65504.f);
-        const float s1 = fminf(fmaxf(fmaf(qf.y, ri.g, so.y), -65504.f), 65504.f);
+        const float g = sm->info[r].g;
+        const float2 so = __half22float2(q.so[j]), qf = __half22float2(qh[j]);
+        const float s0 = fminf(fmaxf(fmaf(qf.x, g, so.x), -65504.f), 65504.f);
+        const float s1 = fminf(fmaxf(fmaf(qf.y, g, so.y), -65504.f), 65504.f);
         *reinterpret_cast<__half2*>(p.Sn + o) = __floats2half2_rn(s0, s1);
       }
     }
   }
-  __device__ __forceinline__ void store_row(int row, int cbase, const double2& x, const double2& v, const float2& e) const {
-    if (row < 0 || (NNMPC_PROBE_NOSTORE && x.x != 123.456)) return;
-    const long long base = (long long)row * p.n + cbase;
-    __stcs(reinterpret_cast<double2*>(p.X + base), x);
-    __stcs(reinterpret_cast<double2*>(p.V + base), v);
-    __stcs(reinterpret_cast<float2*>(p.E + base), e);
+  // start of a row block: the first quarter of its first chunk
+  __device__ __forceinline__ void prime(int col0, int N) { issue<0>(col0, N, qa); }
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N, int next_col0) {
+    // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
+#pragma unroll
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
+    __syncwarp();
+    QLoad qb;
+    issue<1>(col0, N, qb);
+    update_store<0>(col0, N, qa);
+    issue<2>(col0, N, qa);
+    update_store<1>(col0, N, qb);
+    issue<3>(col0, N, qb);
+    update_store<2>(col0, N, qa);
+    if (next_col0 >= 0) issue<0>(next_col0, N, qa);
+    update_store<3>(col0, N, qb);
+    __syncwarp();            // stg is rewritten by the next step
   }
   // L2 prefetch of the state of the NEXT chunk of this warp (lane = row): the loads of a chunk are one exposed DRAM round
   // trip per chunk and warp, and with two warps per scheduler nothing else covers it.  No registers held.
@@ -338,7 +333,7 @@ struct EpiAddX {
   __device__ void begin_tile(int pos0, int M) {
     const int pos = pos0 + lane;
     lp::EpiRowInfo ri;
-    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.pad = 0;
+    ri.row = -1; ri.pw = 0; ri.inv_in = 0.0; ri.s_out = 0.0; ri.inv_out = 0.0; ri.g = 0.f; ri.boff = 0; ri.xoff = 0; ri.doff = 0;
     if (pos < M) {
       const int row = p.list_r ? p.list_r[pos] : pos;
       if (p.state[row] == p.iter_state) {

@@ -69,6 +69,7 @@ struct nnmpc_sim {
   nnmpc::DevBuf<unsigned char> need2;   // per 128-row operand tile: both operator terms needed in the next pass
   double t2_factor;                 // a row is "late" when ||d|| <= t2_factor * tol (0: never skip the second term)
   int t2_every;                     // mixed mode: second fp16 operator term delivered every t2_every-th pass (0: every pass, fused)
+  bool t2_auto;                     // not set by the caller: deferred only where the MMAs weigh (n >= T2_AUTO_MIN_N)
   unsigned long long* tile_stat;    // device: tensor-core tiles run with [0] one, [1] both operator terms, [2] second-term delivery tiles (cumulative)
   unsigned long long* stats;        // device: [0] anchors, [1] exact KKT checks, [2] QPs whose optimum has active bounds, [3] active bounds in total
   long long tot_rowiters, tot_anchors, tot_verifies, tot_qps, tot_qps_active, tot_active;   // since create (host)
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
 // stage, as DenseQPRegulator.solve returns it through get_control_sequence, linearMPC.py:689) and the optimal cost
 // 1/2 z'Pz + q'z = 1/2 z'(g + q) from the gradient g = P z + q of the check that certified z.
 constexpr int ADV_ROWS = 8;
+constexpr int T2_AUTO_MIN_N = 1536;
 __global__ void __launch_bounds__(256)
 k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
                 const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
@@ -803,7 +805,9 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
     if (!q->rinv)
       return set_error(NNMPC_ERR_BADARG, "mixed precision needs the ADMM penalty vector: call nnmpc_qp_set_penalty first");
     if (!q->lpop.ready) NNMPC_TRY(lp_split_operator(q->Top, n, q->top_max, &q->lpop, st));
-    h->lps.defer2 = h->t2_every > 0 && !(h->t2_factor > 0.0);      // (one-term tiles by row phase are the other, older scheme)
+    // (one-term tiles by row phase are the other, older scheme.)  Small QPs keep both terms in every pass: at n = 540 the
+    // MMAs are 15 % of a pass and the pending sums only add epilogue traffic (probe: 0.167 ms fused, 0.189 ms deferred)
+    h->lps.defer2 = h->t2_every > 0 && !(h->t2_factor > 0.0) && (!h->t2_auto || n >= T2_AUTO_MIN_N);
     NNMPC_TRY(lp_state_ensure(&h->lps, h->cap, n, st));
     if (h->exact_oz) {
       if (!q->ozP.ready) NNMPC_TRY(oz_slice_operator(q->P, n, n, &q->ozP, st));
@@ -1089,6 +1093,7 @@ int nnmpc_sim_create(nnmpc_sim_t** out, nnmpc_qp_t* qp, nnmpc_ts_t* ts, int nx, 
   h->cadence = 4;
   h->exact_oz = 1;
   h->cap_useq = h->cap_cost = nullptr;
+  h->t2_auto = true;
   h->t2_every = 8;          // measured (profiles/r02o/p): 4 -> +12 %, 8 -> +16 %, 12 -> +17 %, 16 -> +11 % sim-steps/s over the fused form;
                             // iterations and exact checks per QP are unchanged up to 8 and start to grow at 12
   h->t2_factor = 0.0;       // one-term tiles off: measured share of such tiles 0.4 - 6 % (rows restart inside late tiles), no gain
@@ -1223,6 +1228,7 @@ int nnmpc_sim_set_second_term_cadence(nnmpc_sim_t* h, int every) {
   if (!h) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_second_term_cadence: null handle");
   if (every < 0 || every > 64) return set_error(NNMPC_ERR_BADARG, "nnmpc_sim_set_second_term_cadence: need 0 <= every <= 64");
   h->t2_every = every;
+  h->t2_auto = false;
   h->warm_B = 0;        // the next run starts from cold operand buffers (pending sums are allocated on demand)
   return 0;
 }

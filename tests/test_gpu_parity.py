@@ -272,9 +272,11 @@ def test_oz_int8_gemm_is_fp64_accurate(torch_cuda, M, N, K):
 def precision(request, monkeypatch):
     """Arithmetic of the closed-loop iteration: FP64 DMMA, or tcgen05 fp16 increments + FP64 anchors - with the
     automatic switch to skinny FP64 GEMMs for the last few live rows ("mixed"), or tensor-core passes to the end:
-    "mixed-notail"  the default form: one fp16 operator term per pass, the second delivered every 8th pass from the
-                    pending sums (lp_iter.cuh, deferred second term) - a row's arithmetic is independent of its neighbours;
-    "mixed-fused"   both operator terms in every pass (the round-1 form, NNMPC_T2_EVERY=0);
+    "mixed-notail"  the form large QPs run by default: one fp16 operator term per pass, the second delivered every 8th
+                    pass from the pending sums (lp_iter.cuh, deferred second term); the delivery loops are global, so
+                    a row's arithmetic path (not its certified optimum) depends on when it started relative to them;
+    "mixed-fused"   both operator terms in every pass (the round-1 form, NNMPC_T2_EVERY=0): a row's arithmetic is
+                    independent of its neighbours;
     "mixed-oneterm" both terms, except one-term tiles for late-phase rows at an aggressive threshold."""
     monkeypatch.setenv("NNMPC_PRECISION", request.param.split("-")[0])
     for k in ("NNMPC_TAIL_ROWS", "NNMPC_T2_FACTOR", "NNMPC_T2_EVERY"):
@@ -283,6 +285,8 @@ def precision(request, monkeypatch):
         monkeypatch.setenv("NNMPC_TAIL_ROWS", "0")
     if request.param == "mixed-oneterm":
         monkeypatch.setenv("NNMPC_T2_FACTOR", "10000")
+    if request.param == "mixed-notail":
+        monkeypatch.setenv("NNMPC_T2_EVERY", "8")       # forced: the default defers only for n >= 1536
     if request.param == "mixed-fused":
         monkeypatch.setenv("NNMPC_T2_EVERY", "0")
     return request.param
@@ -332,7 +336,10 @@ def test_generate_data_files_and_sharding_invariance(torch_cuda, cdu_small_probl
         assert set(d) == {"x", "uprev", "xs", "us", "u", "data_gen_time"}
         assert d["x"].shape == (25, p.Nx) and d["u"].shape == (25, p.Nu)
         for k in ("x", "uprev", "xs", "us", "u"):
-            assert np.array_equal(d[k], all4[k][2 + proc]), k     # bitwise: batching does not change results
+            if precision == "mixed-notail":     # global delivery loops of the second operator term: equal to the solver tolerance
+                assert np.max(np.abs(d[k] - all4[k][2 + proc])) <= 1e-7 * max(1.0, np.max(np.abs(d[k]))), k
+            else:
+                assert np.array_equal(d[k], all4[k][2 + proc]), k     # bitwise: batching does not change results
 
 
 def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem, precision):
@@ -352,7 +359,7 @@ def test_closed_loop_engine_across_tile_shapes(torch_cuda, cdu_small_problem, pr
     for sel in (slice(0, 40), slice(100, 230), slice(449, 450)):
         sub = sim.engine.run(p.xprior, p.uprev, spc[sel], dsc[sel])
         for k in ("x", "uprev", "xs", "us", "u", "iters"):
-            if precision in ("mixed", "mixed-oneterm"):
+            if precision in ("mixed", "mixed-notail", "mixed-oneterm"):
                 # the automatic FP64 tail / the one-term tiles make the arithmetic path (not the optimum) depend on
                 # which other trajectories are live, so batches agree to the solver tolerance, not bitwise
                 if k != "iters":
@@ -388,7 +395,7 @@ def test_closed_loop_chunk_queue(torch_cuda, cdu_small_problem, precision):
             q = sim.engine.run(x_init, p.uprev, spc, dsc)
             assert not q["maxiter_hit"] and float(q["kkt"].max()) <= KKT_TOL
             for k in ("x", "uprev", "xs", "us", "u", "x_final", "uprev_final"):
-                if precision in ("mixed", "mixed-oneterm"):
+                if precision in ("mixed", "mixed-notail", "mixed-oneterm"):
                     assert np.max(np.abs(q[k] - ref[k])) <= 1e-7 * max(1.0, np.max(np.abs(ref[k]))), (slots, k)
                 else:
                     assert np.array_equal(q[k], ref[k]), (slots, k)
