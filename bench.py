@@ -599,21 +599,26 @@ def run_cdu(args):
         t1, t2 = sp1["tiles_one_term"] - sp0["tiles_one_term"], sp1["tiles_two_terms"] - sp0["tiles_two_terms"]
         tc = sp1.get("tiles_second_term_delivery", 0) - sp0.get("tiles_second_term_delivery", 0)
         mma_factor = (t1 + 2.0 * t2 + tc) / max(t1 + t2, 1) if (t1 + t2) else 2.0
-        # DRAM bytes per launch: a MODEL, not a per-run measurement - two fp16 operator terms read once per pass
-        # (2 x 2 n^2 B) plus the per-row state, with the per-row constant taken from the one `ncu --set full` capture of
-        # this kernel (profiles/r02h_ncu_full_lp_gemm.txt: 3.72 GB per launch at 16 384 rows, n = 4480 -> 222 kB per row
-        # vs 42 B x n = 188.2 kB algorithmic), scaled linearly in n
+        # DRAM bytes per launch: a MODEL, not a per-run measurement - the fp16 operator terms read once per pass
+        # (mma_factor x 2 n^2 B) plus the per-row state, with the per-row constant taken from the one `ncu --set full`
+        # capture of this kernel: deferred second term (profiles/r02r_ncu_full_lp_gemm.txt) 3.87 GB per launch at 16 384
+        # rows, n = 4480 -> 233.8 kB per row vs 46 B x n = 206.1 kB algorithmic (42 B of state + 4 B of pending sums);
+        # both terms in every pass (profiles/r02h_ncu_full_lp_gemm.txt) 222 kB per row vs 42 B x n; scaled linearly in n
+        deferred = tc > 0
         op_bytes = mma_factor * 2.0 * n * n
-        r_lp = {"bound": "tensor", "kernel": "lp_gemm_kernel<EpiDelta> (+ <EpiAddX> every 4th pass) (regulator-QP iteration: tcgen05 kind::f16, fp16 "
-                                             "increments x two-term fp16 operator split - second term deferred, fp32 TMEM "
-                                             "accumulators, FP64 state)",
+        row_model, row_alg = (233.8e3, 46.0) if deferred else (222.0e3, 42.0)
+        r_lp = {"bound": "tensor", "kernel": ("lp_gemm_kernel<EpiDelta> + lp_gemm_kernel<EpiAddX> (regulator-QP iteration: tcgen05 kind::f16, fp16 "
+                           "increments x first fp16 operator term every pass, second term delivered every 8th pass from the "
+                           "pending sums, fp32 TMEM accumulators, FP64 state)") if deferred else
+                          ("lp_gemm_kernel<EpiDelta> (regulator-QP iteration: tcgen05 kind::f16, fp16 increments x two-term fp16 "
+                           "operator split, fp32 TMEM accumulators, FP64 state)"),
                 "mma_products_per_iteration": mma_factor,
                 "achieved": achieved, "executed_mma": mma_factor * achieved, "peak": lp_peak, "unit": "TFLOP/s",
                 "one_term_tile_share": t1 / max(t1 + t2, 1),
                 "frac": achieved / lp_peak, "frac_executed": mma_factor * achieved / lp_peak,
-                "traffic": op_bytes + 222.0e3 * (n / 4480.0) * rows_per_launch,
+                "traffic": op_bytes + row_model * (n / 4480.0) * rows_per_launch,
                 "traffic_kind": "model scaled from one ncu capture (see bench.py), not measured in this run",
-                "traffic_algorithmic": op_bytes + 42.0 * n * rows_per_launch,
+                "traffic_algorithmic": op_bytes + row_alg * n * rows_per_launch,
                 "rows_per_launch": rows_per_launch,
                 "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "share_of_step": gemm_ms / ms_prof,

@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(1024) k_retire(EngineArrays e, double tol, int
 // 1/2 z'Pz + q'z = 1/2 z'(g + q) from the gradient g = P z + q of the check that certified z.
 constexpr int ADV_ROWS = 8;
 constexpr int T2_AUTO_MIN_N = 1536;
-__global__ void __launch_bounds__(256)
+constexpr int ADV_THREADS = 1024;   // 32 warps share the rows of [A|B|Bd]: the dot products are latency bound (8 warps: 32 rows each)
+__global__ void __launch_bounds__(ADV_THREADS)
 k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, const int* __restrict__ tcur,
                 const int* __restrict__ chunk, int T, const double* __restrict__ Z, const double* __restrict__ us,
                 double* __restrict__ xcur, const double* __restrict__ dist, double* __restrict__ row_u,
@@ -358,7 +359,7 @@ k_advance_plant(const int* __restrict__ rows, const int* __restrict__ count, con
                 double* __restrict__ cap_cost, const double* __restrict__ lb, const double* __restrict__ ub,
                 unsigned long long* __restrict__ stats) {
   extern __shared__ double adv_in[];          // ADV_ROWS x kin_ld
-  __shared__ double red[8];
+  __shared__ double red[ADV_THREADS / 32];
   __shared__ int row_act[ADV_ROWS];
   const int cnt = *count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1010,7 +1011,7 @@ static int sim_run_device(nnmpc_sim* h, int Btot, int T, double* x_io, double* u
       k_qp_store<<<row_grid(B), 256, 0, st>>>(e.l_done, e.counts + N_DONE, e.chunk, *qb, h->Z.p, gbuf, q->Ql.p, h->lb.p, h->ub.p,
                                               h->stats, n, nu);
     else
-      k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), 256, adv_smem, st>>>(
+      k_advance_plant<<<row_grid((B + ADV_ROWS - 1) / ADV_ROWS), ADV_THREADS, adv_smem, st>>>(
           e.l_done, e.counts + N_DONE, e.tcur, e.chunk, T, h->Z.p, ous, h->xcur.p, dist, ou, h->upcur.p, h->ABd, n, nx, nu, nd,
           h->kin_ld, gbuf, q->Ql.p, h->cap_useq, h->cap_cost, h->lb.p, h->ub.p, h->stats);
     count_launch(2);
