@@ -103,6 +103,16 @@ int nnmpc_ts_create(nnmpc_ts_t** out, int nx, int nu, int ny, int nd, const doub
                     const double* Fy_host, const double* Fd_host, const double* f0_host,
                     const double* Gx_host, const double* Gd_host, const double* ulb_host,
                     const double* uub_host, int device);
+/* Output-constrained targets, ylb <= C xs + Cd dhat <= yub next to the input box (the ylb/yub branch of
+ * TargetSelector, lib/linearMPC.py:242-248, :284-288).  Host arrays, row-major, built by the caller from the same
+ * reduction as nnmpc_ts_create (xs = Gx us + Gd dhat):  Hinv = Ht^-1 (nu x nu), Abar = [C Gx; I] ((ny + nu) x nu),
+ * AH = Abar Hinv, Mbar = Abar Hinv Abar' ((ny + nu)^2), Ryd = C Gd + Cd (ny x nd), ylb, yub (ny).  From then on every
+ * solve through this handle (nnmpc_ts_solve*, the closed-loop engine, the online loop) runs an exact dual active-set
+ * method (one warp per sample) over the ny + nu two-sided rows; an infeasible sample raises NNMPC_WARN_TARGET and carries
+ * a negative iteration count.  ny + nu <= 160.  Call once, before the first solve. */
+int nnmpc_ts_set_output_bounds(nnmpc_ts_t* h, const double* Hinv_host, const double* Abar_host, const double* AH_host,
+                               const double* Mbar_host, const double* Ryd_host, const double* ylb_host,
+                               const double* yub_host);
 int nnmpc_ts_destroy(nnmpc_ts_t* h);
 /* ysp: dev B rows of ny doubles, row stride ysp_stride (doubles); d likewise. */
 /* iters (nullable): active-set steps per sample; a sample whose solve stalled at the step cap or went

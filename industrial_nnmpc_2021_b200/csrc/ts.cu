@@ -31,6 +31,10 @@ struct TsParams {
   int indexed;
   TsIndex ix;
   int* fail;   // nullable device flag, set when a solve stalls at the iteration cap or produces non-finite targets
+  int given;   // 1: us (and iters) were written by k_ts_general; this kernel only forms xs and the fused outputs
+  // output-constrained targets (k_ts_general)
+  int mb;
+  const double *Hinv, *Abar, *AH, *Mbar, *Ryd, *ylb, *yub;
 };
 
 __device__ __forceinline__ double warp_min_d(double v) {
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
     // hundreds of steps, controller_evaluation.py:31-47): when this step's (ysp, d) equal the previous
     // step's bit for bit, the target is the previous one - the solve is deterministic - so reuse it.
     bool same = false;
-    if (p.indexed && p.ix.tcur[s] > 0) {
+    if (!p.given && p.indexed && p.ix.tcur[s] > 0) {
       bool eq = true;
       const double* yprev = ysp - p.ysp_stride;
       const double* dprev = dd - p.d_stride;
@@ -90,8 +94,9 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
     int st = 2;  // 0 free, -1 at lower, +1 at upper, 2 padding lane / degenerate (never released)
     if (act) st = (hi <= lo) ? 2 : (u <= lo ? -1 : (u >= hi ? 1 : 0));
     int it = 0;
-    bool done = same;
+    bool done = same || p.given;
     if (same && act) u = p.us[(b - 1) * p.us_stride + lane];
+    if (p.given && act) u = p.us[b * p.us_stride + lane];
     for (; it < maxit && !done; ++it) {
       uvec[lane] = u;
       __syncwarp();
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
     const bool bad = !done || __any_sync(FULLMASK, act && !(fabs(u) <= 1.7e308));
     if (bad && p.fail && lane == 0) atomicExch(p.fail, 1);
     if (act) p.us[(long long)b * p.us_stride + lane] = u;
-    if (p.iters && lane == 0) p.iters[(long long)b * p.iters_stride] = bad ? -it - 1 : it;
+    if (p.iters && lane == 0 && !p.given) p.iters[(long long)b * p.iters_stride] = bad ? -it - 1 : it;
     const TsFused& F = p.f;
     for (int r = lane; r < nx; r += 32) {
       double acc = 0.0;
@@ -225,6 +230,233 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
   }
 }
 
+
+// ---- output-constrained targets: ylb <= C xs + Cd d <= yub next to the input box (linearMPC.py:242-248, :284-288) ----
+// After the elimination of xs the problem is  min 1/2 u'Ht u + f'u  s.t.  lo_i <= abar_i'u <= hi_i  over the mb = ny + nu
+// rows abar = [C Gx; I], with lo/hi = [ylb - Ryd d; ulb], [yub - Ryd d; uub] per sample.  Solved EXACTLY by the dual
+// active-set method of Goldfarb and Idnani in its range-space form, one warp per sample: start at the unconstrained
+// minimiser, add the most violated constraint p, moving along z = Hinv a_p - Hinv A_W' r with r = (A_W Hinv A_W')^-1
+// A_W Hinv a_p until p holds (full step) or a multiplier of the working set W reaches zero (that constraint is
+// dropped).  Hinv, AH = Abar Hinv and Mbar = Abar Hinv Abar' are shared by all samples (host set-up), so a step costs
+// one |W| x |W| Cholesky in shared memory (|W| <= nu <= 32) and a few gathers.  The final point is re-solved from its
+// working set, so rounding does not accumulate over the steps.  An infeasible sample (no step length exists) or one
+// that runs out of steps raises the fail flag and carries a negative iteration count - cvxopt would report a status.
+constexpr int TS_MAXC = 160;      // ny + nu
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+
+// Cholesky of the leading m x m block of S (lower, in place, lane j owns row j) and the solve S x = rhs (lane j: rhs_j);
+// returns x_j in lane j.  A non-positive pivot yields NaN, which the caller turns into the fail flag.
+__device__ __forceinline__ double ws_chol_solve(double* S, int m, double rhs, int lane) {
+  for (int k = 0; k < m; ++k) {
+    const double sd = sqrt(S[k * TS_LD + k]);
+    const double inv = 1.0 / sd;
+    double lik = 0.0;
+    if (lane > k && lane < m) {
+      lik = S[lane * TS_LD + k] * inv;
+      S[lane * TS_LD + k] = lik;
+    }
+    __syncwarp();
+    if (lane == k) S[k * TS_LD + k] = sd;
+    for (int j = k + 1; j < m; ++j) {
+      const double ljk = S[j * TS_LD + k];
+      if (lane >= j && lane < m) S[lane * TS_LD + j] -= lik * ljk;
+    }
+    __syncwarp();
+  }
+  double bb = lane < m ? rhs : 0.0;
+  for (int k = 0; k < m; ++k) {  // L y = rhs
+    const double yk = __shfl_sync(FULLMASK, bb, k) / S[k * TS_LD + k];
+    if (lane == k) bb = yk;
+    else if (lane > k && lane < m) bb -= S[lane * TS_LD + k] * yk;
+  }
+  for (int k = m - 1; k >= 0; --k) {  // L' x = y
+    const double xk = __shfl_sync(FULLMASK, bb, k) / S[k * TS_LD + k];
+    if (lane == k) bb = xk;
+    else if (lane < k) bb -= S[k * TS_LD + lane] * xk;
+  }
+  return bb;
+}
+
+__global__ void __launch_bounds__(TS_WARPS * 32) k_ts_general(TsParams p) {
+  __shared__ double Sw[TS_WARPS][32 * TS_LD];
+  __shared__ double uw[TS_WARPS][32], fw[TS_WARPS][32], lamw[TS_WARPS][32], rw[TS_WARPS][32];
+  __shared__ double blo[TS_WARPS][TS_MAXC], bhi[TS_WARPS][TS_MAXC];
+  __shared__ int widx[TS_WARPS][32], wsgn[TS_WARPS][32];
+  const int nu = p.nu, ny = p.ny, nd = p.nd, mb = p.mb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* S = Sw[warp];
+  double* uvec = uw[warp];
+  double* fvec = fw[warp];
+  double* lam = lamw[warp];
+  double* rvec = rw[warp];
+  double* lo = blo[warp];
+  double* hi = bhi[warp];
+  int* wi = widx[warp];
+  int* ws = wsgn[warp];
+  const bool act = lane < nu;
+  const int maxit = 8 * (nu + 8) + 2 * ny;
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+
+  const int Bn = p.indexed && p.ix.count ? min(*p.ix.count, p.B) : p.B;
+  for (int lb_ = blockIdx.x * TS_WARPS + warp; lb_ < Bn; lb_ += gridDim.x * TS_WARPS) {
+    const long long s = p.indexed ? (long long)p.ix.rows[lb_] : (long long)lb_;
+    const long long b = p.indexed ? (p.ix.chunk ? (long long)p.ix.chunk[s] : s) * p.ix.T + p.ix.tcur[s] : s;
+    const double* ysp = p.ysp + b * p.ysp_stride;
+    const double* dd = p.d + b * p.d_stride;
+    // linear term and per-sample bounds
+    double f = 0.0;
+    if (act) {
+      f = p.f0[lane];
+      const double* fy = p.Fy + (long long)lane * ny;
+      for (int y = 0; y < ny; ++y) f += fy[y] * ysp[y];
+      const double* fd = p.Fd + (long long)lane * nd;
+      for (int k = 0; k < nd; ++k) f += fd[k] * dd[k];
+    }
+    fvec[lane] = f;
+    for (int i = lane; i < mb; i += 32) {
+      if (i < ny) {
+        double r = 0.0;
+        for (int k = 0; k < nd; ++k) r += p.Ryd[(long long)i * nd + k] * dd[k];
+        lo[i] = p.ylb[i] - r;
+        hi[i] = p.yub[i] - r;
+      } else {
+        lo[i] = p.ulb[i - ny];
+        hi[i] = p.uub[i - ny];
+      }
+    }
+    __syncwarp();
+    // unconstrained minimiser
+    double u = 0.0;
+    if (act)
+      for (int j = 0; j < nu; ++j) u -= p.Hinv[(long long)lane * nu + j] * fvec[j];
+    int nW = 0, it = 0;
+    bool done = false, failed = false;
+    for (; it < maxit && !done && !failed; ++it) {
+      uvec[lane] = u;
+      __syncwarp();
+      // most violated constraint (scaled tolerance)
+      double best = 0.0;
+      int bi = -1, bs = 0;
+      for (int i = lane; i < mb; i += 32) {
+        double val = 0.0, mag = 0.0;
+        const double* a = p.Abar + (long long)i * nu;
+        for (int k = 0; k < nu; ++k) {
+          const double t = a[k] * uvec[k];
+          val += t;
+          mag += fabs(t);
+        }
+        const double vu = val - hi[i], vl = lo[i] - val;
+        const double v = vu >= vl ? vu : vl;
+        const double tol = 1e-11 * (1.0 + mag + fabs(vu >= vl ? hi[i] : lo[i]));
+        if (v > tol && v > best) { best = v; bi = i; bs = vu >= vl ? 1 : -1; }
+        if (!(v <= 1.7e308)) { best = INF; bi = i; bs = 1; }      // NaN / Inf: make it visible
+      }
+      const double vmax = warp_max_d(best);
+      if (!(vmax > 0.0)) { done = true; break; }
+      if (!(vmax <= 1.7e308)) { failed = true; break; }
+      const unsigned who = __ballot_sync(FULLMASK, best == vmax && bi >= 0);
+      const int src = __ffs(who) - 1;
+      const int ip = __shfl_sync(FULLMASK, bi, src);
+      const int sp = __shfl_sync(FULLMASK, bs, src);
+      double vp = vmax;
+      double lam_p = 0.0;
+      const double mpp = p.Mbar[(long long)ip * mb + ip];
+      for (int inner = 0; inner <= 2 * nu + 2; ++inner) {
+        // d = A_W Hinv a_p, S = A_W Hinv A_W'
+        double dj = 0.0;
+        if (lane < nW) {
+          const long long ij = wi[lane];
+          dj = (double)(ws[lane] * sp) * p.Mbar[ij * mb + ip];
+          for (int k = 0; k <= lane; ++k) S[lane * TS_LD + k] = (double)(ws[lane] * ws[k]) * p.Mbar[ij * mb + wi[k]];
+        }
+        __syncwarp();
+        const double rj = nW > 0 ? ws_chol_solve(S, nW, dj, lane) : 0.0;
+        rvec[lane] = lane < nW ? rj : 0.0;
+        __syncwarp();
+        // z = Hinv a_p - Hinv A_W' r  (lane k holds z_k),  a_p'z = Mbar[p][p] - d'r
+        double z = 0.0;
+        if (act) {
+          z = (double)sp * p.AH[(long long)ip * nu + lane];
+          for (int j = 0; j < nW; ++j) z -= rvec[j] * (double)ws[j] * p.AH[(long long)wi[j] * nu + lane];
+        }
+        const double apz = mpp - warp_sum_d(lane < nW ? dj * rj : 0.0);
+        // step lengths
+        double t1l = INF;
+        if (lane < nW && rj > 1e-13 * (1.0 + fabs(dj))) t1l = lam[lane] / rj;
+        const double t1 = warp_min_d(t1l);
+        const double t2 = apz > 1e-12 * mpp ? vp / apz : INF;
+        if (!(t1 <= 1.7e308) && !(t2 <= 1.7e308)) { failed = true; break; }      // infeasible (or NaN)
+        const double t = t1 < t2 ? t1 : t2;
+        u -= t * z;
+        if (lane < nW) lam[lane] -= t * rj;
+        lam_p += t;
+        vp -= t * apz;
+        __syncwarp();
+        if (t2 <= t1) {      // full step: p joins the working set
+          if (nW >= 32) { failed = true; break; }
+          if (lane == 0) { wi[nW] = ip; ws[nW] = sp; lam[nW] = lam_p; }
+          ++nW;
+          __syncwarp();
+          break;
+        }
+        // partial step: drop the blocking constraint, keep p for another try
+        const unsigned blk = __ballot_sync(FULLMASK, t1l == t1);
+        const int jb = __ffs(blk) - 1;
+        const int wi_n = (lane >= jb && lane + 1 < nW) ? wi[lane + 1] : 0;
+        const int ws_n = (lane >= jb && lane + 1 < nW) ? ws[lane + 1] : 0;
+        const double lam_n = (lane >= jb && lane + 1 < nW) ? lam[lane + 1] : 0.0;
+        __syncwarp();
+        if (lane >= jb && lane + 1 < nW) { wi[lane] = wi_n; ws[lane] = ws_n; lam[lane] = lam_n; }
+        --nW;
+        __syncwarp();
+        if (inner == 2 * nu + 2) failed = true;
+      }
+    }
+    if (!done && !failed) failed = true;      // out of steps
+    // re-solve on the final working set: lambda = -(A_W Hinv A_W')^-1 (b_W + A_W Hinv f), u = -Hinv f - Hinv A_W' lambda
+    if (done && nW > 0) {
+      double rhs = 0.0;
+      if (lane < nW) {
+        const long long ij = wi[lane];
+        double ahf = 0.0;
+        for (int k = 0; k < nu; ++k) ahf += p.AH[ij * nu + k] * fvec[k];
+        const double bw = ws[lane] > 0 ? hi[ij] : -lo[ij];
+        rhs = -(bw + (double)ws[lane] * ahf);
+        for (int k = 0; k <= lane; ++k) S[lane * TS_LD + k] = (double)(ws[lane] * ws[k]) * p.Mbar[ij * mb + wi[k]];
+      }
+      __syncwarp();
+      const double lj = ws_chol_solve(S, nW, rhs, lane);
+      rvec[lane] = lane < nW ? lj : 0.0;
+      __syncwarp();
+      if (act) {
+        double un = 0.0;
+        for (int j = 0; j < nu; ++j) un -= p.Hinv[(long long)lane * nu + j] * fvec[j];
+        for (int j = 0; j < nW; ++j) un -= rvec[j] * (double)ws[j] * p.AH[(long long)wi[j] * nu + lane];
+        u = un;
+      }
+      // inputs whose own bound is in the working set sit on it exactly; the others are inside the box up to the
+      // violation tolerance (1e-11 relative) and are clipped to it, so that the regulator's shifted bounds
+      // ulb - us <= 0 <= uub - us keep their signs
+      uvec[lane] = u;
+      __syncwarp();
+      if (lane < nW && wi[lane] >= ny) uvec[wi[lane] - ny] = ws[lane] > 0 ? hi[wi[lane]] : lo[wi[lane]];
+      __syncwarp();
+      u = uvec[lane];
+    }
+    if (act && done) u = fmin(fmax(u, p.ulb[lane]), p.uub[lane]);
+    const bool bad = failed || __any_sync(FULLMASK, act && !(fabs(u) <= 1.7e308));
+    if (bad && p.fail && lane == 0) atomicExch(p.fail, 1);
+    if (act) p.us[(long long)b * p.us_stride + lane] = u;
+    if (p.iters && lane == 0) p.iters[(long long)b * p.iters_stride] = bad ? -it - 1 : it;
+    __syncwarp();
+  }
+}
+
 int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride, const double* d,
                     long long d_stride, double* xs, long long xs_stride, double* us, long long us_stride,
                     int* iters, long long iters_stride, const TsFused* fused, const TsIndex* index,
@@ -243,6 +475,13 @@ int ts_solve_device(nnmpc_ts* h, int B, const double* ysp, long long ysp_stride,
   p.fail = fail_flag;
   int blocks = (B + TS_WARPS - 1) / TS_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (h->general) {      // output-constrained targets: the dual active-set kernel solves, the kernel below forms xs / fused outputs
+    p.mb = h->mb; p.Hinv = h->Hinv; p.Abar = h->Abar; p.AH = h->AH; p.Mbar = h->Mbar; p.Ryd = h->Ryd; p.ylb = h->ylb; p.yub = h->yub;
+    k_ts_general<<<blocks, TS_WARPS * 32, 0, st>>>(p);
+    count_launch();
+    NNMPC_CUDA(cudaGetLastError());
+    p.given = 1;
+  }
   k_target_selector<<<blocks, TS_WARPS * 32, 0, st>>>(p);
   count_launch();
   NNMPC_CUDA(cudaGetLastError());
@@ -294,9 +533,31 @@ int nnmpc_ts_destroy(nnmpc_ts_t* h) {
   DeviceGuard dg(h->device);
   cudaFree(h->Ht); cudaFree(h->Fy); cudaFree(h->Fd); cudaFree(h->f0); cudaFree(h->Gx); cudaFree(h->Gd);
   cudaFree(h->ulb); cudaFree(h->uub);
+  cudaFree(h->Hinv); cudaFree(h->Abar); cudaFree(h->AH); cudaFree(h->Mbar); cudaFree(h->Ryd); cudaFree(h->ylb); cudaFree(h->yub);
   if (h->fail) cudaFree(h->fail);
   h->hysp.release(); h->hd.release(); h->hxs.release(); h->hus.release(); h->hiters.release();
   delete h;
+  return 0;
+}
+
+int nnmpc_ts_set_output_bounds(nnmpc_ts_t* h, const double* Hinv, const double* Abar, const double* AH, const double* Mbar,
+                               const double* Ryd, const double* ylb, const double* yub) {
+  if (!h || !Hinv || !Abar || !AH || !Mbar || !Ryd || !ylb || !yub)
+    return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_set_output_bounds: null argument");
+  const int mb = h->ny + h->nu;
+  if (mb > TS_MAXC) return set_error(NNMPC_ERR_UNSUPPORTED, "nnmpc_ts_set_output_bounds: ny + nu = %d exceeds %d", mb, TS_MAXC);
+  if (h->general) return set_error(NNMPC_ERR_BADARG, "nnmpc_ts_set_output_bounds: already set for this handle");
+  DeviceGuard dg(h->device);
+  const size_t nu = (size_t)h->nu, ny = (size_t)h->ny, nd = (size_t)(h->nd > 0 ? h->nd : 1);
+  NNMPC_TRY(upload(&h->Hinv, Hinv, nu * nu));
+  NNMPC_TRY(upload(&h->Abar, Abar, (size_t)mb * nu));
+  NNMPC_TRY(upload(&h->AH, AH, (size_t)mb * nu));
+  NNMPC_TRY(upload(&h->Mbar, Mbar, (size_t)mb * mb));
+  NNMPC_TRY(upload(&h->Ryd, Ryd, ny * nd));
+  NNMPC_TRY(upload(&h->ylb, ylb, ny));
+  NNMPC_TRY(upload(&h->yub, yub, ny));
+  h->mb = mb;
+  h->general = true;
   return 0;
 }
 

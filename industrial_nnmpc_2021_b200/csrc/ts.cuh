@@ -6,6 +6,11 @@ struct nnmpc_ts {
   int nx, nu, ny, nd, device;
   int* fail = nullptr;                               // device flag: some solve of the last call missed its optimum
   double *Ht, *Fy, *Fd, *f0, *Gx, *Gd, *ulb, *uub;  // device operators
+  // output-constrained targets (nnmpc_ts_set_output_bounds): constraint rows Abar = [C Gx; I] (mb x nu), Hinv = Ht^-1,
+  // AH = Abar Hinv, Mbar = Abar Hinv Abar', Ryd = C Gd + Cd (ny x nd), output bounds ylb, yub (ny)
+  bool general = false;
+  int mb = 0;
+  double *Hinv = nullptr, *Abar = nullptr, *AH = nullptr, *Mbar = nullptr, *Ryd = nullptr, *ylb = nullptr, *yub = nullptr;
   nnmpc::DevBuf<double> hysp, hd, hxs, hus;          // staging for the host entry point
   nnmpc::DevBuf<int> hiters;
 };

@@ -105,10 +105,12 @@ class TargetSelector:
         min_(xs,us) |us-usp|^2_Rs + |C xs + Cd dhat - ysp|^2_Qs
         s.t. [I-A, -B; HC, 0][xs; us] = [Bd dhat; H(ysp - Cd dhat)],  ulb <= us <= uub
 
-    Supported configuration = the one both reference examples use: ``H`` empty
-    (cstrs_parameters.py:278, cdu_parameters.py:78), no output bounds, ``I - A`` invertible
-    (any A without an eigenvalue at 1, stable or not), ``Nu <= 32``.  Then ``xs = Gx us + Gd dhat`` and the problem is an exactly equivalent
-    ``Nu``-dimensional box QP (see csrc/ts.cu).
+    Supported configuration: ``H`` empty (both reference examples: cstrs_parameters.py:278,
+    cdu_parameters.py:78), ``I - A`` invertible (any A without an eigenvalue at 1, stable or not), ``Nu <= 32``.
+    Then ``xs = Gx us + Gd dhat`` and the problem is an exactly equivalent ``Nu``-dimensional QP (see csrc/ts.cu): a
+    box QP solved by a primal active-set method, or - with output bounds ``ylb <= C xs + Cd dhat <= yub``
+    (linearMPC.py:242-248, :284-288; ``Ny + Nu <= 160``) - a QP over ``Ny + Nu`` two-sided rows solved by a dual
+    active-set method.  An infeasible or stalled solve raises ``NnmpcError`` (cvxopt would report a status).
     """
 
     def __init__(self, *, A, B, C, H, Bd, Cd, usp, Rs, Qs, ulb, uub, ylb=None, yub=None, device=None):
@@ -118,9 +120,11 @@ class TargetSelector:
         self.usp = usp
         self.ysp, self.dhats, self.xs, self.us = [], [], [], []
         self.ulb, self.uub, self.ylb, self.yub = ulb, uub, ylb, yub
-        if self.Nz != 0 or ylb is not None or yub is not None:
-            raise NotImplementedError("TargetSelector on the GPU supports H empty and input bounds only "
+        if self.Nz != 0:
+            raise NotImplementedError("TargetSelector on the GPU supports H empty only "
                                       "(the configuration of both reference examples)")
+        if (ylb is None) != (yub is None):
+            ylb = yub = self.ylb = self.yub = None      # the reference uses output bounds only when both are given (:242)
         if np.linalg.cond(np.eye(self.Nx) - A) > 1e12:
             raise NotImplementedError("TargetSelector on the GPU eliminates xs through (I - A)^-1: A must not have an "
                                       "eigenvalue at 1 (an integrating plant needs H to pin the target)")
@@ -134,8 +138,14 @@ class TargetSelector:
         nx, nu, ny = self.Nx, self.Nu, self.Ny
         E = np.vstack([np.eye(nu), -np.eye(nu)])
         self.F = np.vstack([np.eye(ny), -np.eye(ny)])
-        self.G = np.hstack([np.zeros((2 * nu, nx)), E])
-        self.h = np.vstack([self.uub, -self.ulb])
+        if self.ylb is not None and self.yub is not None:           # :242-248
+            self.G = np.block([[self.F @ self.C, np.zeros((2 * ny, nu))], [np.zeros((2 * nu, nx)), E]])
+            self.f = np.vstack([self.yub, -self.ylb])
+            self.e = np.vstack([self.uub, -self.ulb])
+            self.h = None
+        else:
+            self.G = np.hstack([np.zeros((2 * nu, nx)), E])
+            self.h = np.vstack([self.uub, -self.ulb])
         self.tA = np.block([[np.eye(nx) - self.A, -self.B], [self.H @ self.C, np.zeros((self.Nz, nu))]])
         self.tb = np.block([[np.zeros((nx, ny)), self.Bd], [self.H, -(self.H @ self.Cd)]])
         self.P = scipy.linalg.block_diag(self.C.T @ (self.Qs @ self.C), self.Rs)
@@ -149,6 +159,16 @@ class TargetSelector:
         self.Fy = -QsCG.T                                    # d f / d ysp
         self.Fd = QsCG.T @ (self.C @ self.Gd + self.Cd)      # d f / d dhat
         self.f0 = -(self.Rs @ self.usp)
+        if self.ylb is not None and self.yub is not None:
+            # operators of the dual active-set solve over the rows Abar = [C Gx; I] (csrc/ts.cu, k_ts_general)
+            self.Abar = np.vstack([CG, np.eye(nu)])
+            cho = scipy.linalg.cho_factor(self.Ht)
+            self.Hinv = scipy.linalg.cho_solve(cho, np.eye(nu))
+            self.Hinv = 0.5 * (self.Hinv + self.Hinv.T)
+            self.AH = scipy.linalg.cho_solve(cho, self.Abar.T).T
+            Mb = self.AH @ self.Abar.T
+            self.Mbar = 0.5 * (Mb + Mb.T)
+            self.Ryd = self.C @ self.Gd + self.Cd
 
     def _create(self):
         L = _lib.lib()
@@ -159,6 +179,10 @@ class TargetSelector:
                                self._dev)
         _lib.check(rc, "nnmpc_ts_create")
         self._handle = hnd
+        if self.ylb is not None and self.yub is not None:
+            arrs = [_lib.host(a) for a in (self.Hinv, self.Abar, self.AH, self.Mbar,
+                                           self.Ryd if self.Nd else np.zeros((self.Ny, 1)), self.ylb, self.yub)]
+            _lib.check(L.nnmpc_ts_set_output_bounds(hnd, *[_lib.hptr(a) for a in arrs]), "nnmpc_ts_set_output_bounds")
 
     def __del__(self):
         try:
@@ -180,7 +204,11 @@ class TargetSelector:
     def _setup_changing_matrices(self, ysp, dhats):
         """linearMPC.py:276-296 (kept for inspection/tests; the GPU path uses Fy, Fd, f0)."""
         q = np.vstack([-(self.C.T @ (self.Qs @ (ysp - self.Cd @ dhats))), -(self.Rs @ self.usp)])
-        return q, self.h, self.tb @ np.vstack([ysp, dhats])
+        if self.h is None:                                          # :284-288
+            h = np.vstack([self.f - self.F @ (self.Cd @ dhats), self.e])
+        else:
+            h = self.h
+        return q, h, self.tb @ np.vstack([ysp, dhats])
 
     def solve_batch(self, YSP, D, return_iters=False):
         """(B,Ny),(B,Nd) -> xs (B,Nx), us (B,Nu).  torch CUDA tensors stay on the device;

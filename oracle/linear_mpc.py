@@ -158,17 +158,26 @@ def rollout_cost(A, B, Q, R, M, Pf, N, x0, useq):
 
 # ----------------------------------------------------------------------------- target selector
 class TargetSelectorOracle:
-    """Steady-state target QP in (xs, us).  linearMPC.py:178-319 (input-bound branch :249-251)."""
+    """Steady-state target QP in (xs, us).  linearMPC.py:178-319 (input-bound branch :249-251, output-bound
+    branch :242-248 when both ylb and yub are given)."""
 
-    def __init__(self, *, A, B, C, H, Bd, Cd, usp, Rs, Qs, ulb, uub):
+    def __init__(self, *, A, B, C, H, Bd, Cd, usp, Rs, Qs, ulb, uub, ylb=None, yub=None):
         self.A, self.B, self.C, self.H, self.Bd, self.Cd = A, B, C, H, Bd, Cd
         self.usp, self.Rs, self.Qs, self.ulb, self.uub = usp, Rs, Qs, ulb, uub
+        self.ylb, self.yub = ylb, yub
         self.Nx, self.Nu = B.shape
         self.Ny, self.Nd, self.Nz = C.shape[0], Bd.shape[1], H.shape[0]
         nx, nu, ny, nz = self.Nx, self.Nu, self.Ny, self.Nz
         E = np.vstack([np.eye(nu), -np.eye(nu)])
-        self.G = np.hstack([np.zeros((2 * nu, nx)), E])                  # :250
-        self.h = np.vstack([uub, -ulb])                                   # :251
+        self.F = np.vstack([np.eye(ny), -np.eye(ny)])                     # :240
+        if ylb is not None and yub is not None:                           # :242-248
+            self.G = np.block([[self.F @ C, np.zeros((2 * ny, nu))], [np.zeros((2 * nu, nx)), E]])
+            self.f = np.vstack([yub, -ylb])
+            self.e = np.vstack([uub, -ulb])
+            self.h = None
+        else:
+            self.G = np.hstack([np.zeros((2 * nu, nx)), E])              # :250
+            self.h = np.vstack([uub, -ulb])                               # :251
         self.tA = np.block([[np.eye(nx) - A, -B], [H @ C, np.zeros((nz, nu))]])     # :254-260
         self.tb = np.block([[np.zeros((nx, ny)), Bd], [H, -(H @ Cd)]])              # :261-267
         self.P = scipy.linalg.block_diag(C.T @ (Qs @ C), Rs)             # :270-274
@@ -177,12 +186,28 @@ class TargetSelectorOracle:
         """:276-296."""
         q = np.vstack([-(self.C.T @ (self.Qs @ (ysp - self.Cd @ dhats))), -(self.Rs @ self.usp)])
         b = self.tb @ np.vstack([ysp, dhats])
-        return q, self.h, b
+        if self.h is None:                                                # :284-288
+            h = np.vstack([self.f - self.F @ (self.Cd @ dhats), self.e])
+        else:
+            h = self.h
+        return q, h, b
 
     def solve(self, ysp, dhats, return_info=False):
         """:298-311 — returns (xs, us)."""
-        q, _, b = self.changing(ysp, dhats)
+        q, h, b = self.changing(ysp, dhats)
         nx = self.Nx
+        if self.h is None:
+            # general inequalities next to the equalities: eliminate tA w = b through a null-space basis, then the
+            # inequality QP of oracle.qp (interior point + active-set polish); raises when no feasible point exists
+            wp = np.linalg.lstsq(self.tA, b, rcond=None)[0]
+            Z = scipy.linalg.null_space(self.tA)
+            Pr = Z.T @ self.P @ Z
+            y, info = _qp.solve_general_qp(0.5 * (Pr + Pr.T), Z.T @ (q + self.P @ wp), self.G @ Z, h - self.G @ wp)
+            w = wp + Z @ y
+            if not np.all(np.isfinite(w)) or not np.max(self.G @ w - h) <= 1e-7 * (1.0 + np.abs(h).max()):
+                raise ValueError("TargetSelectorOracle: the output-constrained target problem is infeasible")
+            xs, us = w[:nx], w[nx:]
+            return ((xs, us), info) if return_info else (xs, us)
         lb = np.vstack([np.full((nx, 1), -np.inf), self.ulb])
         ub = np.vstack([np.full((nx, 1), np.inf), self.uub])
         w, info = _qp.solve_eq_box_qp(self.P, q, self.tA, b, lb, ub)

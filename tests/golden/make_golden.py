@@ -38,8 +38,30 @@ def import_reference():
     return ref_lmpc, ref_ce
 
 
+def make_ts_outputs(ref):
+    """Output-constrained target selector (lib/linearMPC.py:242-248, :284-288): the reference's own fixed and changing
+    matrices for the small CDU stand-in with output bounds -> target_selector_outputs.npz."""
+    from industrial_nnmpc_2021_b200.plants import get_cdu_problem
+    prob = get_cdu_problem(Nx=24, Nu=4, Ny=8, with_scenarios=False)
+    rng = np.random.default_rng(21)
+    ylb = -0.4 - 0.2 * rng.uniform(size=(prob.Ny, 1))
+    yub = 0.3 + 0.2 * rng.uniform(size=(prob.Ny, 1))
+    ts = ref.TargetSelector(A=prob.A, B=prob.B, C=prob.C, H=prob.H, Bd=prob.Bd, Cd=prob.Cd, usp=prob.usp, Rs=prob.Rs,
+                            Qs=prob.Qs, ulb=prob.ulb, uub=prob.uub, ylb=ylb, yub=yub)
+    ysp = 0.5 * rng.standard_normal((prob.Ny, 1))
+    d = rng.standard_normal((prob.Nd, 1))
+    q, h, b = ts._setup_changing_matrices(ysp, d)
+    assert ts.h is None
+    np.savez_compressed(os.path.join(HERE, "target_selector_outputs.npz"), ylb=ylb, yub=yub, ysp=ysp, d=d, P=ts.P, G=ts.G,
+                        f=ts.f, e=ts.e, F=ts.F, tA=ts.tA, tb=ts.tb, q=q, h=h, b=b)
+
+
 def main():
     ref, ref_ce = import_reference()
+    if "ts_outputs" in sys.argv[1:]:
+        make_ts_outputs(ref)
+        return
+    make_ts_outputs(ref)
     from industrial_nnmpc_2021_b200.plants import get_cstrs_problem, get_cdu_problem
 
     # ---- 1. PRBS signals with the reference seeds/constants (cstrs_parameters.py:328-337,
