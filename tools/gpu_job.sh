@@ -1,9 +1,13 @@
 #!/bin/bash
 # The GPU job of the current development step (overwritten per step; results land in gpurun_out/, the ones worth
 # keeping are copied to profiles/).
-# r02t: output-constrained target selector tests
+# r02u: BASELINE configs[4] on one GPU with the deferred second term: horizon x1 / x2 / x4 (reduced sample counts)
 set -x
 mkdir -p gpurun_out
-T=r02t
-timeout -k 10 600 python -m pytest tests/test_gpu_target_selector_outputs.py -q > gpurun_out/${T}_pytest_ts.log 2>&1
-grep -v "Warning\|^  \|^$\|warnings.html" gpurun_out/${T}_pytest_ts.log | tail -40 | cut -c1-300
+T=r02u
+for cfg in "140 1000000 16384" "280 250000 16384" "560 60000 8192"; do
+  set -- $cfg
+  timeout -k 10 900 python bench.py --workload horizon_sweep --horizon $1 --samples $2 --traj $3 --slots $3 --steps 2 --warmup 3 --no-cpu-baseline \
+     > gpurun_out/${T}_sweep_N$1.json 2> gpurun_out/${T}_sweep_N$1.err
+  tail -c 400 gpurun_out/${T}_sweep_N$1.err; cut -c1-300 gpurun_out/${T}_sweep_N$1.json
+done
