@@ -467,7 +467,7 @@ lp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // CTA's 128 accumulator rows into its own TMEM.  Per output element this halves the operand bytes pulled
 // from L2, which is what bounds the single-CTA kernel (6.3 kB/clk chip-wide TMA throughput).
 constexpr int BN2 = 256;          // output columns per pair tile (128 operator rows staged per CTA)
-constexpr int STAGES2 = 4;
+constexpr int STAGES2 = EPI_WARPS == 16 ? 3 : 4;
 constexpr int STAGE2_BYTES = BM * BK * 2 + 2 * (BN2 / 2) * BK * 2;   // A + B1 half + B2 half = 48 KB
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
 static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory");

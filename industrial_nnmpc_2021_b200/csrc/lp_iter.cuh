@@ -34,11 +34,14 @@ namespace nnmpc {
 #ifndef NNMPC_PROBE_NOSTORE
 #define NNMPC_PROBE_NOSTORE 0
 #endif
-using LpTileN128 = lp::LpTile<128, 4>;
-using LpTileM256 = lp::LpTile<128, 3, 2>;     // 256 x 128 outputs per CTA tile: operator bytes per flop halved
+// (ring depths: 192 KB of operand stages next to the epilogue's staging blocks; the 16-warp build - twice the staging
+//  blocks - runs one stage shallower)
+constexpr int LP_SH = lp::EPI_WARPS == 16 ? 1 : 0;
+using LpTileN128 = lp::LpTile<128, 4 - LP_SH>;
+using LpTileM256 = lp::LpTile<128, 3 - LP_SH, 2>;     // 256 x 128 outputs per CTA tile: operator bytes per flop halved
 // one operator term per pass (deferred second term): a stage is A + B1
-using LpTile1N128 = lp::LpTile<128, 6, 1, 1>;
-using LpTile1M256 = lp::LpTile<128, 4, 2, 1>;
+using LpTile1N128 = lp::LpTile<128, 6 - LP_SH, 1, 1>;
+using LpTile1M256 = lp::LpTile<128, 4 - LP_SH, 2, 1>;
 
 // one element of the Douglas-Rachford delta update (shared by the tensor-core epilogue and k_dr_first)
 __device__ __forceinline__ void dr_delta_one(double& x, double& v, double wl, double l, double u, double alpha,

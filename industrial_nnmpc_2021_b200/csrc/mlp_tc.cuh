@@ -19,7 +19,7 @@
 
 namespace nnmpc {
 
-using MlpTile = lp::LpTile<128, 4>;
+using MlpTile = lp::LpTile<128, lp::EPI_WARPS == 16 ? 3 : 4>;
 
 // power of two s with s * bound in [2^13, 2^14)  (fp16 max is 65504); bound = 0 or non-finite -> 1
 __device__ __forceinline__ double mlp_row_scale(double bound) {
