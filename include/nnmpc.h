@@ -15,8 +15,10 @@
  *    solve did not reach its optimum);
  *  - the caller owns every buffer it passes; handles own only the replicated operators and
  *    scratch, released by *_destroy; one device per handle.
- *  - threading: the OPERATORS of a handle never change after create (nnmpc_qp_set_penalty completes
- *    the create of a regulator handle and is called once, before the first solve), but a handle also
+ *  - threading: the OPERATORS of a handle never change after create (nnmpc_qp_set_penalty and
+ *    nnmpc_ts_set_output_bounds complete the create of a regulator / target-selector handle and are called
+ *    once, before the first solve; the one exception is nnmpc_mlp_train_step, which updates the weights
+ *    of a network handle in place - that is its purpose), but a handle also
  *    owns solver SCRATCH and, for nnmpc_sim, the run options of the nnmpc_sim_set_* calls: one call
  *    at a time per handle (the reference's objects are single-threaded too, lib/linearMPC.py:685-686
  *    mutates the regulator on every call).  Different handles are independent and may be driven from
