@@ -1,17 +1,13 @@
 #!/bin/bash
 # The GPU job of the current development step (overwritten per step; results land in gpurun_out/, the ones worth
 # keeping are copied to profiles/).
-# r02x: 16 epilogue warps (CW = 8, 96 registers, one-row pipeline stages) against the default 8
+# r02y: two-GPU validation with the final kernels: sharded generator (NCCL gather, content check), default bench at N = 2
 set -x
 mkdir -p gpurun_out
-T=r02x
-C=$PWD/industrial_nnmpc_2021_b200/csrc
-for v in "" _e16; do
-  echo "== libnnmpc$v" >> gpurun_out/${T}_lp_pass_split.txt
-  NNMPC_LIB_PATH=$C/libnnmpc$v.so timeout -k 10 300 python tools/probes/lp_pass_split.py 16384x4480 8192x4480 16384x540 >> gpurun_out/${T}_lp_pass_split.txt 2>&1
-done
-cut -c1-700 gpurun_out/${T}_lp_pass_split.txt
-NNMPC_LIB_PATH=$C/libnnmpc_e16.so timeout -k 10 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ab_e16.json 2> gpurun_out/${T}_ab_e16.err
-tail -c 300 gpurun_out/${T}_ab_e16.err; cut -c1-1200 gpurun_out/${T}_ab_e16.json
-NNMPC_LIB_PATH=$C/libnnmpc_e16.so timeout -k 10 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cdu_fullsize.py -q -x > gpurun_out/${T}_pytest_e16.log 2>&1
-tail -3 gpurun_out/${T}_pytest_e16.log | cut -c1-300
+T=r02y
+nvidia-smi -L
+timeout -k 10 600 python -m pytest tests/test_gpu_distributed.py -q -s > gpurun_out/${T}_dist_pytest.log 2>&1
+tail -4 gpurun_out/${T}_dist_pytest.log | cut -c1-300
+timeout -k 10 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+  bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_2gpu.json 2> gpurun_out/${T}_bench_2gpu.err
+tail -c 400 gpurun_out/${T}_bench_2gpu.err; cut -c1-400 gpurun_out/${T}_bench_2gpu.json
