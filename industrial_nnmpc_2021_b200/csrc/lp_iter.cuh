@@ -185,7 +185,13 @@ struct EpiDelta {
     float2 e[QR];
     __half2 so[QR];
   };
-  QLoad qa;                // the quarter in flight between two chunk() calls
+  QLoad qa;                // the quarter(s) in flight between two chunk() calls
+#ifndef NNMPC_EPI_DEPTH
+#define NNMPC_EPI_DEPTH 1   // quarters the loads run ahead of their use (2: three quarters of registers in flight)
+#endif
+#if NNMPC_EPI_DEPTH == 2
+  QLoad qn;
+#endif
   template <int QI>
   __device__ __forceinline__ void issue(int col0, int N, QLoad& q) const {
     const int cbase = col0 + 2 * cp;       // n is even: the pair is inside when its first column is
@@ -255,6 +261,30 @@ struct EpiDelta {
     }
   }
   // start of a row block: the first quarter of its first chunk
+#if NNMPC_EPI_DEPTH == 2
+  __device__ __forceinline__ void prime(int col0, int N) {
+    issue<0>(col0, N, qa);
+    issue<1>(col0, N, qn);
+  }
+  __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N, int next_col0) {
+#pragma unroll
+    for (int c = 0; c < lp::CW; ++c) sm->stg[c * lp::STG_LD + lane] = __uint_as_float(acc[c]);
+    __syncwarp();
+    // on entry quarter 0 is in qa and quarter 1 in qn; on exit the next chunk's quarters 0 and 1 are
+    QLoad qc;
+    issue<2>(col0, N, qc);
+    update_store<0>(col0, N, qa);
+    issue<3>(col0, N, qa);
+    update_store<1>(col0, N, qn);
+    if (next_col0 >= 0) issue<0>(next_col0, N, qn);
+    update_store<2>(col0, N, qc);
+    if (next_col0 >= 0) issue<1>(next_col0, N, qc);
+    update_store<3>(col0, N, qa);
+    qa = qn;
+    qn = qc;
+    __syncwarp();            // stg is rewritten by the next step
+  }
+#else
   __device__ __forceinline__ void prime(int col0, int N) { issue<0>(col0, N, qa); }
   __device__ void chunk(int col0, const uint32_t (&acc)[lp::CW], int N, int next_col0) {
     // transpose: stg[c][r], leading dimension STG_LD: conflict-free writes and reads
@@ -272,6 +302,7 @@ struct EpiDelta {
     update_store<3>(col0, N, qb);
     __syncwarp();            // stg is rewritten by the next step
   }
+#endif
   // L2 prefetch of the state of the NEXT chunk of this warp (lane = row): the loads of a chunk are one exposed DRAM round
   // trip per chunk and warp, and with two warps per scheduler nothing else covers it.  No registers held.
   __device__ __forceinline__ void prefetch(int col0, int N) const {
