@@ -90,16 +90,10 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_target_selector(TsParams p) {
       const double* fd = p.Fd + (long long)lane * nd;
       for (int k = 0; k < nd; ++k) f += fd[k] * dd[k];
     }
-    // Start: the projection of the origin, or - inside a trajectory - of the previous step's target: a primal
-    // active-set method may start at any feasible point, the optimum is unique, and with the CDU tuning (Rs = 1e-6,
-    // Qs = 1e-16) the targets sit in corners of the input box, which a start at the origin reaches one bound per
-    // step (each step a 32 x 32 Cholesky), a start at the previous corner in one or two.
-    double ustart = 0.0;
-    if (act && !same && p.indexed && p.ix.tcur[s] > 0) {
-      ustart = p.us[(b - 1) * p.us_stride + lane];
-      if (!(fabs(ustart) <= 1.7e308)) ustart = 0.0;
-    }
-    double u = act ? fmin(fmax(ustart, lo), hi) : 0.0;
+    // Start: the projection of the origin.  (Starting inside a trajectory from the previous step's target was measured
+    // and dropped: with the CDU tuning the targets sit in corners of the input box, and leaving a corner one
+    // multiplier at a time takes twice as long as reaching the next one from the interior.)
+    double u = act ? fmin(fmax(0.0, lo), hi) : 0.0;
     int st = 2;  // 0 free, -1 at lower, +1 at upper, 2 padding lane / degenerate (never released)
     if (act) st = (hi <= lo) ? 2 : (u <= lo ? -1 : (u >= hi ? 1 : 0));
     int it = 0;
