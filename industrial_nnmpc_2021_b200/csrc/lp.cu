@@ -8,14 +8,11 @@
 
 namespace nnmpc {
 
-// which tcgen05 kernel serves the passes: the one-CTA kernel (128 x 128 tiles) unless
-// NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles).  Measured on B200 (round 1ab/1ae): the
-// pair kernel halves the L2->SMEM operand traffic (5.3 vs 9.0 GB per 8192-row pass) but is not faster (332 vs 372
-// TFLOP/s algorithmic with the slim epilogue), so the one-CTA kernel, which sits at the L2->SMEM ceiling, is the default.
-// 0 = 128 x 128 tiles (default), 1 = 256 x 128 tiles (NNMPC_LP_TILE=m256).  Measured on B200 (round 2c): the 256-row
-// tile halves the operator bytes pulled from L2 per flop and is 7 % SLOWER (343 vs 367 TFLOP/s algorithmic) - the pass is
-// not bound by L2->SM operand traffic but by its FP64 epilogue (ncu warp states: 41 % long scoreboard, 24 % math-pipe
-// throttle; profiles/r02b_ncu_full_lp_gemm_m128.txt).
+// Which tcgen05 kernel serves the TWO-term passes (small QPs, NNMPC_T2_EVERY=0): the one-CTA kernel with 128 x 128 tiles
+// unless NNMPC_LP_KERNEL=pair selects the CTA-pair kernel (cta_group::2, 256 x 256 tiles) or NNMPC_LP_TILE=m256 the
+// 256 x 128 tiles.  Measured on B200: both halve the operator bytes pulled from L2 per flop and both are SLOWER (pair:
+// 332 vs 372 TFLOP/s algorithmic, round 1ab/1ae; 256-row tiles: 343 vs 367, round 2c) - the two-term pass is bound by
+// board power and its FP64 epilogue, not by L2->SM operand traffic (profiles/r02n_pass_energy_diagnosis.md).
 static int lp_tile_m256() {
   static int v = -1;
   if (v < 0) {

@@ -21,10 +21,13 @@
 //              instruction; the B1 and B2 products accumulate into the same TMEM tile),
 //              tcgen05.commit releases ring slots and publishes finished accumulators
 //   warps 2-9  epilogue: tcgen05.ld (32 lanes x 16 columns per warp and step; two warps share a
-//              lane quarter and split the columns) -> FP64 update on registers -> global; TMEM
-//              accumulators are double buffered so the epilogue of tile i overlaps the MMAs of
-//              tile i+1.  The epilogue moves 42 B of FP64 state per element through HBM, so it
-//              needs as many loads in flight as the MMA issue needs none.
+//              lane quarter and split the columns) -> transpose through shared memory -> FP64
+//              update on registers -> global; TMEM accumulators are double buffered so the epilogue
+//              of tile i overlaps the MMAs of tile i+1.  The epilogue moves 42-46 B of state per
+//              element through HBM and is what bounds the one-term pass (lp_iter.cuh); the two-term
+//              pass is bound by board power (profiles/r02n_pass_energy_diagnosis.md).
+// LpTile<BN, STAGES, MR, TERMS>: TERMS = 2 multiplies (B1 + B2) in every pass, TERMS = 1 only B1 (the
+// second operator term is then delivered every m-th pass by a TERMS = 1 launch over the pending sums).
 #pragma once
 #include <cuda.h>   // CUtensorMap and its enums (types only: the encoder is fetched through cudart)
 #include <cuda_fp16.h>
