@@ -16,14 +16,16 @@ constexpr int OZ_NS = OZ_LMAX + 1;
 #endif
 constexpr int OZ_LMAX_ANCHOR = NNMPC_OZ_LMAX_ANCHOR;   // anchors: 6 levels = 21 products (|Top| <= 1; the result only steers the iteration, the 8-level check certifies; measured: same checks per QP as with 7 levels)
 
-// kernel variant: 2 (default) = 128-column tiles, two level windows; 1 = 64-column tiles, one launch, just-in-time
-// operator slices; 0 = first-generation kernel (64 columns, double-buffered slice sets)
+// kernel variant: 2 (default) = 128-column tiles, two level windows; 3 = the high window on 128-column tiles, the low
+// window (levels 0..3, whose epilogue - partial sums in, functor out - is as long as its 10 products) on 64-column
+// tiles with DOUBLE-BUFFERED accumulators, so that epilogue overlaps the next tile's products; 1 = 64-column tiles, one
+// launch, just-in-time operator slices; 0 = first-generation kernel (64 columns, double-buffered slice sets)
 static int oz_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NNMPC_OZ_VARIANT");
     v = e ? atoi(e) : 2;
-    if (v < 0 || v > 2) v = 2;
+    if (v < 0 || v > 3) v = 2;
   }
   return v;
 }
@@ -198,7 +200,8 @@ static int oz_apply(const OzOperator* op, OzRows* r, int max_rows, const int* co
     e = oz::launch_oz_gemm2<4, LMAX, 128, OzEpiStore>(r->tm, op->tm128, oz::OzShape2{g, nullptr, 0, 1},
                                                       OzEpiStore::Params{r->partial.p, op->nrows}, sms, st);
     if (e == cudaSuccess)
-      e = oz::launch_oz_gemm2<0, 3, 128, Epi>(r->tm, op->tm128, oz::OzShape2{g, r->partial.p, op->nrows, 0}, ep, sms, st);
+      e = var == 3 ? oz::launch_oz_gemm2<0, 3, 64, Epi>(r->tm, op->tm, oz::OzShape2{g, r->partial.p, op->nrows, 0}, ep, sms, st)
+                   : oz::launch_oz_gemm2<0, 3, 128, Epi>(r->tm, op->tm128, oz::OzShape2{g, r->partial.p, op->nrows, 0}, ep, sms, st);
     count_launch(2);
   }
   if (e != cudaSuccess) return set_error(NNMPC_ERR_CUDA, "oz_gemm launch failed: %s", cudaGetErrorString(e));

@@ -1,14 +1,11 @@
 #!/bin/bash
 # The GPU job of the current development step (overwritten per step; results land in gpurun_out/, the ones worth
 # keeping are copied to profiles/).
-# r02ad: final state of round 2 - full GPU suite, default bench line (CPU baseline and e2e included), launch list
+# r02af: last sanity run of the final library: smoke() and the parity / full-size suites
 set -x
 mkdir -p gpurun_out
-T=r02ad
-timeout -k 10 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest.log 2>&1
-tail -3 gpurun_out/${T}_pytest.log | cut -c1-300
-timeout -k 10 900 python bench.py > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err
-tail -c 300 gpurun_out/${T}_bench_default.err; cut -c1-300 gpurun_out/${T}_bench_default.json
-timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12000 -c 4000 --csv --log-file gpurun_out/${T}_launches.csv \
-  python bench.py --traj 16384 --slab 6 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ncu_launches.log 2>&1
-python tools/launch_summary.py gpurun_out/${T}_launches.csv | head -14
+T=r02af
+timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1
+tail -1 gpurun_out/${T}_smoke.log | cut -c1-300
+timeout -k 10 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cdu_fullsize.py -q -x > gpurun_out/${T}_pytest.log 2>&1
+tail -2 gpurun_out/${T}_pytest.log | cut -c1-300
