@@ -99,16 +99,31 @@ struct OzEpiVerify {
     const long long base = pr * p.n;
     const double* lbr = p.lb + pr * p.nu;
     const double* ubr = p.ub + pr * p.nu;
+    // two halves, each: all loads, then the arithmetic and the stores - a load cannot be moved above the store of G of
+    // an earlier column (they may alias), so a column-by-column loop pays one exposed round trip per column
 #pragma unroll
-    for (int k = 0; k < oz::CH; ++k) {
-      const int col = col0 + k;
-      if (col < N) {
-        const int s = col % p.nu;
-        const double z = p.Z[base + col], g = v[k] + p.Ql[base + col];
-        if (p.G) p.G[base + col] = g;
-        double r = fabs(z - fmin(fmax(z - g, lbr[s]), ubr[s]));
-        if (!(r <= 1.7e308)) r = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
-        rmax = fmax(rmax, r);
+    for (int h = 0; h < oz::CH; h += oz::CH / 2) {
+      double z[oz::CH / 2], ql[oz::CH / 2], l[oz::CH / 2], u[oz::CH / 2];
+#pragma unroll
+      for (int k = 0; k < oz::CH / 2; ++k) {
+        const int col = col0 + h + k;
+        const bool in = col < N;
+        const int s = (in ? col : 0) % p.nu;
+        z[k] = in ? p.Z[base + col] : 0.0;
+        ql[k] = in ? p.Ql[base + col] : 0.0;
+        l[k] = lbr[s];
+        u[k] = ubr[s];
+      }
+#pragma unroll
+      for (int k = 0; k < oz::CH / 2; ++k) {
+        const int col = col0 + h + k;
+        if (col < N) {
+          const double g = v[h + k] + ql[k];
+          if (p.G) p.G[base + col] = g;
+          double r = fabs(z[k] - fmin(fmax(z[k] - g, l[k]), u[k]));
+          if (!(r <= 1.7e308)) r = __longlong_as_double(0x7ff0000000000000ll);   // NaN/Inf must not look converged
+          rmax = fmax(rmax, r);
+        }
       }
     }
   }

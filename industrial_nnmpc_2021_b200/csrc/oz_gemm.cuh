@@ -453,6 +453,33 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int c = hsel * CHUNKS; c < (hsel + 1) * CHUNKS; ++c) {
         double v[CH];
+        // what the chunk adds and scales with is requested BEFORE the TMEM loads and the level fold, so that its
+        // latency (the partial sums of the other window come from HBM) is covered by them: with single-buffered
+        // accumulators the epilogue of the low window is as long as its products (round-1 profile: half of the
+        // tile time), and these loads used to be issued at their first use
+        const int colc = bn * BN + c * CH;
+        double pin[CH], es[CH];
+        {
+          // whole chunk inside and an even row pitch of the partial sums: 16-byte loads (colc is a multiple of 16)
+          const bool vec_ok = colc + CH <= g.N && (!g2.partial_in || (g2.ldp & 1) == 0);
+          const bool has_p = g2.partial_in && rok;
+          const double* pp = g2.partial_in + (has_p ? (long long)pos * g2.ldp + colc : 0);
+#pragma unroll
+          for (int k = 0; k < CH; k += 2) {
+            double2 t = make_double2(0.0, 0.0), e2 = make_double2(0.0, 0.0);
+            if (vec_ok) {
+              if (has_p) t = *reinterpret_cast<const double2*>(pp + k);
+              if (!g2.raw_out) e2 = *reinterpret_cast<const double2*>(g.escale + colc + k);
+            } else {
+              if (has_p && colc + k < g.N) t.x = pp[k];
+              if (has_p && colc + k + 1 < g.N) t.y = pp[k + 1];
+              if (!g2.raw_out && colc + k < g.N) e2.x = g.escale[colc + k];
+              if (!g2.raw_out && colc + k + 1 < g.N) e2.y = g.escale[colc + k + 1];
+            }
+            pin[k] = t.x; pin[k + 1] = t.y;
+            es[k] = e2.x; es[k + 1] = e2.y;
+          }
+        }
         if constexpr (NL <= 4) {
           // Fold the levels in 64-bit INTEGER arithmetic (exact: |acc_L| < 2^31, three shifts by 7 bits stay below
           // 2^53) and convert once: one I2F + one multiply per element on the FP64 pipe instead of a convert, an add
@@ -487,12 +514,11 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < CH; ++k) v[k] *= lev0;                 // sum_L acc_L 128^-(L+2)
         }
-        const int col0 = bn * BN + c * CH;
+        const int col0 = colc;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-          const int col = col0 + k;
-          if (g2.partial_in && rok && col < g.N) v[k] += g2.partial_in[(long long)pos * g2.ldp + col];
-          if (!g2.raw_out) v[k] *= fs * (col < g.N ? g.escale[col] : 0.0);
+          v[k] += pin[k];                              // 0 where there is no partial sum (or the column is outside)
+          if (!g2.raw_out) v[k] *= fs * es[k];         // es = 0 outside N
         }
         if (rok) epi.chunk(col0, v, g.N);
       }
