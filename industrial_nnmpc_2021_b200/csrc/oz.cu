@@ -60,15 +60,20 @@ struct OzEpiAnchor {
   __device__ explicit OzEpiAnchor(const Params& p_) : p(p_), base(0) {}
   __device__ void begin_row(int pos, bool ok) { base = ok ? (long long)(p.rows ? p.rows[pos] : pos) * p.n : 0; }
   __device__ void chunk(int col0, const double (&v)[oz::CH], int N) {
+    // all loads of C first: a load cannot be moved above the store of X of an earlier column pair (they may alias)
+    double2 c[oz::CH / 2];
 #pragma unroll
     for (int k = 0; k < oz::CH; k += 2) {
       const int col = col0 + k;
-      if (col + 1 < N) {
-        const double2 c = *reinterpret_cast<const double2*>(p.C + base + col);
-        *reinterpret_cast<double2*>(p.X + base + col) = make_double2(v[k] - c.x, v[k + 1] - c.y);
-      } else if (col < N) {
-        p.X[base + col] = v[k] - p.C[base + col];
-      }
+      c[k / 2] = make_double2(0.0, 0.0);
+      if (col + 1 < N) c[k / 2] = *reinterpret_cast<const double2*>(p.C + base + col);
+      else if (col < N) c[k / 2].x = p.C[base + col];
+    }
+#pragma unroll
+    for (int k = 0; k < oz::CH; k += 2) {
+      const int col = col0 + k;
+      if (col + 1 < N) *reinterpret_cast<double2*>(p.X + base + col) = make_double2(v[k] - c[k / 2].x, v[k + 1] - c[k / 2].y);
+      else if (col < N) p.X[base + col] = v[k] - c[k / 2].x;
     }
   }
   __device__ void end_row() {}
